@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the stencil-sweep + ghost-exchange path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], SURVEY §8d "C2"): a 512^3 level split into 64^3 boxes, 1 ghost
+cell, fully periodic, double precision, hash-initialised; ONE STEP = 100 x { ghost exchange ;
+7-point Jacobi/heat sweep } with ping-pong levels.  With N > 1 GPUs (torchrun, one rank per GPU) the
+domain is 512 x 512 x 512*N cut into z-slabs by the reference's ownership rule (weak scaling,
+configs[4]); the halo travels by NCCL send/recv and overlaps the interior boxes.
+
+One JSON line on rank 0: metric = Gcell-updates/s (whole job), plus `roofline` (the sweep kernel
+against the measured HBM copy bandwidth, 16 algorithmic bytes per cell-update), `cpu_baseline`
+(the reference's own CPU code, oracle/_ref, timed on this host on a bounded sample), `e2e` (same
+job through the C ABI with HOST buffers: H2D + 100 sweeps + D2H per step), `clocks`, `gpu_launches`.
+
+`--impl reference` times the reference's CPU implementation (oracle/_ref/libsgcref*.so, compiled
+from /root/reference in the build container; falls back to the oracle port) on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_CELL = 16.0      # read u once + write unew once, double
+FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sweeps", type=int, default=100, help="sweeps per step (config: 100)")
+    ap.add_argument("--domain", type=int, default=512, help="cells per side per GPU")
+    ap.add_argument("--box", type=int, default=64)
+    ap.add_argument("--f", type=float, default=0.125)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sweeps", type=int, default=12, help="sweeps of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def hash_field(lo, n):
+    """SURVEY §8c seedless dyadic init on the box [lo, lo+n): values k/1024."""
+    i = (np.arange(lo[0], lo[0] + n[0], dtype=np.uint32) * np.uint32(73856093))[None, None, :]
+    j = (np.arange(lo[1], lo[1] + n[1], dtype=np.uint32) * np.uint32(19349663))[None, :, None]
+    k = (np.arange(lo[2], lo[2] + n[2], dtype=np.uint32) * np.uint32(83492791))[:, None, None]
+    return ((i ^ j ^ k) % np.uint32(1024)).astype(np.float64) / 1024.0
+
+
+def fill_level_host(host, boxes, ng):
+    off = 0
+    for b in boxes:
+        n = b[3:] - b[:3] + 1
+        m = n + 2 * ng
+        f = host[off:off + int(np.prod(m))].reshape(m[2], m[1], m[0])
+        f[...] = 0.0
+        f[ng:ng + n[2], ng:ng + n[1], ng:ng + n[0]] = hash_field(b[:3], n)
+        off += int(np.prod(m))
+    return host
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 8] or [r for (_, r) in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(domain, box, f, sweeps, threads_mode="best"):
+    """Time the reference's CPU implementation (kind "reference": oracle/_ref built from
+    /root/reference; else kind "port": the oracle) on `sweeps` x {exchange; sweep} of the
+    domain^3 level.  Returns dict(value Gcell/s, cores, kind, ms split)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    O = po.Oracle()
+    dlo, dhi, mb = (0, 0, 0), (domain - 1,) * 3, (box,) * 3
+    boxes, _, _ = O.layout(dlo, dhi, mb)
+    u0 = np.empty(O.level_size(boxes, 1, 1))
+    fill_level_host(u0, boxes, 1)
+    cells = float(domain) ** 3
+    runs = []
+    if po.have_reference(""):
+        variants = [("", 1)]
+        if po.have_reference("_omp") and threads_mode == "best":
+            variants.append(("_omp", os.cpu_count() or 1))
+        for variant, cores in variants:
+            if variant == "_omp":
+                os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+            R = po.Reference(variant)
+            u = u0.copy()
+            t0 = time.time()
+            _, tm = R.level_heat(dlo, dhi, mb, 1, 7, 0, f, sweeps, u)
+            wall = time.time() - t0
+            ms = float(tm[1] + tm[2])
+            runs.append(dict(kind="reference", variant=variant or "serial", cores=R.threads() if variant == "_omp" else 1,
+                             ms=ms, exchange_ms=float(tm[1]), sweep_ms=float(tm[2]), plan_ms=float(tm[0]), wall_s=wall,
+                             value=cells * sweeps / (ms * 1e-3) / 1e9))
+    else:
+        u = u0.copy()
+        _, tm = O.level_heat(dlo, dhi, mb, 1, 7, 0, f, sweeps, u, 1)
+        ms = float(tm[1] + tm[2])
+        runs.append(dict(kind="port", variant="oracle", cores=1, ms=ms, exchange_ms=float(tm[1]), sweep_ms=float(tm[2]),
+                         plan_ms=float(tm[0]), wall_s=0.0, value=cells * sweeps / (ms * 1e-3) / 1e9))
+    return runs
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: each step = `cpu_sweeps` sweeps of the full per-GPU level
+    sample_sweeps = max(1, min(a.cpu_sweeps, a.sweeps))
+    probe = cpu_reference_run(a.domain, a.box, a.f, 1)
+    best = max(probe, key=lambda r: r["value"])
+    mode = "best" if best["variant"] == "_omp" else "serial"
+    vals, split = [], None
+    for s in range(a.warmup + a.steps):
+        runs = cpu_reference_run(a.domain, a.box, a.f, sample_sweeps, threads_mode=mode)
+        r = max(runs, key=lambda r: r["value"]) if mode == "best" else runs[0]
+        if s >= a.warmup:
+            vals.append(r)
+            split = r
+    ms = float(np.mean([r["ms"] for r in vals])) * (a.sweeps / sample_sweeps)
+    value = float(a.domain) ** 3 * a.sweeps / (ms * 1e-3) / 1e9
+    sample = "%d of %d sweeps per step on the full %d^3 level in %d^3 boxes (exchange+sweep, Stopwatch)" % (
+        sample_sweeps, a.sweeps, a.domain, a.box)
+    line = {
+        "impl": "reference", "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, 1),
+        "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": split["cores"], "kind": split["kind"],
+                         "variant": split["variant"], "sample": sample, "exchange_ms_per_sweep": split["exchange_ms"] / sample_sweeps,
+                         "sweep_ms_per_sweep": split["sweep_ms"] / sample_sweeps, "probe": probe},
+        "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, n):
+    return {"workload": "C2: %dx%dx%d level in %d^3 boxes, 1 ghost, periodic xyz, %d x {exchange; 7-pt heat sweep} per step"
+                        % (a.domain, a.domain, a.domain * n, a.box, a.sweeps),
+            "domain": [a.domain, a.domain, a.domain * n], "box": a.box, "nghost": 1, "ncomp": 1,
+            "sweeps_per_step": a.sweeps, "f": a.f, "periodic": "xyz", "partition": "z-slabs, owner = idx/(nbox/N)",
+            "l2_policy": "inputs larger than L2 (2 x %.2f GB per GPU)" % (((a.domain // a.box) ** 3) * (a.box + 2) ** 3 * 8 / 1e9)}
+
+
+# ------------------------------------------------------------------------------ our arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
+    n_gpus = world
+
+    from _loadpkg import load_package
+    sgc = load_package()
+    sgc.init(local_rank)
+    if world > 1:
+        ids = [sgc.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sgc.comm_init(world, rank, ids[0])
+
+    dom = sgc.Box((0, 0, 0), (a.domain - 1, a.domain - 1, a.domain * world - 1))
+    dbl = sgc.DisjointBoxLayout(dom, a.box, world, rank)
+    A = sgc.LevelData(dbl, 1, 1)
+    B = sgc.LevelData(dbl, 1, 1)
+    cells_local = float(a.domain) ** 3
+    cells_total = cells_local * world
+
+    pin_in = sgc.PinnedBuffer(A.elems)
+    pin_out = sgc.PinnedBuffer(A.elems)
+    fill_level_host(pin_in.array, dbl.local_boxes(), 1)
+    A.upload(pin_in.array)
+    B.upload(pin_in.array)
+    t0 = time.time()
+    cp = sgc.Copier().defineExchangeLD(A, 7, 0)
+    plan_ms = (time.time() - t0) * 1e3
+    sum0 = None
+
+    def barrier():
+        sgc.sync()
+        if dist is not None:
+            dist.barrier()
+        sgc.sync()
+
+    cur, oth = A, B
+
+    def step():
+        nonlocal cur, oth
+        res = sgc.heat_run(cur, oth, cp, a.f, a.sweeps)
+        if res is not cur:
+            cur, oth = oth, cur
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    sgc.profile_enable(True)
+    sgc.profile_read(0), sgc.profile_read(1)
+    launches0 = sgc.launch_count()
+    e0, e1 = sgc.Event(), sgc.Event()
+    barrier()
+    tw0 = time.time()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    tw1 = time.time()
+    ms_total = e0.elapsed_ms(e1)
+    launches = sgc.launch_count() - launches0
+    sweep_n, sweep_ms = sgc.profile_read(0)
+    exch_n, exch_ms = sgc.profile_read(1)
+    sgc.profile_enable(False)
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_total], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t[0])
+    ms_per_step = ms_total / a.steps
+    value = cells_total * a.sweeps / (ms_per_step * 1e-3) / 1e9
+
+    # conservation check of the device result (periodic heat equation conserves the sum)
+    out = cur.download(out=pin_out.array)
+    mask_sum = 0.0
+    off = 0
+    m = a.box + 2
+    for _ in range(A.size()):
+        mask_sum += float(out[off:off + m ** 3].reshape(m, m, m)[1:-1, 1:-1, 1:-1].sum())
+        off += m ** 3
+    ref_sum = 0.0
+    off = 0
+    for _ in range(A.size()):
+        ref_sum += float(pin_in.array[off:off + m ** 3].reshape(m, m, m)[1:-1, 1:-1, 1:-1].sum())
+        off += m ** 3
+    conserved = abs(mask_sum - ref_sum) <= 1e-9 * abs(ref_sum)
+
+    # roofline of the dominant kernel (the sweep): algorithmic bytes per launch / mean launch time
+    peak, peak_src = measured_hbm_peak()
+    # with N > 1 a step issues 2-3 sweep launches (interior + boundary ranges): use bytes per sweep
+    sweeps_done = a.steps * a.sweeps
+    sweep_ms_per_sweep = sweep_ms / max(sweeps_done, 1)
+    achieved = cells_local * ALGO_BYTES_PER_CELL / (sweep_ms_per_sweep * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "heat sweep (class 0)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": load_traffic(),
+                "algorithmic_bytes_per_launch": cells_local * ALGO_BYTES_PER_CELL,
+                "avg_launch_ms": sweep_ms / max(sweep_n, 1), "launches_timed": sweep_n,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
+                "sweep_only_gcells": cells_local / (sweep_ms_per_sweep * 1e-3) / 1e9 if sweep_ms > 0 else 0.0,
+                "exchange_ms_per_sweep": exch_ms / max(sweeps_done, 1), "sweep_ms_per_sweep": sweep_ms_per_sweep,
+                "exchange_bytes_per_sweep": 16.0 * cp.numCells()}
+
+    # e2e: the same job through the C ABI with HOST buffers (pinned): H2D + sweeps + D2H per step
+    e2e_ms = []
+    for s in range(a.e2e_steps + 1):
+        barrier()
+        ea, eb = sgc.Event(), sgc.Event()
+        ea.record()
+        A.upload(pin_in.array, wait=False)
+        B.upload(pin_in.array, wait=False)     # both ping-pong levels start from the host state (BC ghosts)
+        res = sgc.heat_run(A, B, cp, a.f, a.sweeps)
+        res.download(out=pin_out.array)
+        eb.record()
+        sgc.sync()
+        if s > 0:
+            e2e_ms.append(ea.elapsed_ms(eb))
+    e2e_t = float(np.mean(e2e_ms)) if e2e_ms else float("nan")
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_t], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t[0])
+    e2e = {"value": cells_total * a.sweeps / (e2e_t * 1e-3) / 1e9, "unit": "Gcell-updates/s",
+           "h2d_bytes_per_step": int(2 * A.elems * 8), "d2h_bytes_per_step": int(A.elems * 8), "ms_per_step": e2e_t,
+           "call": "sgc_level_upload x2 + sgc_heat_run(%d sweeps) + sgc_level_download, pinned host buffers" % a.sweeps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            runs = cpu_reference_run(a.domain, a.box, a.f, a.cpu_sweeps)
+            best = max(runs, key=lambda r: r["value"])
+            cpu = {"value": best["value"], "unit": "Gcell-updates/s", "cores": best["cores"], "kind": best["kind"],
+                   "variant": best["variant"],
+                   "sample": "%d sweeps (of %d per step) of the full %d^3 level in %d^3 boxes, exchange+sweep" % (
+                       a.cpu_sweeps, a.sweeps, a.domain, a.box),
+                   "exchange_ms_per_sweep": best["exchange_ms"] / a.cpu_sweeps, "sweep_ms_per_sweep": best["sweep_ms"] / a.cpu_sweeps,
+                   "host_cores_available": os.cpu_count(), "all_variants": runs}
+        except Exception as ex:   # the baseline must never take the GPU number down with it
+            cpu = {"value": None, "error": repr(ex)}
+
+    if rank == 0:
+        name, sms, mem = sgc.device_info()
+        line = {"metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": n_gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(a, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "clocks": clocks, "gpu_launches": int(launches), "device": name, "sm_count": sms,
+                "plan_build_ms": plan_ms, "motion_items": cp.numMotionItem(), "remote_items": cp.numRemoteItem(),
+                "sum_conserved": bool(conserved)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        sgc.comm_finalize()
+        dist.destroy_process_group()
+
+
+def load_traffic():
+    """dram bytes per sweep launch from the last committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("sweep_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    main()

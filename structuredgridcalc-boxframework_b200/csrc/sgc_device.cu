@@ -1,0 +1,730 @@
+// sgc_device.cu — runtime, device-resident level data, exchange plans and the C ABI entry points
+// of include/sgc_b200.h (everything except the host-only layout/plan builders in sgc_plan.cpp and
+// the multi-rank transport in sgc_comm.cu).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "sgc_device.h"
+
+namespace sgc {
+
+Runtime& rt() {
+  static Runtime r;
+  return r;
+}
+
+// kernels / launchers (sgc_kernels.cu, sgc_stream.cu)
+int launch_heat_generic(const int*, int, int, const FabGeom*, const FabGeom*, const double*, double*, double, int,
+                        cudaStream_t);
+int launch_lap_generic(const int*, int, int, const FabGeom*, const FabGeom*, const double*, double*, double, int, int,
+                       cudaStream_t);
+int launch_wave_generic(const int*, int, int, const FabGeom*, const FabGeom*, const double*, double*, const double*,
+                        double, int, cudaStream_t);
+int sweep_tile_y();
+int sweep_tile_z();
+// streaming sweep (returns 1 when it does not apply to this geometry, 0 when launched, <0 on error)
+int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int box_begin, int box_end,
+                       cudaStream_t s);
+// multi-rank transport (sgc_comm.cu)
+int comm_plan_setup(sgc_plan_s* plan, sgc_level_s* level, const Grid& g, unsigned periodic, unsigned trim);
+void comm_plan_release(sgc_plan_s* plan);
+int comm_exchange_begin(sgc_level_s* level, sgc_plan_s* plan);
+int comm_exchange_end(sgc_level_s* level, sgc_plan_s* plan);
+
+ProfScope::ProfScope(int klass_, cudaStream_t s_) : klass(klass_), s(s_), slot(-1) {
+  Runtime& r = rt();
+  if (!r.profiling) return;
+  ProfLog& L = r.prof[klass];
+  if (L.used >= 8192) return;
+  if (L.used == (int)L.a.size()) {
+    cudaEvent_t ea, eb;
+    if (cudaEventCreate(&ea) != cudaSuccess || cudaEventCreate(&eb) != cudaSuccess) return;
+    L.a.push_back(ea); L.b.push_back(eb);
+  }
+  slot = L.used++;
+  cudaEventRecord(L.a[slot], s);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(rt().prof[klass].b[slot], s);
+}
+
+void CopyTable::release() {
+  if (d_items) cudaFree(d_items);
+  if (d_cell_start) cudaFree(d_cell_start);
+  if (d_chunk_first) cudaFree(d_chunk_first);
+  d_items = nullptr; d_cell_start = nullptr; d_chunk_first = nullptr;
+  nitem = nchunk = 0; ncell = 0;
+}
+
+int CopyTable::upload(const std::vector<CopyItem>& items) {
+  release();
+  nitem = (int)items.size();
+  if (nitem == 0) return 0;
+  std::vector<long long> start(nitem + 1);
+  start[0] = 0;
+  for (int i = 0; i < nitem; ++i)
+    start[i + 1] = start[i] + (long long)items[i].nx * items[i].ny * items[i].nz * items[i].nc;
+  ncell = start[nitem];
+  nchunk = (int)((ncell + kCopyChunk - 1) / kCopyChunk);
+  std::vector<int> first(nchunk + 1);
+  int it = 0;
+  for (int c = 0; c < nchunk; ++c) {
+    const long long cell = (long long)c * kCopyChunk;
+    while (it + 1 < nitem && start[it + 1] <= cell) ++it;
+    first[c] = it;
+  }
+  first[nchunk] = nitem - 1;
+  SGC_CUDA(cudaMalloc(&d_items, sizeof(CopyItem) * (size_t)nitem));
+  SGC_CUDA(cudaMalloc(&d_cell_start, sizeof(long long) * (size_t)(nitem + 1)));
+  SGC_CUDA(cudaMalloc(&d_chunk_first, sizeof(int) * (size_t)(nchunk + 1)));
+  SGC_CUDA(cudaMemcpy(d_items, items.data(), sizeof(CopyItem) * (size_t)nitem, cudaMemcpyHostToDevice));
+  SGC_CUDA(cudaMemcpy(d_cell_start, start.data(), sizeof(long long) * (size_t)(nitem + 1), cudaMemcpyHostToDevice));
+  SGC_CUDA(cudaMemcpy(d_chunk_first, first.data(), sizeof(int) * (size_t)(nchunk + 1), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Region-copy descriptor between two fabs (both described by their FabGeom).
+static CopyItem make_item(const FabGeom& gd, const IBox& dreg, int dcomp, const FabGeom& gs, const IBox& sreg, int scomp,
+                          int nc, unsigned flags) {
+  CopyItem c;
+  c.nx = dreg.ext(0); c.ny = dreg.ext(1); c.nz = dreg.ext(2); c.nc = nc;
+  c.dsy = gd.n[0]; c.dsz = gd.n[0] * gd.n[1]; c.dcs = gd.cs;
+  c.ssy = gs.n[0]; c.ssz = gs.n[0] * gs.n[1]; c.scs = gs.cs;
+  c.dst = gd.off + dcomp * gd.cs + (dreg.lo[0] - gd.lo[0]) + (long long)(dreg.lo[1] - gd.lo[1]) * c.dsy +
+          (long long)(dreg.lo[2] - gd.lo[2]) * c.dsz;
+  c.src = gs.off + scomp * gs.cs + (sreg.lo[0] - gs.lo[0]) + (long long)(sreg.lo[1] - gs.lo[1]) * c.ssy +
+          (long long)(sreg.lo[2] - gs.lo[2]) * c.ssz;
+  c.flags = flags;
+  c.c0 = dcomp;
+  return c;
+}
+
+// A dense buffer holding `reg` for nc components in wire order comp->k->j->i, starting at element `off`.
+static FabGeom dense_geom(const IBox& reg, long long off) {
+  FabGeom g;
+  g.off = off;
+  for (int d = 0; d < 3; ++d) { g.lo[d] = reg.lo[d]; g.n[d] = reg.ext(d); g.vlo[d] = reg.lo[d]; g.vn[d] = reg.ext(d); }
+  g.cs = reg.size();
+  return g;
+}
+
+static bool fab_contains(const FabGeom& g, const IBox& r) {
+  for (int d = 0; d < 3; ++d)
+    if (r.lo[d] < g.lo[d] || r.hi[d] >= g.lo[d] + g.n[d]) return false;
+  return true;
+}
+
+static bool same_geometry(const sgc_level_s* a, const sgc_level_s* b) {
+  if (a->nbox != b->nbox || a->ncomp != b->ncomp || a->ng != b->ng || a->esz != b->esz) return false;
+  for (int i = 0; i < a->nbox; ++i)
+    if (memcmp(&a->boxes[i], &b->boxes[i], sizeof(IBox)) != 0) return false;
+  return true;
+}
+
+static bool same_layout(const sgc_level_s* a, const sgc_level_s* b) {
+  if (a->nbox != b->nbox) return false;
+  for (int i = 0; i < a->nbox; ++i)
+    if (memcmp(&a->boxes[i], &b->boxes[i], sizeof(IBox)) != 0) return false;
+  return true;
+}
+
+static bool plan_matches(const sgc_plan_s* p, const sgc_level_s* l) {
+  if (p->nbox != l->nbox || p->ncomp != l->ncomp || p->ng != l->ng || p->esz != l->esz) return false;
+  for (int i = 0; i < l->nbox; ++i)
+    if (memcmp(&p->boxes[i], &l->boxes[i], sizeof(IBox)) != 0) return false;
+  return true;
+}
+
+static int ensure_scratch(sgc_level_s* l, size_t bytes) {
+  if (l->scratch_bytes >= bytes) return 0;
+  if (l->d_scratch) cudaFree(l->d_scratch);
+  l->d_scratch = nullptr; l->scratch_bytes = 0;
+  SGC_CUDA(cudaMalloc(&l->d_scratch, bytes));
+  l->scratch_bytes = bytes;
+  return 0;
+}
+
+}  // namespace sgc
+
+using namespace sgc;
+
+extern "C" {
+
+// ------------------------------------------------------------------------------- runtime
+int sgc_init(int device) {
+  Runtime& r = rt();
+  if (r.ready && r.device == device) return 0;
+  if (r.ready) return fail(SGC_ERR_ARG, "sgc_init: already bound to another device");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(SGC_ERR_CUDA, std::string("sgc_init: no CUDA device (") + cudaGetErrorString(e) +
+                                  "); this library has no CPU fallback");
+  if (device < 0 || device >= n) return fail(SGC_ERR_ARG, "sgc_init: device index out of range");
+  SGC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp p;
+  SGC_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major < 10)
+    return fail(SGC_ERR_UNSUPPORTED, "sgc_init: kernels are built for sm_100a only; device is sm_" +
+                                         std::to_string(p.major) + std::to_string(p.minor));
+  r.sm_count = p.multiProcessorCount;
+  SGC_CUDA(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking));
+  SGC_CUDA(cudaStreamCreateWithFlags(&r.comm, cudaStreamNonBlocking));
+  r.device = device;
+  r.launches = 0;
+  r.ready = true;
+  return 0;
+}
+
+int sgc_shutdown(void) {
+  Runtime& r = rt();
+  if (!r.ready) return 0;
+  cudaDeviceSynchronize();
+  if (r.compute) cudaStreamDestroy(r.compute);
+  if (r.comm) cudaStreamDestroy(r.comm);
+  r = Runtime();
+  return 0;
+}
+
+int sgc_device_info(char* name, int cap, int* sm_count, size_t* hbm_bytes) {
+  SGC_REQUIRE_RT();
+  cudaDeviceProp p;
+  SGC_CUDA(cudaGetDeviceProperties(&p, rt().device));
+  if (name && cap > 0) { strncpy(name, p.name, cap - 1); name[cap - 1] = 0; }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
+  return 0;
+}
+
+int sgc_sync(void) {
+  SGC_REQUIRE_RT();
+  SGC_CUDA(cudaStreamSynchronize(rt().compute));
+  SGC_CUDA(cudaStreamSynchronize(rt().comm));
+  return 0;
+}
+
+long long sgc_launch_count(void) { return rt().launches; }
+
+int sgc_profile_enable(int on) {
+  SGC_REQUIRE_RT();
+  rt().profiling = on != 0;
+  return 0;
+}
+
+int sgc_profile_read(int klass, int* launches, double* total_ms) {
+  SGC_REQUIRE_RT();
+  if (klass < 0 || klass > 1) return fail(SGC_ERR_ARG, "sgc_profile_read: class must be 0 or 1");
+  ProfLog& L = rt().prof[klass];
+  double sum = 0;
+  for (int i = 0; i < L.used; ++i) {
+    float ms = 0;
+    SGC_CUDA(cudaEventSynchronize(L.b[i]));
+    SGC_CUDA(cudaEventElapsedTime(&ms, L.a[i], L.b[i]));
+    sum += ms;
+  }
+  if (launches) *launches = L.used;
+  if (total_ms) *total_ms = sum;
+  L.used = 0;
+  return 0;
+}
+
+int sgc_event_create(sgc_event_t* ev) {
+  SGC_REQUIRE_RT();
+  if (!ev) return fail(SGC_ERR_ARG, "null event");
+  sgc_event_s* e = new sgc_event_s;
+  cudaError_t st = cudaEventCreate(&e->ev);
+  if (st != cudaSuccess) { delete e; return fail(SGC_ERR_CUDA, cudaGetErrorString(st)); }
+  *ev = e;
+  return 0;
+}
+int sgc_event_destroy(sgc_event_t ev) {
+  if (!ev) return 0;
+  cudaEventDestroy(ev->ev);
+  delete ev;
+  return 0;
+}
+int sgc_event_record(sgc_event_t ev) {
+  SGC_REQUIRE_RT();
+  if (!ev) return fail(SGC_ERR_ARG, "null event");
+  SGC_CUDA(cudaEventRecord(ev->ev, rt().compute));
+  return 0;
+}
+int sgc_event_elapsed_ms(sgc_event_t start, sgc_event_t stop, float* ms) {
+  SGC_REQUIRE_RT();
+  if (!start || !stop || !ms) return fail(SGC_ERR_ARG, "null event");
+  SGC_CUDA(cudaEventSynchronize(stop->ev));
+  SGC_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+  return 0;
+}
+
+int sgc_host_alloc(size_t bytes, void** ptr) {
+  SGC_REQUIRE_RT();
+  if (!ptr) return fail(SGC_ERR_ARG, "null pointer");
+  SGC_CUDA(cudaMallocHost(ptr, bytes));
+  return 0;
+}
+int sgc_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- level data
+int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int elem_bytes, int global_index0,
+                     sgc_level_t* level) {
+  SGC_REQUIRE_RT();
+  if (!boxes6 || !level || nbox < 1 || ncomp < 1 || nghost < 0)
+    return fail(SGC_ERR_ARG, "sgc_level_create: bad argument");
+  if (elem_bytes != 8 && elem_bytes != 4 && elem_bytes != 1)
+    return fail(SGC_ERR_UNSUPPORTED, "sgc_level_create: elem_bytes must be 8, 4 or 1");
+  sgc_level_s* l = new sgc_level_s;
+  l->nbox = nbox; l->ncomp = ncomp; l->ng = nghost; l->esz = elem_bytes; l->gidx0 = global_index0;
+  l->boxes.resize(nbox); l->off.resize(nbox); l->geom.resize(nbox);
+  long long off = 0;
+  for (int b = 0; b < nbox; ++b) {
+    const IBox v = IBox::from6(boxes6 + 6 * b);
+    if (v.empty()) { delete l; return fail(SGC_ERR_ARG, "sgc_level_create: empty box"); }
+    const IBox f = v.grown(nghost);
+    l->boxes[b] = v;
+    l->off[b] = off;
+    FabGeom& g = l->geom[b];
+    g.off = off; g.cs = f.size();
+    for (int d = 0; d < 3; ++d) { g.lo[d] = f.lo[d]; g.n[d] = f.ext(d); g.vlo[d] = v.lo[d]; g.vn[d] = v.ext(d); }
+    if (g.cs * ncomp > 0x7fffffffLL) {   // the reference indexes with int; we keep its limit per fab
+      delete l;
+      return fail(SGC_ERR_UNSUPPORTED, "sgc_level_create: a single fab exceeds 2^31 elements");
+    }
+    if (b && memcmp(l->geom[0].n, g.n, sizeof g.n) != 0) l->uniform = false;
+    off += g.cs * ncomp;
+  }
+  l->elems = off;
+  // Arena: fabs exactly contiguous in box order (whole-level H2D/D2H is one memcpy and the
+  // streaming sweep sees one uniform plane sequence).  `lead` elements of padding in front so
+  // that (a) aligned-down bulk loads never leave the allocation and (b) for 8-byte elements the
+  // first valid cell of every row of fab 0 is 16-byte aligned when the pitch allows it.
+  const FabGeom& g0 = l->geom[0];
+  const long long first_valid = (long long)nghost * (1 + g0.n[0] + (long long)g0.n[0] * g0.n[1]);
+  l->lead = 32 + ((first_valid & 1) ? 1 : 0);
+  const size_t bytes = (size_t)(l->lead + l->elems + 64) * elem_bytes;
+  cudaError_t e = cudaMalloc(&l->d_base, bytes);
+  if (e != cudaSuccess) { delete l; return fail(SGC_ERR_CUDA, std::string("cudaMalloc level arena: ") + cudaGetErrorString(e)); }
+  cudaMemsetAsync(l->d_base, 0, bytes, rt().compute);
+  l->d_arena = (char*)l->d_base + l->lead * elem_bytes;
+  e = cudaMalloc(&l->d_geom, sizeof(FabGeom) * (size_t)nbox);
+  if (e == cudaSuccess) e = cudaMemcpy(l->d_geom, l->geom.data(), sizeof(FabGeom) * (size_t)nbox, cudaMemcpyHostToDevice);
+  // sweep work table for the generic kernel: (box, y0, z0) tiles of the valid region
+  std::vector<int> work;
+  l->work_begin.resize(nbox + 1);
+  const int ty = sweep_tile_y(), tz = sweep_tile_z();
+  for (int b = 0; b < nbox; ++b) {
+    l->work_begin[b] = (int)(work.size() / 3);
+    for (int z = 0; z < l->geom[b].vn[2]; z += tz)
+      for (int y = 0; y < l->geom[b].vn[1]; y += ty) { work.push_back(b); work.push_back(y); work.push_back(z); }
+  }
+  l->nwork = (int)(work.size() / 3);
+  l->work_begin[nbox] = l->nwork;
+  if (e == cudaSuccess) e = cudaMalloc(&l->d_work, sizeof(int) * work.size());
+  if (e == cudaSuccess) e = cudaMemcpy(l->d_work, work.data(), sizeof(int) * work.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    sgc_level_destroy(l);
+    return fail(SGC_ERR_CUDA, std::string("sgc_level_create: ") + cudaGetErrorString(e));
+  }
+  *level = l;
+  return 0;
+}
+
+int sgc_level_destroy(sgc_level_t l) {
+  if (!l) return 0;
+  if (rt().ready) cudaStreamSynchronize(rt().compute);
+  if (l->d_base) cudaFree(l->d_base);
+  if (l->d_geom) cudaFree(l->d_geom);
+  if (l->d_work) cudaFree(l->d_work);
+  if (l->d_scratch) cudaFree(l->d_scratch);
+  delete l;
+  return 0;
+}
+
+long long sgc_level_elems(sgc_level_t l) { return l ? l->elems : -1; }
+long long sgc_level_fab_offset(sgc_level_t l, int box) {
+  if (!l || box < 0 || box >= l->nbox) return -1;
+  return l->off[box];
+}
+void* sgc_level_device_ptr(sgc_level_t l, int box) {
+  if (!l || box < 0 || box >= l->nbox) return nullptr;
+  return (char*)l->d_arena + l->off[box] * l->esz;
+}
+
+int sgc_level_upload(sgc_level_t l, int box, const void* host) {
+  SGC_REQUIRE_RT();
+  if (!l || !host || box < -1 || box >= l->nbox) return fail(SGC_ERR_ARG, "sgc_level_upload: bad argument");
+  if (box < 0) {
+    SGC_CUDA(cudaMemcpyAsync(l->d_arena, host, (size_t)l->elems * l->esz, cudaMemcpyHostToDevice, rt().compute));
+  } else {
+    SGC_CUDA(cudaMemcpyAsync((char*)l->d_arena + l->off[box] * l->esz, host,
+                             (size_t)l->geom[box].cs * l->ncomp * l->esz, cudaMemcpyHostToDevice, rt().compute));
+  }
+  return 0;
+}
+
+int sgc_level_download(sgc_level_t l, int box, void* host) {
+  SGC_REQUIRE_RT();
+  if (!l || !host || box < -1 || box >= l->nbox) return fail(SGC_ERR_ARG, "sgc_level_download: bad argument");
+  if (box < 0) {
+    SGC_CUDA(cudaMemcpyAsync(host, l->d_arena, (size_t)l->elems * l->esz, cudaMemcpyDeviceToHost, rt().compute));
+  } else {
+    SGC_CUDA(cudaMemcpyAsync(host, (char*)l->d_arena + l->off[box] * l->esz,
+                             (size_t)l->geom[box].cs * l->ncomp * l->esz, cudaMemcpyDeviceToHost, rt().compute));
+  }
+  SGC_CUDA(cudaStreamSynchronize(rt().compute));
+  return 0;
+}
+
+int sgc_level_setval(sgc_level_t l, int box, int comp, const void* value) {
+  SGC_REQUIRE_RT();
+  if (!l || !value || box < -1 || box >= l->nbox || comp < -1 || comp >= l->ncomp)
+    return fail(SGC_ERR_ARG, "sgc_level_setval: bad argument");
+  if (comp < 0) {
+    if (box < 0) return launch_fill(l->d_arena, l->elems, l->esz, value, rt().compute);
+    return launch_fill((char*)l->d_arena + l->off[box] * l->esz, l->geom[box].cs * l->ncomp, l->esz, value, rt().compute);
+  }
+  const int b0 = box < 0 ? 0 : box, b1 = box < 0 ? l->nbox : box + 1;
+  for (int b = b0; b < b1; ++b) {
+    const int st = launch_fill((char*)l->d_arena + (l->off[b] + comp * l->geom[b].cs) * l->esz, l->geom[b].cs, l->esz,
+                               value, rt().compute);
+    if (st) return st;
+  }
+  return 0;
+}
+
+int sgc_fab_copy(sgc_level_t dst, int dst_box, const int dlo[3], const int dhi[3], int dst_comp, sgc_level_t src,
+                 int src_box, const int slo[3], const int shi[3], int src_comp, int ncomp, unsigned comp_flags) {
+  SGC_REQUIRE_RT();
+  if (!dst || !src || !dlo || !dhi || !slo || !shi) return fail(SGC_ERR_ARG, "sgc_fab_copy: null argument");
+  if (dst_box < 0 || dst_box >= dst->nbox || src_box < 0 || src_box >= src->nbox)
+    return fail(SGC_ERR_ARG, "sgc_fab_copy: box index out of range");
+  if (dst->esz != src->esz) return fail(SGC_ERR_ARG, "sgc_fab_copy: element types differ");
+  IBox dr, sr;
+  for (int d = 0; d < 3; ++d) { dr.lo[d] = dlo[d]; dr.hi[d] = dhi[d]; sr.lo[d] = slo[d]; sr.hi[d] = shi[d]; }
+  const FabGeom& gd = dst->geom[dst_box];
+  const FabGeom& gs = src->geom[src_box];
+  // the reference asserts these (BaseFab.cpp:306-312)
+  if (dr.empty() || dr.ext(0) != sr.ext(0) || dr.ext(1) != sr.ext(1) || dr.ext(2) != sr.ext(2))
+    return fail(SGC_ERR_ARG, "sgc_fab_copy: regions must be non-empty and of equal extents");
+  if (!fab_contains(gd, dr) || !fab_contains(gs, sr)) return fail(SGC_ERR_ARG, "sgc_fab_copy: region outside fab");
+  if (dst_comp < 0 || src_comp < 0 || ncomp < 1 || dst_comp + ncomp > dst->ncomp || src_comp + ncomp > src->ncomp)
+    return fail(SGC_ERR_ARG, "sgc_fab_copy: component range");
+  std::vector<CopyItem> v(1, make_item(gd, dr, dst_comp, gs, sr, src_comp, ncomp, comp_flags));
+  CopyTable t;
+  int st = t.upload(v);
+  if (!st) st = launch_copy(t, dst->d_arena, src->d_arena, dst->esz, rt().compute);
+  if (!st) cudaStreamSynchronize(rt().compute);
+  t.release();
+  return st;
+}
+
+static int linear_io(sgc_level_t l, int box, const int rlo[3], const int rhi[3], int c0, int c1, unsigned flags,
+                     void* buffer, bool out) {
+  SGC_REQUIRE_RT();
+  if (!l || !rlo || !rhi || !buffer || box < 0 || box >= l->nbox) return fail(SGC_ERR_ARG, "linearOut/In: bad argument");
+  if (c0 < 0 || c1 < c0 || c1 > l->ncomp) return fail(SGC_ERR_ARG, "linearOut/In: component range");
+  IBox r;
+  for (int d = 0; d < 3; ++d) { r.lo[d] = rlo[d]; r.hi[d] = rhi[d]; }
+  const FabGeom& g = l->geom[box];
+  if (r.empty() || !fab_contains(g, r)) return fail(SGC_ERR_ARG, "linearOut/In: region outside fab");
+  // wire format: only the selected components are present, packed back to back (BaseFab.cpp:365-373)
+  std::vector<CopyItem> v;
+  long long pos = 0;
+  for (int c = c0; c < c1; ++c) {
+    if (!(c >= 32 || ((flags >> c) & 1u))) continue;
+    const FabGeom bg = dense_geom(r, pos);
+    v.push_back(out ? make_item(bg, r, 0, g, r, c, 1, ~0u) : make_item(g, r, c, bg, r, 0, 1, ~0u));
+    pos += r.size();
+  }
+  if (pos == 0) return 0;
+  int st = ensure_scratch(l, (size_t)pos * l->esz);
+  if (st) return st;
+  CopyTable t;
+  st = t.upload(v);
+  if (st) return st;
+  if (out) {
+    st = launch_copy(t, l->d_scratch, l->d_arena, l->esz, rt().compute);
+    if (!st) {
+      cudaError_t e = cudaMemcpyAsync(buffer, l->d_scratch, (size_t)pos * l->esz, cudaMemcpyDeviceToHost, rt().compute);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(rt().compute);
+      if (e != cudaSuccess) st = fail(SGC_ERR_CUDA, cudaGetErrorString(e));
+    }
+  } else {
+    cudaError_t e = cudaMemcpyAsync(l->d_scratch, buffer, (size_t)pos * l->esz, cudaMemcpyHostToDevice, rt().compute);
+    if (e != cudaSuccess) st = fail(SGC_ERR_CUDA, cudaGetErrorString(e));
+    if (!st) st = launch_copy(t, l->d_arena, l->d_scratch, l->esz, rt().compute);
+    if (!st) cudaStreamSynchronize(rt().compute);
+  }
+  t.release();
+  return st;
+}
+
+int sgc_fab_linear_out(sgc_level_t l, int box, const int rlo[3], const int rhi[3], int c0, int c1, unsigned flags,
+                       void* buffer) {
+  return linear_io(l, box, rlo, rhi, c0, c1, flags, buffer, true);
+}
+int sgc_fab_linear_in(sgc_level_t l, int box, const int rlo[3], const int rhi[3], int c0, int c1, unsigned flags,
+                      const void* buffer) {
+  return linear_io(l, box, rlo, rhi, c0, c1, flags, const_cast<void*>(buffer), false);
+}
+
+// ------------------------------------------------------------------------------- plans
+static sgc_plan_s* new_plan_for(sgc_level_s* l, int c0, int nc) {
+  sgc_plan_s* p = new sgc_plan_s;
+  p->nbox = l->nbox; p->ncomp = l->ncomp; p->ng = l->ng; p->esz = l->esz; p->gidx0 = l->gidx0;
+  p->boxes = l->boxes;
+  p->c0 = c0; p->nc = nc;
+  p->box_is_boundary.assign(l->nbox, 0);
+  return p;
+}
+
+static int upload_local_items(sgc_plan_s* p, sgc_level_s* l) {
+  std::vector<CopyItem> v;
+  v.reserve(p->items.size());
+  p->nremote = 0;
+  for (const sgc_motion_item& it : p->items) {
+    const int ld = it.recv_box - l->gidx0;
+    if (ld < 0 || ld >= l->nbox) return fail(SGC_ERR_ARG, "plan: receiving box is not local to this level");
+    if (it.recv_proc != it.send_proc) { ++p->nremote; p->box_is_boundary[ld] = 1; continue; }
+    const int ls = it.send_box - l->gidx0;
+    if (ls < 0 || ls >= l->nbox) return fail(SGC_ERR_ARG, "plan: local item refers to a box outside this level");
+    IBox dr, sr;
+    for (int d = 0; d < 3; ++d) { dr.lo[d] = it.recv_lo[d]; dr.hi[d] = it.recv_hi[d]; sr.lo[d] = it.src_lo[d]; sr.hi[d] = it.src_hi[d]; }
+    if (dr.empty()) continue;
+    if (!fab_contains(l->geom[ld], dr) || !fab_contains(l->geom[ls], sr))
+      return fail(SGC_ERR_ARG, "plan: motion item region outside its fab (nghost of the level too small?)");
+    v.push_back(make_item(l->geom[ld], dr, p->c0, l->geom[ls], sr, p->c0, p->nc, it.comp_flags));
+  }
+  p->n_boundary_boxes = 0;
+  for (char c : p->box_is_boundary) p->n_boundary_boxes += c;
+  return p->local.upload(v);
+}
+
+int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], const int maxbox[3], unsigned periodic,
+                             unsigned trim, int comp_begin, int ncomp, int nproc, int rank, sgc_plan_t* plan) {
+  SGC_REQUIRE_RT();
+  if (!l || !dlo || !dhi || !maxbox || !plan) return fail(SGC_ERR_ARG, "sgc_plan_create_exchange: null argument");
+  if (comp_begin < 0 || ncomp < 1 || comp_begin + ncomp > l->ncomp)
+    return fail(SGC_ERR_ARG, "sgc_plan_create_exchange: component range");
+  Grid g(dlo, dhi, maxbox, nproc);
+  if (g.status) return fail(SGC_ERR_ARG, "sgc_plan_create_exchange: boxes must tile the domain and divide among ranks");
+  if (g.bpp != l->nbox || l->gidx0 != rank * g.bpp)
+    return fail(SGC_ERR_GEOMETRY, "sgc_plan_create_exchange: level does not hold this rank's boxes of the layout");
+  for (int b = 0; b < l->nbox; ++b) {
+    const IBox gb = g.box(l->gidx0 + b);
+    if (memcmp(&gb, &l->boxes[b], sizeof(IBox)) != 0)
+      return fail(SGC_ERR_GEOMETRY, "sgc_plan_create_exchange: level boxes differ from the layout");
+  }
+  sgc_plan_s* p = new_plan_for(l, comp_begin, ncomp);
+  p->nproc = nproc; p->rank = rank;
+  int st = build_exchange_items(g, l->ng, periodic, trim, rank, p->items);
+  if (!st) st = upload_local_items(p, l);
+  if (!st && p->nremote > 0) st = comm_plan_setup(p, l, g, periodic, trim);
+  if (st) { sgc_plan_destroy(p); return st; }
+  *plan = p;
+  return 0;
+}
+
+int sgc_plan_create_items(sgc_level_t l, const sgc_motion_item* items, int nitem, int comp_begin, int ncomp,
+                          sgc_plan_t* plan) {
+  SGC_REQUIRE_RT();
+  if (!l || (!items && nitem > 0) || nitem < 0 || !plan) return fail(SGC_ERR_ARG, "sgc_plan_create_items: bad argument");
+  if (comp_begin < 0 || ncomp < 1 || comp_begin + ncomp > l->ncomp)
+    return fail(SGC_ERR_ARG, "sgc_plan_create_items: component range");
+  sgc_plan_s* p = new_plan_for(l, comp_begin, ncomp);
+  p->items.assign(items, items + nitem);
+  for (const sgc_motion_item& it : p->items)
+    if (it.recv_proc != it.send_proc) {
+      sgc_plan_destroy(p);
+      return fail(SGC_ERR_ARG, "sgc_plan_create_items: only local items are accepted");
+    }
+  const int st = upload_local_items(p, l);
+  if (st) { sgc_plan_destroy(p); return st; }
+  *plan = p;
+  return 0;
+}
+
+int sgc_plan_create_bc_zero_gradient(sgc_level_t l, const int dlo[3], const int dhi[3], sgc_plan_t* plan) {
+  SGC_REQUIRE_RT();
+  if (!l || !dlo || !dhi || !plan) return fail(SGC_ERR_ARG, "sgc_plan_create_bc_zero_gradient: null argument");
+  if (l->ng < 1) return fail(SGC_ERR_ARG, "sgc_plan_create_bc_zero_gradient: level has no ghost cells");
+  std::vector<sgc_motion_item> items;
+  for (int b = 0; b < l->nbox; ++b) {
+    const IBox& v = l->boxes[b];
+    for (int dir = 0; dir < 3; ++dir)
+      for (int side = -1; side <= 1; side += 2) {
+        const bool touches = side < 0 ? v.lo[dir] == dlo[dir] : v.hi[dir] == dhi[dir];
+        if (!touches) continue;
+        IBox src = v;                                   // boundary layer of valid cells
+        if (side < 0) src.hi[dir] = src.lo[dir]; else src.lo[dir] = src.hi[dir];
+        IBox dstb = src;
+        dstb.lo[dir] += side; dstb.hi[dir] += side;   // the ghost face next to it
+        sgc_motion_item it;
+        memset(&it, 0, sizeof it);
+        it.recv_box = it.send_box = l->gidx0 + b;
+        for (int d = 0; d < 3; ++d) {
+          it.recv_lo[d] = dstb.lo[d]; it.recv_hi[d] = dstb.hi[d];
+          it.src_lo[d] = src.lo[d];   it.src_hi[d] = src.hi[d];
+          it.send_lo[d] = src.lo[d];  it.send_hi[d] = src.hi[d];
+        }
+        it.dir[dir] = side;
+        it.comp_flags = ~0u;
+        items.push_back(it);
+      }
+  }
+  return sgc_plan_create_items(l, items.data(), (int)items.size(), 0, l->ncomp, plan);
+}
+
+int sgc_plan_destroy(sgc_plan_t p) {
+  if (!p) return 0;
+  if (rt().ready) { cudaStreamSynchronize(rt().compute); cudaStreamSynchronize(rt().comm); }
+  p->local.release();
+  comm_plan_release(p);
+  delete p;
+  return 0;
+}
+
+int sgc_plan_num_items(sgc_plan_t p) { return p ? (int)p->items.size() : -1; }
+int sgc_plan_num_remote_items(sgc_plan_t p) { return p ? p->nremote : -1; }
+long long sgc_plan_num_cells(sgc_plan_t p) {
+  if (!p) return -1;
+  long long n = 0;
+  for (const sgc_motion_item& it : p->items) {
+    long long c = 1;
+    for (int d = 0; d < 3; ++d) c *= (it.recv_hi[d] - it.recv_lo[d] + 1);
+    n += c * p->nc;
+  }
+  return n;
+}
+
+int sgc_exchange_begin(sgc_level_t l, sgc_plan_t p) {
+  SGC_REQUIRE_RT();
+  if (!l || !p) return fail(SGC_ERR_ARG, "sgc_exchange: null handle");
+  if (!plan_matches(p, l)) return fail(SGC_ERR_GEOMETRY, "sgc_exchange: plan was built for a different layout");
+  if (p->in_flight) return fail(SGC_ERR_ARG, "sgc_exchange_begin: previous exchange not ended");
+  if (p->nremote > 0) {
+    const int st = comm_exchange_begin(l, p);
+    if (st) return st;
+  }
+  int st;
+  {
+    ProfScope prof(1, rt().compute);
+    st = launch_copy(p->local, l->d_arena, l->d_arena, l->esz, rt().compute);
+  }
+  if (st) return st;
+  p->in_flight = true;
+  return 0;
+}
+
+int sgc_exchange_end(sgc_level_t l, sgc_plan_t p) {
+  SGC_REQUIRE_RT();
+  if (!l || !p) return fail(SGC_ERR_ARG, "sgc_exchange: null handle");
+  if (!p->in_flight) return fail(SGC_ERR_ARG, "sgc_exchange_end without sgc_exchange_begin");
+  p->in_flight = false;
+  if (p->nremote > 0) return comm_exchange_end(l, p);
+  return 0;
+}
+
+int sgc_exchange(sgc_level_t l, sgc_plan_t p) {
+  const int st = sgc_exchange_begin(l, p);
+  if (st) return st;
+  return sgc_exchange_end(l, p);
+}
+
+// ------------------------------------------------------------------------------- stencil apply
+static int check_sweep(sgc_level_s* out, sgc_level_s* in, const char* who) {
+  if (!out || !in) return fail(SGC_ERR_ARG, std::string(who) + ": null level");
+  if (out->esz != 8 || in->esz != 8) return fail(SGC_ERR_UNSUPPORTED, std::string(who) + ": needs 8-byte Real");
+  if (out == in) return fail(SGC_ERR_ARG, std::string(who) + ": in-place sweep is not defined");
+  if (!same_layout(out, in)) return fail(SGC_ERR_GEOMETRY, std::string(who) + ": levels are on different layouts");
+  for (int b = 0; b < out->nbox; ++b)
+    if (!fab_contains(in->geom[b], out->boxes[b].grown(1)))
+      return fail(SGC_ERR_ARG, std::string(who) + ": input fab must contain grow(box,1)");
+  return 0;
+}
+
+int sgc_heat_sweep_range(sgc_level_t unew, sgc_level_t u, double f, unsigned flags, int box_begin, int box_end) {
+  SGC_REQUIRE_RT();
+  int st = check_sweep(unew, u, "sgc_heat_sweep");
+  if (st) return st;
+  if (box_begin < 0 || box_end > unew->nbox || box_begin > box_end) return fail(SGC_ERR_ARG, "sgc_heat_sweep: box range");
+  if (box_begin == box_end) return 0;
+  const int fma = (flags & SGC_FMA) ? 1 : 0;
+  ProfScope prof(0, rt().compute);
+  st = launch_heat_stream(unew, u, f, fma, box_begin, box_end, rt().compute);
+  if (st <= 0) return st;
+  const int w0 = unew->work_begin[box_begin], w1 = unew->work_begin[box_end];
+  return launch_heat_generic(unew->d_work, w0, w1 - w0, u->d_geom, unew->d_geom, (const double*)u->d_arena,
+                             (double*)unew->d_arena, f, fma, rt().compute);
+}
+
+int sgc_heat_sweep(sgc_level_t unew, sgc_level_t u, double f, unsigned flags) {
+  SGC_REQUIRE_RT();
+  if (!unew) return fail(SGC_ERR_ARG, "sgc_heat_sweep: null level");
+  return sgc_heat_sweep_range(unew, u, f, flags, 0, unew->nbox);
+}
+
+int sgc_laplacian_apply(sgc_level_t B, sgc_level_t A, double coef, int niter, int fuse_iters, unsigned flags) {
+  SGC_REQUIRE_RT();
+  int st = check_sweep(B, A, "sgc_laplacian_apply");
+  if (st) return st;
+  if (niter < 0) return fail(SGC_ERR_ARG, "sgc_laplacian_apply: niter");
+  const int launches = fuse_iters ? 1 : niter;
+  const int per = fuse_iters ? niter : 1;
+  for (int i = 0; i < launches && !st; ++i)
+    st = launch_lap_generic(B->d_work, 0, B->nwork, A->d_geom, B->d_geom, (const double*)A->d_arena,
+                            (double*)B->d_arena, coef, (flags & SGC_FMA) ? 1 : 0, per, rt().compute);
+  return st;
+}
+
+int sgc_wave_step(sgc_level_t unp1, sgc_level_t un, sgc_level_t unm1, double factor, unsigned flags) {
+  SGC_REQUIRE_RT();
+  int st = check_sweep(unp1, un, "sgc_wave_step");
+  if (st) return st;
+  if (!unm1 || !same_geometry(un, unm1)) return fail(SGC_ERR_GEOMETRY, "sgc_wave_step: un and unm1 must share geometry");
+  if (unm1 == unp1) return fail(SGC_ERR_ARG, "sgc_wave_step: unp1 must not alias unm1");
+  return launch_wave_generic(unp1->d_work, 0, unp1->nwork, un->d_geom, unp1->d_geom, (const double*)un->d_arena,
+                             (double*)unp1->d_arena, (const double*)unm1->d_arena, factor, (flags & SGC_FMA) ? 1 : 0,
+                             rt().compute);
+}
+
+int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags, int nstep, int* result_in_b) {
+  SGC_REQUIRE_RT();
+  if (!a || !b || !plan || nstep < 0) return fail(SGC_ERR_ARG, "sgc_heat_run: bad argument");
+  if (!same_geometry(a, b)) return fail(SGC_ERR_GEOMETRY, "sgc_heat_run: the two levels must share geometry");
+  sgc_level_t cur = a, nxt = b;
+  for (int s = 0; s < nstep; ++s) {
+    int st;
+    if (plan->nremote > 0 && plan->n_boundary_boxes < cur->nbox) {
+      // overlap: halo in flight while boxes without remote items sweep (boundary boxes are the
+      // first and last box layers of a z-slab partition, so interior boxes form one range)
+      st = sgc_exchange_begin(cur, plan);
+      int b0 = 0, b1 = cur->nbox;
+      while (b0 < b1 && plan->box_is_boundary[b0]) ++b0;
+      while (b1 > b0 && plan->box_is_boundary[b1 - 1]) --b1;
+      bool contiguous = true;
+      for (int i = b0; i < b1; ++i) if (plan->box_is_boundary[i]) contiguous = false;
+      if (!st && contiguous) st = sgc_heat_sweep_range(nxt, cur, f, flags, b0, b1);
+      if (!st) st = sgc_exchange_end(cur, plan);
+      if (!st && contiguous) {
+        st = sgc_heat_sweep_range(nxt, cur, f, flags, 0, b0);
+        if (!st) st = sgc_heat_sweep_range(nxt, cur, f, flags, b1, cur->nbox);
+      } else if (!st) {
+        st = sgc_heat_sweep(nxt, cur, f, flags);
+      }
+    } else {
+      st = sgc_exchange(cur, plan);
+      if (!st) st = sgc_heat_sweep(nxt, cur, f, flags);
+    }
+    if (st) return st;
+    std::swap(cur, nxt);
+  }
+  if (result_in_b) *result_in_b = (cur == b) ? 1 : 0;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// sgc_device.h — device-side data model shared by the .cu files.
+//
+// Replaces the reference's device data model: CudaFab (CudaFab.H:104-530, an
+// alias of one BaseFab), SymbolPair host/device mirrors per fab (BaseFab.cpp:509-528) and the
+// __constant__ pointer tables of WavePatch_Cuda.cu:22-24 by ONE arena per level plus a device
+// box table of PODs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "sgc_internal.h"
+
+namespace sgc {
+
+// One entry of the device box table: where fab b lives and which cells are valid.
+struct FabGeom {
+  long long off;   // element offset of the fab's first element (comp 0) in the level arena
+  long long cs;    // component stride = n[0]*n[1]*n[2]   (BaseFab::getComponentStride)
+  int lo[3];       // lower corner of the fab box (= valid box grown by nghost)
+  int n[3];        // extents of the fab box; x pitch = n[0], plane pitch = n[0]*n[1]
+  int vlo[3];      // lower corner of the valid box
+  int vn[3];       // extents of the valid box
+};
+
+// One region copy dst[region, c] = src[region + shift, c] — a Motion2Way, a BaseFab::copy, a
+// linearOut/linearIn (the buffer side is a dense box) or a physical-BC face copy.
+struct CopyItem {
+  long long dst;   // element offset of the region origin, component c0, in the dst arena
+  long long src;   // same in the src arena
+  long long dcs, scs;   // component strides
+  int nx, ny, nz, nc;   // region extents and number of components
+  int dsy, dsz;    // dst row / plane pitch (elements)
+  int ssy, ssz;    // src row / plane pitch
+  unsigned flags;  // component mask, bit = absolute destination component (BaseFab.cpp:320)
+  int c0;          // first destination component (for the mask test)
+};
+
+struct CopyTable {
+  CopyItem* d_items = nullptr;
+  long long* d_cell_start = nullptr;   // exclusive prefix sum of item cell counts, n+1 entries
+  int* d_chunk_first = nullptr;        // first item overlapping chunk c, nchunk+1 entries
+  int nitem = 0;
+  int nchunk = 0;
+  long long ncell = 0;
+  void release();
+  int upload(const std::vector<CopyItem>& items);
+};
+
+constexpr int kCopyChunk = 2048;       // cells per CTA of the batched copy kernel
+constexpr int kCopyThreads = 256;
+
+// Event-pair log for sgc_profile_* (class 0 = sweep, 1 = exchange copy).
+struct ProfLog {
+  std::vector<cudaEvent_t> a, b;
+  int used = 0;
+};
+struct ProfScope {          // RAII: records the pair around one launch when profiling is on
+  int klass; cudaStream_t s; int slot;
+  ProfScope(int klass_, cudaStream_t s_);
+  ~ProfScope();
+};
+
+struct Runtime {
+  bool profiling = false;
+  ProfLog prof[2];
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t compute = nullptr;
+  cudaStream_t comm = nullptr;
+  long long launches = 0;
+};
+Runtime& rt();
+
+#define SGC_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::sgc::fail(SGC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define SGC_REQUIRE_RT()                                                                     \
+  do {                                                                                      \
+    if (!::sgc::rt().ready)                                                                 \
+      return ::sgc::fail(SGC_ERR_CUDA, "sgc_init() has not succeeded: no CUDA device bound " \
+                                       "(this library has no CPU fallback)");               \
+  } while (0)
+
+// launchers implemented in sgc_kernels.cu
+int launch_copy(const CopyTable& t, void* dst_arena, const void* src_arena, int esz, cudaStream_t s);
+int launch_fill(void* p, long long n, int esz, const void* value, cudaStream_t s);
+
+}  // namespace sgc
+
+// opaque handle bodies
+struct sgc_level_s {
+  int nbox = 0, ncomp = 0, ng = 0, esz = 8, gidx0 = 0;
+  std::vector<sgc::IBox> boxes;         // valid boxes
+  std::vector<long long> off;           // element offset of fab b in the host concatenation
+  long long elems = 0;                  // total elements, all fabs and comps
+  long long lead = 0;                   // elements of padding before fab 0 in the arena
+  void* d_base = nullptr;               // cudaMalloc'ed block
+  void* d_arena = nullptr;              // = d_base + lead*esz : fab b at element off[b]
+  sgc::FabGeom* d_geom = nullptr;
+  std::vector<sgc::FabGeom> geom;
+  bool uniform = true;                  // all fabs have the same extents
+  // sweep work table (box, y0, z0) for the generic kernel, built at creation
+  int* d_work = nullptr;
+  int nwork = 0;
+  std::vector<int> work_begin;          // first work item of box b (nbox+1 entries)
+  // scratch device buffer for linearOut/In
+  void* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+struct sgc_plan_s {
+  // geometry signature of the level the plan was built for
+  int nbox = 0, ncomp = 0, ng = 0, esz = 0, gidx0 = 0;
+  std::vector<sgc::IBox> boxes;
+  int c0 = 0, nc = 0;
+  int nproc = 1, rank = 0;
+  std::vector<sgc_motion_item> items;   // this rank's items, reference order
+  int nremote = 0;
+  sgc::CopyTable local;                 // local items: arena -> arena
+  // multi-rank: per-peer staging
+  struct Peer {
+    int rank = -1;
+    sgc::CopyTable pack;                // arena -> send buffer   (dense, receiver's item order)
+    sgc::CopyTable unpack;              // recv buffer -> arena
+    void* d_send = nullptr;
+    void* d_recv = nullptr;
+    long long send_elems = 0, recv_elems = 0;
+  };
+  std::vector<Peer> peers;
+  std::vector<int> interior_boxes_first;  // not used yet
+  int n_boundary_boxes = 0;               // boxes with at least one remote item
+  std::vector<char> box_is_boundary;
+  cudaEvent_t ev_local = nullptr, ev_halo = nullptr, ev_ready = nullptr;
+  bool in_flight = false;
+};
+
+struct sgc_event_s {
+  cudaEvent_t ev = nullptr;
+};

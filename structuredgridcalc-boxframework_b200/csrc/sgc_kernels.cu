@@ -1,0 +1,212 @@
+// sgc_kernels.cu — generic sm_100a kernels: batched region copy (ghost fill / pack / unpack /
+// BaseFab::copy / physical BC), fill, and the table-driven 7-point sweeps that work for any fab
+// geometry.  The bandwidth-tuned streaming sweep for uniform levels lives in sgc_stream.cu.
+#include <cstdint>
+
+#include "sgc_device.h"
+
+namespace sgc {
+
+// ---------------------------------------------------------------------------------------------
+// Batched region copy: ONE launch runs every item of a table (all motion items of
+// an exchange are independent and race-free, so order does not matter and the result is
+// bit-identical to the reference's serial loop, LevelData.H:471-486).
+//
+// Work split: the items' cells are numbered consecutively (prefix sum cell_start[]); CTA c owns
+// cells [c*kCopyChunk, (c+1)*kCopyChunk).  chunk_first[c] is the first item overlapping the
+// chunk, so a thread finds its item with a short binary search over a handful of entries (one
+// entry for a 64x64 face, up to kCopyChunk entries when the chunk is all single-cell corners).
+// Balanced regardless of the face/edge/corner mix (C3: 851 968 items from 1 to 256 cells).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kCopyThreads)
+k_copy_items(const CopyItem* __restrict__ items, const long long* __restrict__ cell_start,
+             const int* __restrict__ chunk_first, T* __restrict__ dst_arena,
+             const T* __restrict__ src_arena, long long ncell) {
+  const long long base = (long long)blockIdx.x * kCopyChunk;
+  const int it_lo = chunk_first[blockIdx.x];
+  const int it_hi = chunk_first[blockIdx.x + 1];   // last item that can overlap this chunk
+#pragma unroll 2
+  for (int t = threadIdx.x; t < kCopyChunk; t += kCopyThreads) {
+    const long long cell = base + t;
+    if (cell >= ncell) break;
+    // largest it in [it_lo, it_hi] with cell_start[it] <= cell
+    int lo = it_lo, hi = it_hi;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(cell_start + mid) <= cell) lo = mid; else hi = mid - 1;
+    }
+    const CopyItem* __restrict__ I = items + lo;
+    unsigned r = (unsigned)(cell - __ldg(cell_start + lo));
+    const unsigned nx = I->nx, ny = I->ny, nz = I->nz;
+    const unsigned x = r % nx; r /= nx;
+    const unsigned y = r % ny; r /= ny;
+    const unsigned z = r % nz;
+    const unsigned c = r / nz;
+    const unsigned dc = I->c0 + c;
+    if (dc < 32u && !((I->flags >> dc) & 1u)) continue;
+    const long long d = I->dst + c * I->dcs + x + (long long)y * I->dsy + (long long)z * I->dsz;
+    const long long s = I->src + c * I->scs + x + (long long)y * I->ssy + (long long)z * I->ssz;
+    dst_arena[d] = src_arena[s];
+  }
+}
+
+int launch_copy(const CopyTable& t, void* dst_arena, const void* src_arena, int esz, cudaStream_t s) {
+  if (t.nitem == 0 || t.ncell == 0) return 0;
+  switch (esz) {
+    case 8:
+      k_copy_items<uint64_t><<<t.nchunk, kCopyThreads, 0, s>>>(t.d_items, t.d_cell_start, t.d_chunk_first,
+                                                               (uint64_t*)dst_arena, (const uint64_t*)src_arena, t.ncell);
+      break;
+    case 4:
+      k_copy_items<uint32_t><<<t.nchunk, kCopyThreads, 0, s>>>(t.d_items, t.d_cell_start, t.d_chunk_first,
+                                                               (uint32_t*)dst_arena, (const uint32_t*)src_arena, t.ncell);
+      break;
+    case 1:
+      k_copy_items<uint8_t><<<t.nchunk, kCopyThreads, 0, s>>>(t.d_items, t.d_cell_start, t.d_chunk_first,
+                                                              (uint8_t*)dst_arena, (const uint8_t*)src_arena, t.ncell);
+      break;
+    default:
+      return fail(SGC_ERR_UNSUPPORTED, "element size must be 1, 4 or 8 bytes");
+  }
+  rt().launches++;
+  SGC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fill (BaseFab::setVal, BaseFab.cpp:219-246)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_fill(T* __restrict__ p, long long n, T v) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+int launch_fill(void* p, long long n, int esz, const void* value, cudaStream_t s) {
+  if (n <= 0) return 0;
+  const int threads = 256;
+  long long want = (n + threads - 1) / threads;
+  const int blocks = (int)(want < 148LL * 16 ? want : 148LL * 16);
+  switch (esz) {
+    case 8: k_fill<uint64_t><<<blocks, threads, 0, s>>>((uint64_t*)p, n, *(const uint64_t*)value); break;
+    case 4: k_fill<uint32_t><<<blocks, threads, 0, s>>>((uint32_t*)p, n, *(const uint32_t*)value); break;
+    case 1: k_fill<uint8_t><<<blocks, threads, 0, s>>>((uint8_t*)p, n, *(const uint8_t*)value); break;
+    default: return fail(SGC_ERR_UNSUPPORTED, "element size must be 1, 4 or 8 bytes");
+  }
+  rt().launches++;
+  SGC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table-driven 7-point sweep, any geometry.  One CTA per work item (box, y0, z0) of a
+// kTileY x kTileZ slab of columns; a thread owns column (x, y) and marches in z with the three
+// z-neighbours rolling through registers (the "register-blocked sweep along the slow axis");
+// x/y neighbours come from global memory through L1.  The arithmetic is written with explicit
+// rounding intrinsics so nvcc cannot contract or re-associate anything.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileX = 64, kTileY = 4, kTileZ = 16;
+
+struct HeatOp {                       // unew = u + f*S
+  double f; int fma;
+  __device__ __forceinline__ double operator()(double c, double tx, double ty, double tz, double) const {
+    const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
+    return fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+  }
+};
+struct LapOp {                        // niter x { b -= coef*Tx; b -= coef*Ty; b -= coef*Tz }
+  double coef; int fma; int niter;
+  __device__ __forceinline__ double operator()(double, double tx, double ty, double tz, double b) const {
+    const double mc = -coef;
+    for (int it = 0; it < niter; ++it) {
+      if (fma) { b = __fma_rn(mc, tx, b); b = __fma_rn(mc, ty, b); b = __fma_rn(mc, tz, b); }
+      else {
+        b = __dsub_rn(b, __dmul_rn(coef, tx)); b = __dsub_rn(b, __dmul_rn(coef, ty));
+        b = __dsub_rn(b, __dmul_rn(coef, tz));
+      }
+    }
+    return b;
+  }
+};
+struct WaveOp {                       // r = 2u - um1; r += f*Tx; r += f*Ty; r += f*Tz
+  double f; int fma;
+  __device__ __forceinline__ double operator()(double c, double tx, double ty, double tz, double um1) const {
+    double r = __dsub_rn(__dmul_rn(2.0, c), um1);       // 2*c is exact: contraction-invariant
+    if (fma) { r = __fma_rn(f, tx, r); r = __fma_rn(f, ty, r); r = __fma_rn(f, tz, r); }
+    else {
+      r = __dadd_rn(r, __dmul_rn(f, tx)); r = __dadd_rn(r, __dmul_rn(f, ty)); r = __dadd_rn(r, __dmul_rn(f, tz));
+    }
+    return r;
+  }
+};
+
+// second difference in the reference's association: (u[+e] - 2u) + u[-e]; 2u is exact.
+__device__ __forceinline__ double d2(double p, double c, double m) {
+  return __dadd_rn(__dsub_rn(p, __dmul_rn(2.0, c)), m);
+}
+
+// AUX: 0 none, 1 = read old value of out (read-modify-write), 2 = third level with in geometry
+template <class Op, int AUX>
+__global__ void __launch_bounds__(kTileX * kTileY)
+k_sweep7(const int* __restrict__ work, const FabGeom* __restrict__ gin, const FabGeom* __restrict__ gout,
+         const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ aux, Op op) {
+  const int b = work[3 * blockIdx.x], y0 = work[3 * blockIdx.x + 1], z0 = work[3 * blockIdx.x + 2];
+  const FabGeom GI = gin[b], GO = gout[b];
+  const int y = y0 + threadIdx.y;
+  if (y >= GO.vn[1]) return;
+  const int zend = min(z0 + kTileZ, GO.vn[2]);
+  const long long isy = GI.n[0], isz = (long long)GI.n[0] * GI.n[1];
+  const long long osy = GO.n[0], osz = (long long)GO.n[0] * GO.n[1];
+  // offsets of valid cell (0, y, z0) of this box in the in / out fabs
+  const long long ibase = GI.off + (GO.vlo[0] - GI.lo[0]) + (GO.vlo[1] + y - GI.lo[1]) * isy +
+                          (long long)(GO.vlo[2] + z0 - GI.lo[2]) * isz;
+  const long long obase = GO.off + (GO.vlo[0] - GO.lo[0]) + (GO.vlo[1] + y - GO.lo[1]) * osy +
+                          (long long)(GO.vlo[2] + z0 - GO.lo[2]) * osz;
+  for (int x = threadIdx.x; x < GO.vn[0]; x += kTileX) {
+    const double* __restrict__ p = in + ibase + x;
+    double* __restrict__ q = out + obase + x;
+    const double* __restrict__ a = (AUX == 2) ? aux + ibase + x : nullptr;
+    double zm = __ldg(p - isz), c = __ldg(p);
+    for (int z = z0; z < zend; ++z) {
+      const double zp = __ldg(p + isz);
+      const double tx = d2(__ldg(p + 1), c, __ldg(p - 1));
+      const double ty = d2(__ldg(p + isy), c, __ldg(p - isy));
+      const double tz = d2(zp, c, zm);
+      double av = 0.0;
+      if (AUX == 1) av = *q;
+      if (AUX == 2) { av = __ldg(a); a += isz; }
+      *q = op(c, tx, ty, tz, av);
+      zm = c; c = zp;
+      p += isz; q += osz;
+    }
+  }
+}
+
+template <class Op, int AUX>
+static int launch_sweep(const int* d_work, int w0, int nwork, const FabGeom* gin, const FabGeom* gout,
+                        const double* in, double* out, const double* aux, Op op, cudaStream_t s) {
+  if (nwork <= 0) return 0;
+  k_sweep7<Op, AUX><<<nwork, dim3(kTileX, kTileY), 0, s>>>(d_work + 3 * (size_t)w0, gin, gout, in, out, aux, op);
+  rt().launches++;
+  SGC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_heat_generic(const int* d_work, int w0, int nwork, const FabGeom* gin, const FabGeom* gout,
+                        const double* in, double* out, double f, int fma, cudaStream_t s) {
+  return launch_sweep<HeatOp, 0>(d_work, w0, nwork, gin, gout, in, out, nullptr, HeatOp{f, fma}, s);
+}
+int launch_lap_generic(const int* d_work, int w0, int nwork, const FabGeom* gin, const FabGeom* gout,
+                       const double* in, double* out, double coef, int fma, int niter, cudaStream_t s) {
+  return launch_sweep<LapOp, 1>(d_work, w0, nwork, gin, gout, in, out, nullptr, LapOp{coef, fma, niter}, s);
+}
+int launch_wave_generic(const int* d_work, int w0, int nwork, const FabGeom* gin, const FabGeom* gout,
+                        const double* in, double* out, const double* um1, double f, int fma, cudaStream_t s) {
+  return launch_sweep<WaveOp, 2>(d_work, w0, nwork, gin, gout, in, out, um1, WaveOp{f, fma}, s);
+}
+
+int sweep_tile_y() { return kTileY; }
+int sweep_tile_z() { return kTileZ; }
+
+}  // namespace sgc

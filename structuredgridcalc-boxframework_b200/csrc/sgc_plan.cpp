@@ -1,0 +1,164 @@
+// sgc_plan.cpp — host-side index algebra: uniform layout and the ghost-exchange plan.
+//
+// Mirrors (clean-room, from the behaviour documented in SURVEY.md §3.1/§A and checked against
+// the oracle): DisjointBoxLayout::define (lib/src/BoxFramework/DisjointBoxLayout.cpp:93-168),
+// NeighborIterator / PeriodicIterator (LayoutIterator.H:522-783) and
+// Copier::defineExchangeDBL (Copier.H:521-659).  No CUDA in this file: it runs (and is tested)
+// on machines without a GPU.
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "sgc_internal.h"
+
+namespace sgc {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int status, const std::string& msg) {
+  g_err = msg;
+  return status;
+}
+const char* last_error_cstr() { return g_err.c_str(); }
+
+Grid::Grid(const int dlo[3], const int dhi[3], const int mb[3], int nproc_) : nproc(nproc_), status(0) {
+  for (int d = 0; d < 3; ++d) {
+    domain.lo[d] = dlo[d];
+    domain.hi[d] = dhi[d];
+    maxbox[d] = mb[d];
+    const int ext = dhi[d] - dlo[d] + 1;
+    if (mb[d] < 1 || ext < 1) { status = SGC_ERR_ARG; nb[d] = 0; continue; }
+    nb[d] = ext / mb[d];
+    if (nb[d] * mb[d] != ext) status = SGC_ERR_ARG;  // boxes must tile the domain (:104-106)
+  }
+  nbox = nb[0] * nb[1] * nb[2];
+  if (nproc < 1 || nbox < 1 || nbox % nproc) status = SGC_ERR_ARG;  // (:125)
+  bpp = (status == 0) ? nbox / nproc : 1;
+}
+
+IBox Grid::box(int g) const {
+  const int c[3] = {g % nb[0], (g / nb[0]) % nb[1], g / (nb[0] * nb[1])};
+  IBox b;
+  for (int d = 0; d < 3; ++d) {
+    b.lo[d] = domain.lo[d] + c[d] * maxbox[d];
+    b.hi[d] = b.lo[d] + maxbox[d] - 1;
+  }
+  return b;
+}
+
+// One neighbour direction of one box. `outside`: the offset leaves the box grid (periodic image).
+struct Nbr {
+  int dir[3];
+  int cell[3];  // wrapped grid coordinate of the neighbour box
+  bool outside;
+};
+
+// Enumerate the 26 directions in x-fastest order and classify them for box-grid cell `c`.
+template <class F>
+static void for_each_direction(const Grid& g, const int c[3], unsigned periodic, unsigned trim, F&& f) {
+  const unsigned mask = trim | SGC_TRIM_CENTER;
+  for (int code = 0; code < 27; ++code) {
+    Nbr n;
+    n.dir[0] = code % 3 - 1;
+    n.dir[1] = (code / 3) % 3 - 1;
+    n.dir[2] = code / 9 - 1;
+    const int codim = std::abs(n.dir[0]) + std::abs(n.dir[1]) + std::abs(n.dir[2]);
+    if (mask & (1u << codim)) continue;  // Trim{Center,Face,Edge,Corner} = 1<<norm1
+    n.outside = false;
+    bool reachable = true;
+    for (int d = 0; d < 3; ++d) {
+      int p = c[d] + n.dir[d];
+      if (p < 0 || p >= g.nb[d]) {
+        n.outside = true;
+        if (!(periodic & (1u << d))) reachable = false;
+        p += (p < 0) ? g.nb[d] : -g.nb[d];
+      }
+      n.cell[d] = p;
+    }
+    if (reachable) f(n);
+  }
+}
+
+int build_exchange_items(const Grid& g, int ng, unsigned periodic, unsigned trim, int rank,
+                         std::vector<sgc_motion_item>& out) {
+  if (g.status) return fail(SGC_ERR_ARG, "layout: boxes must tile the domain and divide evenly among ranks");
+  if (rank < 0 || rank >= g.nproc) return fail(SGC_ERR_ARG, "rank out of range");
+  if (ng <= 0) return 0;
+  const int first = rank * g.bpp;
+  for (int gl = first; gl < first + g.bpp; ++gl) {
+    const int c[3] = {gl % g.nb[0], (gl / g.nb[0]) % g.nb[1], gl / (g.nb[0] * g.nb[1])};
+    const IBox local = g.box(gl);
+    const IBox halo = local.grown(ng);
+    // the reference emits all in-grid neighbours of a box before its periodic images
+    for (int want_outside = 0; want_outside < 2; ++want_outside) {
+      for_each_direction(g, c, periodic, trim, [&](const Nbr& n) {
+        if ((int)n.outside != want_outside) return;
+        const int gr = n.cell[0] + g.nb[0] * (n.cell[1] + g.nb[1] * n.cell[2]);
+        const IBox remote = g.box(gr);
+        int shift[3] = {0, 0, 0}, back[3] = {0, 0, 0};
+        if (n.outside)
+          for (int d = 0; d < 3; ++d) {
+            shift[d] = local.lo[d] - remote.lo[d] + n.dir[d] * local.ext(d);
+            back[d] = -shift[d];
+          }
+        const IBox image = remote.shifted(shift);       // where the neighbour appears to be
+        const IBox recv = halo.isect(image);            // ghost cells it covers
+        const IBox send = local.isect(image.grown(ng)); // what the neighbour needs from us
+        const IBox src = recv.shifted(back);            // same cells in the neighbour's frame
+        sgc_motion_item it;
+        it.recv_box = gl;
+        it.send_box = gr;
+        for (int d = 0; d < 3; ++d) {
+          it.recv_lo[d] = recv.lo[d]; it.recv_hi[d] = recv.hi[d];
+          it.src_lo[d] = src.lo[d];   it.src_hi[d] = src.hi[d];
+          it.send_lo[d] = send.lo[d]; it.send_hi[d] = send.hi[d];
+          it.dir[d] = n.dir[d];
+        }
+        it.recv_proc = g.owner(gl);
+        it.send_proc = g.owner(gr);
+        it.tag_send = 27 * gl + (n.dir[0] + 1) + 3 * (n.dir[1] + 1) + 9 * (n.dir[2] + 1);
+        it.tag_recv = 27 * gr + (1 - n.dir[0]) + 3 * (1 - n.dir[1]) + 9 * (1 - n.dir[2]);
+        it.comp_flags = ~0u;
+        out.push_back(it);
+      });
+    }
+  }
+  return 0;
+}
+
+}  // namespace sgc
+
+extern "C" {
+
+const char* sgc_last_error(void) { return sgc::last_error_cstr(); }
+int sgc_abi_version(void) { return SGC_ABI_VERSION; }
+
+int sgc_layout_define(const int dlo[3], const int dhi[3], const int maxbox[3], int nproc, int* boxes6,
+                      int* owner, int cap, int numbox[3]) {
+  if (!dlo || !dhi || !maxbox) return sgc::fail(SGC_ERR_ARG, "sgc_layout_define: null argument");
+  sgc::Grid g(dlo, dhi, maxbox, nproc);
+  if (g.status)
+    return sgc::fail(SGC_ERR_ARG, "sgc_layout_define: boxes must tile the domain and divide evenly among ranks");
+  if (numbox)
+    for (int d = 0; d < 3; ++d) numbox[d] = g.nb[d];
+  for (int i = 0; i < g.nbox && i < cap; ++i) {
+    const sgc::IBox b = g.box(i);
+    if (boxes6)
+      for (int d = 0; d < 3; ++d) { boxes6[6 * i + d] = b.lo[d]; boxes6[6 * i + 3 + d] = b.hi[d]; }
+    if (owner) owner[i] = g.owner(i);
+  }
+  return g.nbox;
+}
+
+int sgc_copier_define(const int dlo[3], const int dhi[3], const int maxbox[3], int nghost, unsigned periodic,
+                      unsigned trim, int nproc, int rank, sgc_motion_item* items, int cap) {
+  if (!dlo || !dhi || !maxbox) return sgc::fail(SGC_ERR_ARG, "sgc_copier_define: null argument");
+  sgc::Grid g(dlo, dhi, maxbox, nproc);
+  std::vector<sgc_motion_item> v;
+  const int st = sgc::build_exchange_items(g, nghost, periodic, trim, rank, v);
+  if (st) return st;
+  for (size_t i = 0; i < v.size() && (int)i < cap; ++i) items[i] = v[i];
+  return (int)v.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+"""CPU-only checks of the product library: it loads, exports every symbol include/sgc_b200.h
+declares, its host-side layout/plan builders agree with the golden vectors from the real reference,
+and the data path fails loudly without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def items_as_matrix(it):
+    """sgc_motion_item array -> the 24-int record layout of the reference shim / golden vectors
+    (local indices and flags are derived by the caller)."""
+    m = np.zeros((len(it), 21), np.int32)
+    m[:, 0], m[:, 1] = it["recv_box"], it["send_box"]
+    m[:, 2:5], m[:, 5:8] = it["recv_lo"], it["recv_hi"]
+    m[:, 8:11], m[:, 11:14] = it["src_lo"], it["src_hi"]
+    m[:, 14:17] = it["dir"]
+    m[:, 17], m[:, 18] = it["recv_proc"], it["send_proc"]
+    m[:, 19], m[:, 20] = it["tag_send"], it["tag_recv"]
+    return m
+
+
+def test_library_exports_every_declared_symbol(sgc):
+    L = sgc.lib()
+    header = open(os.path.join(ROOT, "include", "sgc_b200.h")).read()
+    declared = set(re.findall(r"\b(sgc_[a-z0-9_]+)\s*\(", header))
+    declared -= {"sgc_status"}
+    assert len(declared) >= 45
+    for name in sorted(declared):
+        assert hasattr(L, name), "libsgc_b200.so does not export %s" % name
+    assert set(sgc.SYMBOLS) == declared
+    assert L.sgc_abi_version() == 1
+
+
+def test_no_cpu_fallback(sgc):
+    import ctypes as C
+    L = sgc.lib()
+    try:
+        sgc.init(0)
+        have_gpu = True
+    except sgc.SgcError as e:
+        have_gpu = False
+        assert "no CPU fallback" in str(e)
+    if have_gpu:
+        pytest.skip("a GPU is present")
+    boxes = np.array([[0, 0, 0, 3, 3, 3]], np.int32)
+    h = C.c_void_p()
+    st = L.sgc_level_create(boxes.ctypes.data, 1, 1, 1, 8, 0, C.byref(h))
+    assert st == -2 and b"no CPU fallback" in L.sgc_last_error()
+    assert L.sgc_heat_sweep(None, None, 0.1, 1) == -2
+    assert L.sgc_exchange(None, None) == -2
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "structuredgridcalc-boxframework_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".H")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in src and "sgcoracle" not in src and "sgcref" not in src, f
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
+        for f in files:
+            src = open(os.path.join(dirpath, f), errors="ignore").read()
+            assert "sgcoracle" not in src and "sgcref" not in src, f
+
+
+def test_layout_and_plan_match_reference_golden(sgc, golden):
+    meta, arr = golden
+    for c in meta["plan"]:
+        dbl = sgc.DisjointBoxLayout(sgc.Box(c["dlo"], c["dhi"]), c["maxbox"], c["nproc"], c["rank"])
+        name = c["key"][len("plan_"):].rsplit("_n", 1)[0]
+        assert np.array_equal(dbl.boxes, arr["layout_" + name])
+        it = dbl.copier_items(c["ng"], c["periodic"], c["trim"])
+        ref = arr[c["key"]]
+        assert len(it) == c["nitem"]
+        assert np.array_equal(items_as_matrix(it), ref[:, :21]), c["key"]
+        assert np.array_equal(it["recv_box"] - dbl.localIdxBegin(), ref[:, 21])
+        assert (it["comp_flags"] == 0xFFFFFFFF).all()
+
+
+def test_plan_matches_oracle_including_send_regions(sgc, oracle):
+    rng = np.random.default_rng(7)
+    for _ in range(25):
+        mb = rng.integers(2, 6, 3)
+        nb = rng.integers(1, 5, 3)
+        dlo = rng.integers(-4, 4, 3)
+        dhi = dlo + mb * nb - 1
+        ng = 1 if mb.min() < 2 else int(rng.integers(1, 3))
+        per, trim = int(rng.integers(0, 8)), int(rng.integers(0, 8)) * 2
+        nbox = int(np.prod(nb))
+        nproc = int(rng.choice([p for p in (1, 2, 4) if nbox % p == 0]))
+        for r in range(nproc):
+            dbl = sgc.DisjointBoxLayout(sgc.Box(dlo, dhi), mb, nproc, r)
+            it = dbl.copier_items(ng, per, trim)
+            oi = oracle.copier_items(dlo, dhi, mb, ng, per, trim, nproc, r)
+            assert np.array_equal(items_as_matrix(it), oi[:, :21])
+            assert np.array_equal(it["send_lo"], oi[:, 24:27]) and np.array_equal(it["send_hi"], oi[:, 27:30])
+
+
+def test_layout_rejects_bad_decompositions(sgc):
+    with pytest.raises(sgc.SgcError):
+        sgc.DisjointBoxLayout(sgc.Box((0, 0, 0), (62, 63, 63)), 16)          # DisjointBoxLayout.cpp:104-106
+    with pytest.raises(sgc.SgcError):
+        sgc.DisjointBoxLayout(sgc.Box((0, 0, 0), (63, 63, 63)), 16, nproc=7)  # :125
+
+
+def test_halo_lists_pair_up_across_ranks(sgc):
+    """What rank r sends to q must be, item for item, what q expects to receive from r."""
+    dom = sgc.Box((0, 0, 0), (15, 15, 31))
+    for nproc in (2, 4):
+        for per in (0, 7, 4):
+            lists = [sgc.DisjointBoxLayout(dom, 4, nproc, r).halo_lists(1, per, 0) for r in range(nproc)]
+            for r in range(nproc):
+                for peer, recv, send in lists[r]:
+                    back = [x for x in lists[peer] if x[0] == r]
+                    assert len(back) == 1
+                    _, precv, psend = back[0]
+                    assert np.array_equal(send, precv)       # same items, same order
+                    assert np.array_equal(recv, psend)
+                    assert (recv["send_proc"] == peer).all() and (recv["recv_proc"] == r).all()
