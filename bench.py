@@ -322,7 +322,7 @@ def main():
 
     # e2e: the same job through the C ABI with HOST buffers (pinned): H2D + sweeps + D2H per step
     e2e_ms = []
-    for s in range(a.e2e_steps + 1):
+    for s in range(a.e2e_steps + 1 if a.e2e_steps > 0 else 0):
         barrier()
         ea, eb = sgc.Event(), sgc.Event()
         ea.record()
@@ -340,7 +340,7 @@ def main():
         t = torch.tensor([e2e_t], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_t = float(t[0])
-    e2e = {"value": cells_total * a.sweeps / (e2e_t * 1e-3) / 1e9, "unit": "Gcell-updates/s",
+    e2e = None if not e2e_ms else {"value": cells_total * a.sweeps / (e2e_t * 1e-3) / 1e9, "unit": "Gcell-updates/s",
            "h2d_bytes_per_step": int(2 * A.elems * 8), "d2h_bytes_per_step": int(A.elems * 8), "ms_per_step": e2e_t,
            "call": "sgc_level_upload x2 + sgc_heat_run(%d sweeps) + sgc_level_download, pinned host buffers" % a.sweeps}
 

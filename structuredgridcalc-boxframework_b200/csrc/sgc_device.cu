@@ -122,13 +122,6 @@ static bool same_geometry(const sgc_level_s* a, const sgc_level_s* b) {
   return true;
 }
 
-static bool same_layout(const sgc_level_s* a, const sgc_level_s* b) {
-  if (a->nbox != b->nbox) return false;
-  for (int i = 0; i < a->nbox; ++i)
-    if (memcmp(&a->boxes[i], &b->boxes[i], sizeof(IBox)) != 0) return false;
-  return true;
-}
-
 static bool plan_matches(const sgc_plan_s* p, const sgc_level_s* l) {
   if (p->nbox != l->nbox || p->ncomp != l->ncomp || p->ng != l->ng || p->esz != l->esz) return false;
   for (int i = 0; i < l->nbox; ++i)
@@ -299,12 +292,10 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
   }
   l->elems = off;
   // Arena: fabs exactly contiguous in box order (whole-level H2D/D2H is one memcpy and the
-  // streaming sweep sees one uniform plane sequence).  `lead` elements of padding in front so
-  // that (a) aligned-down bulk loads never leave the allocation and (b) for 8-byte elements the
-  // first valid cell of every row of fab 0 is 16-byte aligned when the pitch allows it.
-  const FabGeom& g0 = l->geom[0];
-  const long long first_valid = (long long)nghost * (1 + g0.n[0] + (long long)g0.n[0] * g0.n[1]);
-  l->lead = 32 + ((first_valid & 1) ? 1 : 0);
+  // streaming sweep sees one uniform plane sequence).  32 elements of padding in front and 64
+  // behind keep the arena 256-byte aligned (bulk copies need 16-byte aligned sources) and give
+  // the kernels slack at both ends.
+  l->lead = 32;
   const size_t bytes = (size_t)(l->lead + l->elems + 64) * elem_bytes;
   cudaError_t e = cudaMalloc(&l->d_base, bytes);
   if (e != cudaSuccess) { delete l; return fail(SGC_ERR_CUDA, std::string("cudaMalloc level arena: ") + cudaGetErrorString(e)); }
@@ -640,7 +631,9 @@ static int check_sweep(sgc_level_s* out, sgc_level_s* in, const char* who) {
   if (!out || !in) return fail(SGC_ERR_ARG, std::string(who) + ": null level");
   if (out->esz != 8 || in->esz != 8) return fail(SGC_ERR_UNSUPPORTED, std::string(who) + ": needs 8-byte Real");
   if (out == in) return fail(SGC_ERR_ARG, std::string(who) + ": in-place sweep is not defined");
-  if (!same_layout(out, in)) return fail(SGC_ERR_GEOMETRY, std::string(who) + ": levels are on different layouts");
+  // The swept region of box b is out's valid box; the two levels need not share a layout (the PR1
+  // driver sweeps B on (2..n-1)^3 from A on (1..n)^3, laplacian.cpp:13-33) but must pair up box by box.
+  if (out->nbox != in->nbox) return fail(SGC_ERR_GEOMETRY, std::string(who) + ": levels have different box counts");
   for (int b = 0; b < out->nbox; ++b)
     if (!fab_contains(in->geom[b], out->boxes[b].grown(1)))
       return fail(SGC_ERR_ARG, std::string(who) + ": input fab must contain grow(box,1)");
