@@ -64,47 +64,65 @@ __device__ __forceinline__ double sd2(double p, double twoc, double m) {   // (p
   return __dadd_rn(__dsub_rn(p, twoc), m);
 }
 
-template <int VNX, int VNY, int NG, int PS, int NS, int NT>
-__global__ void __launch_bounds__(NT, 1)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// NCW consumer warps + 1 producer warp.  Consumer warps never synchronise with each other: a slot
+// of the ring is handed back to the producer through an `empty` mbarrier that counts one arrival
+// per consumer warp, so warps drift apart by up to NS-2 stages and stalls of one warp (store
+// back-pressure, a late plane) do not stop the others.
+// MODE: 0 = the sweep.  1..3 are roofline diagnostics of the same pipeline (env SGC_STREAM_MODE,
+// never used by the product path): 1 = plain copy of the centre value, 2 = loads only, 3 = stores only.
+template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1)
 k_heat_stream(const double* __restrict__ in, double* __restrict__ out, int nstages, int n2, double f, int fma) {
+  constexpr int NT = NCW * 32;                   // consumer threads
   constexpr int N0 = VNX + 2 * NG, N1 = VNY + 2 * NG;
   constexpr int PLANE = N0 * N1;                 // elements per plane
   constexpr int STAGE = PS * PLANE;              // elements per stage
   constexpr uint32_t STAGE_BYTES = STAGE * 8u;
-  constexpr int RING_PLANES = NS * PS;
   constexpr int COLS = VNX * VNY;
-  constexpr int CPT = (COLS + NT - 1) / NT;      // columns per thread
+  constexpr int CPT = (COLS + NT - 1) / NT;      // columns per consumer thread
   static_assert(STAGE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  static_assert(NS >= 3, "two stages are being read while at least one is in flight");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES);
+  uint64_t* empty = full + NS;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s_begin = (int)((long long)blockIdx.x * nstages / gridDim.x);
   const int s_end = (int)((long long)(blockIdx.x + 1) * nstages / gridDim.x);
   if (s_begin >= s_end) return;
+  // stages to load: one before and one after the range (z halo of the first / last output plane)
   const int l_begin = s_begin > 0 ? s_begin - 1 : 0;
   const int l_end = s_end < nstages ? s_end + 1 : nstages;
 
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) mbar_init(full + i, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NCW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  int next_load = l_begin;       // meaningful in thread 0 only
-  auto issue = [&](int t) {
-    const int slot = t % NS;
-    mbar_expect_tx(full + slot, STAGE_BYTES);
-    bulk_g2s(ring + (size_t)slot * STAGE, in + (size_t)t * STAGE, STAGE_BYTES, full + slot);
-  };
-  if (tid == 0) {
-    const int stop = l_begin + NS < l_end ? l_begin + NS : l_end;
-    for (; next_load < stop; ++next_load) issue(next_load);
+  if (warp == NCW) {
+    // ---------------- producer: one lane keeps the ring full ----------------
+    if (lane == 0) {
+      int slot = 0, round = 0;                   // ring slot of stage t is (t - l_begin) % NS
+      for (int t = l_begin; t < l_end; ++t) {
+        if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
+        if (MODE == 3) { mbar_arrive(full + slot); if (++slot == NS) { slot = 0; ++round; } continue; }
+        mbar_expect_tx(full + slot, STAGE_BYTES);
+        bulk_g2s(ring + (size_t)slot * STAGE, in + (size_t)t * STAGE, STAGE_BYTES, full + slot);
+        if (++slot == NS) { slot = 0; ++round; }
+      }
+    }
+    return;
   }
 
+  // ---------------- consumers ----------------
   int soff[CPT];
 #pragma unroll
   for (int m = 0; m < CPT; ++m) {
@@ -112,69 +130,68 @@ k_heat_stream(const double* __restrict__ in, double* __restrict__ out, int nstag
     const int i = idx % VNX, j = idx / VNX;
     soff[m] = (idx < COLS) ? (j + NG) * N0 + (i + NG) : -1;
   }
-  double cc[CPT], zm[CPT];
-  bool primed = false;
+  const int p_lo = s_begin * PS, p_hi = s_end * PS;   // planes whose output this CTA owns
+  int q = l_begin * PS;                                // plane being read as the "z+1" plane
+  int kz = q % n2;                                     // its index inside its fab
+  int slot = 0, prev_slot = 0;
   uint32_t phase = 0;
-  int waited = l_begin - 1;
+  double cc[CPT], zm[CPT];                             // column values at planes q-1 and q-2
+  const double* prev = ring;
+  bool prev_out = false;
 
-  for (int s = s_begin; s < s_end; ++s) {
-    const int need = (s + 1 < l_end) ? s + 1 : l_end - 1;
-    while (waited < need) {
-      ++waited;
-      const int slot = waited % NS;
-      mbar_wait(full + slot, (phase >> slot) & 1u);
-      phase ^= 1u << slot;
-    }
+  for (int t = l_begin; t < l_end; ++t) {
+    mbar_wait(full + slot, (phase >> slot) & 1u);
+    phase ^= 1u << slot;
 #pragma unroll
     for (int p = 0; p < PS; ++p) {
-      const int q = s * PS + p;                 // plane index within this launch
-      const int kz = q % n2;
-      if (kz < NG || kz >= n2 - NG) { primed = false; continue; }
-      const double* __restrict__ pc = ring + (size_t)(q % RING_PLANES) * PLANE;
-      const double* __restrict__ pm = ring + (size_t)((q - 1) % RING_PLANES) * PLANE;
-      const double* __restrict__ pp = ring + (size_t)((q + 1) % RING_PLANES) * PLANE;
-      double* __restrict__ po = out + (size_t)q * PLANE;
-      if (!primed) {
-#pragma unroll
-        for (int m = 0; m < CPT; ++m)
-          if (soff[m] >= 0) { zm[m] = pm[soff[m]]; cc[m] = pc[soff[m]]; }
-        primed = true;
-      }
+      const double* __restrict__ cur = ring + (size_t)(slot * PS + p) * PLANE;
+      const bool emit = prev_out && (q - 1 >= p_lo) && (q - 1 < p_hi);
+      double* __restrict__ po = out + (size_t)(q - 1) * PLANE;
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
         if (soff[m] < 0) continue;
         const int o = soff[m];
-        const double c = cc[m];
-        const double zp = pp[o];
-        const double twoc = __dmul_rn(2.0, c);
-        const double tx = sd2(pc[o + 1], twoc, pc[o - 1]);
-        const double ty = sd2(pc[o + N0], twoc, pc[o - N0]);
-        const double tz = sd2(zp, twoc, zm[m]);
-        const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
-        po[o] = fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
-        zm[m] = c;
+        const double zp = cur[o];
+        if (MODE == 1 || MODE == 3) { if (emit) po[o] = cc[m]; }
+        else if (MODE == 2) { if (emit && zp == 1.2345e300) po[o] = zp; }
+        else if (emit) {
+          const double c = cc[m];
+          const double twoc = __dmul_rn(2.0, c);
+          const double tx = sd2(prev[o + 1], twoc, prev[o - 1]);
+          const double ty = sd2(prev[o + N0], twoc, prev[o - N0]);
+          const double tz = sd2(zp, twoc, zm[m]);
+          const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
+          po[o] = fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+        }
+        zm[m] = cc[m];
         cc[m] = zp;
       }
+      prev = cur;
+      prev_out = (kz >= NG) && (kz < n2 - NG);
+      ++q;
+      if (++kz == n2) kz = 0;
     }
-    __syncthreads();            // every warp is done with stage s-1: its slot may be refilled
-    if (tid == 0) {
-      while (next_load < l_end && next_load - NS <= s - 1) { issue(next_load); ++next_load; }
+    if (t > l_begin) {                           // stage t-1 is no longer read by this warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + prev_slot);
     }
+    prev_slot = slot;
+    if (++slot == NS) slot = 0;
   }
 }
 
-template <int VNX, int VNY, int NG, int PS, int NS, int NT>
+template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0>
 static int launch_cfg(const double* in, double* out, int nstages, int n2, double f, int fma, cudaStream_t s) {
-  constexpr size_t smem = (size_t)NS * PS * (VNX + 2 * NG) * (VNY + 2 * NG) * 8 + NS * 8;
+  constexpr size_t smem = (size_t)NS * PS * (VNX + 2 * NG) * (VNY + 2 * NG) * 8 + 2 * NS * 8;
   static bool configured = false;
-  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NT>;
+  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE>;
   if (!configured) {
     SGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int grid = rt().sm_count;
   if (grid > nstages) grid = nstages;
-  kern<<<grid, NT, smem, s>>>(in, out, nstages, n2, f, fma);
+  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in, out, nstages, n2, f, fma);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
@@ -193,13 +210,21 @@ int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int
   const long long planes = (long long)(box_end - box_begin) * n2;
   if (planes > 0x7fffffffLL) return 1;
   if (getenv("SGC_NO_STREAM")) return 1;
-#define SGC_STREAM_CASE(VX, VY, PS_, NS_, NT_)                                                       \
+#define SGC_STREAM_CASE(VX, VY, PS_, NS_, NCW_)                                                      \
   if (vnx == VX && vny == VY && n2 % PS_ == 0)                                                       \
-    return launch_cfg<VX, VY, 1, PS_, NS_, NT_>(in, out, (int)(planes / PS_), n2, f, fma, s)
-  SGC_STREAM_CASE(64, 64, 1, 6, 512);
-  SGC_STREAM_CASE(32, 32, 2, 10, 512);
-  SGC_STREAM_CASE(16, 16, 6, 12, 256);
-  SGC_STREAM_CASE(8, 8, 10, 24, 64);
+    return launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in, out, (int)(planes / PS_), n2, f, fma, s)
+  if (const char* m = getenv("SGC_STREAM_MODE")) {      // diagnostics only
+    if (vnx == 64 && vny == 64) {
+      const int ns = (int)(planes);
+      if (m[0] == '1') return launch_cfg<64, 64, 1, 1, 6, 16, 1>(in, out, ns, n2, f, fma, s);
+      if (m[0] == '2') return launch_cfg<64, 64, 1, 1, 6, 16, 2>(in, out, ns, n2, f, fma, s);
+      if (m[0] == '3') return launch_cfg<64, 64, 1, 1, 6, 16, 3>(in, out, ns, n2, f, fma, s);
+    }
+  }
+  SGC_STREAM_CASE(64, 64, 1, 6, 16);
+  SGC_STREAM_CASE(32, 32, 2, 10, 16);
+  SGC_STREAM_CASE(16, 16, 6, 12, 8);
+  SGC_STREAM_CASE(8, 8, 10, 24, 2);
 #undef SGC_STREAM_CASE
   return 1;
 }
