@@ -75,28 +75,6 @@ static int load_nccl() {
       return fail(SGC_ERR_COMM, std::string(#expr) + ": " + cm().api.GetErrorString(_r));          \
   } while (0)
 
-// helpers duplicated from sgc_device.cu (kept static there)
-static CopyItem region_item(const FabGeom& gd, const IBox& dreg, int dcomp, const FabGeom& gs, const IBox& sreg,
-                            int scomp, int nc, unsigned flags) {
-  CopyItem c;
-  c.nx = dreg.ext(0); c.ny = dreg.ext(1); c.nz = dreg.ext(2); c.nc = nc;
-  c.dsy = gd.n[0]; c.dsz = gd.n[0] * gd.n[1]; c.dcs = gd.cs;
-  c.ssy = gs.n[0]; c.ssz = gs.n[0] * gs.n[1]; c.scs = gs.cs;
-  c.dst = gd.off + dcomp * gd.cs + (dreg.lo[0] - gd.lo[0]) + (long long)(dreg.lo[1] - gd.lo[1]) * c.dsy +
-          (long long)(dreg.lo[2] - gd.lo[2]) * c.dsz;
-  c.src = gs.off + scomp * gs.cs + (sreg.lo[0] - gs.lo[0]) + (long long)(sreg.lo[1] - gs.lo[1]) * c.ssy +
-          (long long)(sreg.lo[2] - gs.lo[2]) * c.ssz;
-  c.flags = flags;
-  c.c0 = dcomp;
-  return c;
-}
-static FabGeom dense(const IBox& reg, long long off) {
-  FabGeom g;
-  g.off = off;
-  for (int d = 0; d < 3; ++d) { g.lo[d] = reg.lo[d]; g.n[d] = reg.ext(d); g.vlo[d] = reg.lo[d]; g.vn[d] = reg.ext(d); }
-  g.cs = reg.size();
-  return g;
-}
 static IBox box_of(const int lo[3], const int hi[3]) {
   IBox b;
   for (int d = 0; d < 3; ++d) { b.lo[d] = lo[d]; b.hi[d] = hi[d]; }
@@ -148,7 +126,7 @@ int comm_plan_setup(sgc_plan_s* p, sgc_level_s* l, const Grid& g, unsigned perio
     for (const sgc_motion_item& it : h.recv) {
       const IBox r = box_of(it.recv_lo, it.recv_hi);
       const int ld = it.recv_box - l->gidx0;
-      unpack.push_back(region_item(l->geom[ld], r, p->c0, dense(r, pos), r, 0, p->nc, it.comp_flags));
+      make_items(unpack, l->geom[ld], r, p->c0, dense_geom(r, pos), r, 0, p->nc, it.comp_flags);
       pos += r.size() * p->nc;
     }
     peer.recv_elems = pos;
@@ -157,7 +135,7 @@ int comm_plan_setup(sgc_plan_s* p, sgc_level_s* l, const Grid& g, unsigned perio
       const IBox r = box_of(it.src_lo, it.src_hi);
       const int ls = it.send_box - l->gidx0;
       if (ls < 0 || ls >= l->nbox) return fail(SGC_ERR_COMM, "halo: peer asks for a box this rank does not own");
-      pack.push_back(region_item(dense(r, pos), r, 0, l->geom[ls], r, p->c0, p->nc, ~0u));
+      make_items(pack, dense_geom(r, pos), r, 0, l->geom[ls], r, p->c0, p->nc, ~0u);
       pos += r.size() * p->nc;
     }
     peer.send_elems = pos;

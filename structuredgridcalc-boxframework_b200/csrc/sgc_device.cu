@@ -84,35 +84,70 @@ int CopyTable::upload(const std::vector<CopyItem>& items) {
   return 0;
 }
 
-// Region-copy descriptor between two fabs (both described by their FabGeom).
-static CopyItem make_item(const FabGeom& gd, const IBox& dreg, int dcomp, const FabGeom& gs, const IBox& sreg, int scomp,
-                          int nc, unsigned flags) {
-  CopyItem c;
-  c.nx = dreg.ext(0); c.ny = dreg.ext(1); c.nz = dreg.ext(2); c.nc = nc;
-  c.dsy = gd.n[0]; c.dsz = gd.n[0] * gd.n[1]; c.dcs = gd.cs;
-  c.ssy = gs.n[0]; c.ssz = gs.n[0] * gs.n[1]; c.scs = gs.cs;
-  c.dst = gd.off + dcomp * gd.cs + (dreg.lo[0] - gd.lo[0]) + (long long)(dreg.lo[1] - gd.lo[1]) * c.dsy +
-          (long long)(dreg.lo[2] - gd.lo[2]) * c.dsz;
-  c.src = gs.off + scomp * gs.cs + (sreg.lo[0] - gs.lo[0]) + (long long)(sreg.lo[1] - gs.lo[1]) * c.ssy +
-          (long long)(sreg.lo[2] - gs.lo[2]) * c.ssz;
-  c.flags = flags;
-  c.c0 = dcomp;
-  return c;
-}
-
-// A dense buffer holding `reg` for nc components in wire order comp->k->j->i, starting at element `off`.
-static FabGeom dense_geom(const IBox& reg, long long off) {
+FabGeom level_fab_geom(const IBox& valid, int ng, long long off, long long xoff) {
   FabGeom g;
+  const IBox f = valid.grown(ng);
+  for (int d = 0; d < 3; ++d) { g.lo[d] = f.lo[d]; g.n[d] = f.ext(d); g.vlo[d] = valid.lo[d]; g.vn[d] = valid.ext(d); }
+  g.ngx = ng;
+  g.mx = g.n[0] - 2 * ng;
+  g.cs = (long long)g.mx * g.n[1] * g.n[2];
+  g.xcs = (long long)2 * ng * g.n[1] * g.n[2];
   g.off = off;
-  for (int d = 0; d < 3; ++d) { g.lo[d] = reg.lo[d]; g.n[d] = reg.ext(d); g.vlo[d] = reg.lo[d]; g.vn[d] = reg.ext(d); }
-  g.cs = reg.size();
+  g.xoff = xoff;
   return g;
 }
 
-static bool fab_contains(const FabGeom& g, const IBox& r) {
+// A dense buffer holding `reg` in wire order comp->k->j->i, starting at element `off`.
+FabGeom dense_geom(const IBox& reg, long long off) {
+  FabGeom g;
+  for (int d = 0; d < 3; ++d) { g.lo[d] = reg.lo[d]; g.n[d] = reg.ext(d); g.vlo[d] = reg.lo[d]; g.vn[d] = reg.ext(d); }
+  g.ngx = 0;
+  g.mx = g.n[0];
+  g.cs = reg.size();
+  g.xcs = 0;
+  g.off = off;
+  g.xoff = 0;
+  return g;
+}
+
+bool fab_contains(const FabGeom& g, const IBox& r) {
   for (int d = 0; d < 3; ++d)
     if (r.lo[d] < g.lo[d] || r.hi[d] >= g.lo[d] + g.n[d]) return false;
   return true;
+}
+
+// Strides of the block that holds fab-relative x index i: main (1, mx, mx*n1) or xg (n2*n1, 1, n1).
+static void block_strides(const FabGeom& g, int i, int& sx, int& sy, int& sz, long long& cs) {
+  const int vi = i - g.ngx;
+  if (vi >= 0 && vi < g.mx) { sx = 1; sy = g.mx; sz = g.mx * g.n[1]; cs = g.cs; }
+  else { sx = g.n[2] * g.n[1]; sy = 1; sz = g.n[1]; cs = g.xcs; }
+}
+
+void make_items(std::vector<CopyItem>& out, const FabGeom& gd, const IBox& dreg, int dcomp, const FabGeom& gs,
+                const IBox& sreg, int scomp, int nc, unsigned flags) {
+  // cut the x range where either side changes block (low ghost columns | valid columns | high ghost columns)
+  const int nx = dreg.ext(0);
+  int cuts[6], ncut = 0;
+  cuts[ncut++] = 0;
+  const int dx0 = dreg.lo[0] - gd.lo[0], sx0 = sreg.lo[0] - gs.lo[0];   // fab-relative x of the region origin
+  const int cand[4] = {gd.ngx - dx0, gd.ngx + gd.mx - dx0, gs.ngx - sx0, gs.ngx + gs.mx - sx0};
+  for (int c : cand)
+    if (c > 0 && c < nx) cuts[ncut++] = c;
+  cuts[ncut++] = nx;
+  std::sort(cuts, cuts + ncut);
+  for (int p = 0; p + 1 < ncut; ++p) {
+    const int x0 = cuts[p], x1 = cuts[p + 1];
+    if (x1 <= x0) continue;
+    CopyItem c;
+    c.nx = x1 - x0; c.ny = dreg.ext(1); c.nz = dreg.ext(2); c.nc = nc;
+    block_strides(gd, dx0 + x0, c.dsx, c.dsy, c.dsz, c.dcs);
+    block_strides(gs, sx0 + x0, c.ssx, c.ssy, c.ssz, c.scs);
+    c.dst = fab_index(gd, dx0 + x0, dreg.lo[1] - gd.lo[1], dreg.lo[2] - gd.lo[2], dcomp);
+    c.src = fab_index(gs, sx0 + x0, sreg.lo[1] - gs.lo[1], sreg.lo[2] - gs.lo[2], scomp);
+    c.flags = flags;
+    c.c0 = dcomp;
+    out.push_back(c);
+  }
 }
 
 static bool same_geometry(const sgc_level_s* a, const sgc_level_s* b) {
@@ -176,6 +211,9 @@ int sgc_shutdown(void) {
   cudaDeviceSynchronize();
   if (r.compute) cudaStreamDestroy(r.compute);
   if (r.comm) cudaStreamDestroy(r.comm);
+  if (r.d_stage) cudaFree(r.d_stage);
+  for (ProfLog& L : r.prof)
+    for (size_t i = 0; i < L.a.size(); ++i) { cudaEventDestroy(L.a[i]); cudaEventDestroy(L.b[i]); }
   r = Runtime();
   return 0;
 }
@@ -273,34 +311,52 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
   sgc_level_s* l = new sgc_level_s;
   l->nbox = nbox; l->ncomp = ncomp; l->ng = nghost; l->esz = elem_bytes; l->gidx0 = global_index0;
   l->boxes.resize(nbox); l->off.resize(nbox); l->geom.resize(nbox);
-  long long off = 0;
+  long long off = 0, moff = 0, xoff = 0;
   for (int b = 0; b < nbox; ++b) {
     const IBox v = IBox::from6(boxes6 + 6 * b);
     if (v.empty()) { delete l; return fail(SGC_ERR_ARG, "sgc_level_create: empty box"); }
-    const IBox f = v.grown(nghost);
     l->boxes[b] = v;
     l->off[b] = off;
     FabGeom& g = l->geom[b];
-    g.off = off; g.cs = f.size();
-    for (int d = 0; d < 3; ++d) { g.lo[d] = f.lo[d]; g.n[d] = f.ext(d); g.vlo[d] = v.lo[d]; g.vn[d] = v.ext(d); }
-    if (g.cs * ncomp > 0x7fffffffLL) {   // the reference indexes with int; we keep its limit per fab
+    g = level_fab_geom(v, nghost, moff, xoff);           // xoff is rebased below
+    const long long fab_elems = (long long)g.n[0] * g.n[1] * g.n[2];
+    if (fab_elems * ncomp > 0x7fffffffLL) {   // the reference indexes with int; we keep its limit per fab
       delete l;
       return fail(SGC_ERR_UNSUPPORTED, "sgc_level_create: a single fab exceeds 2^31 elements");
     }
     if (b && memcmp(l->geom[0].n, g.n, sizeof g.n) != 0) l->uniform = false;
-    off += g.cs * ncomp;
+    off += fab_elems * ncomp;
+    moff += g.cs * ncomp;
+    xoff += g.xcs * ncomp;
   }
   l->elems = off;
-  // Arena: fabs exactly contiguous in box order (whole-level H2D/D2H is one memcpy and the
-  // streaming sweep sees one uniform plane sequence).  32 elements of padding in front and 64
-  // behind keep the arena 256-byte aligned (bulk copies need 16-byte aligned sources) and give
-  // the kernels slack at both ends.
+  // Arena (split-x layout, sgc_device.h): the main blocks of all fabs back to back in box order —
+  // for a uniform level one homogeneous sequence of z-planes, which is what the streaming sweep
+  // walks — then, 512-byte aligned, the xg blocks of all fabs.  32 elements of padding in front and
+  // 64 behind keep bulk copies 16-byte aligned and give the kernels slack at both ends.
   l->lead = 32;
-  const size_t bytes = (size_t)(l->lead + l->elems + 64) * elem_bytes;
+  l->main_elems = moff;
+  l->xg_base = (moff + 63) / 64 * 64;
+  l->arena_elems = l->xg_base + xoff;
+  for (int b = 0; b < nbox; ++b) l->geom[b].xoff += l->xg_base;
+  const size_t bytes = (size_t)(l->lead + l->arena_elems + 64) * elem_bytes;
   cudaError_t e = cudaMalloc(&l->d_base, bytes);
   if (e != cudaSuccess) { delete l; return fail(SGC_ERR_CUDA, std::string("cudaMalloc level arena: ") + cudaGetErrorString(e)); }
   cudaMemsetAsync(l->d_base, 0, bytes, rt().compute);
   l->d_arena = (char*)l->d_base + l->lead * elem_bytes;
+  {
+    // conversion tables: reference-order staging (fab b at element off[b]) <-> arena
+    std::vector<CopyItem> cin, cout;
+    for (int b = 0; b < nbox; ++b) {
+      const IBox f = l->boxes[b].grown(nghost);
+      const FabGeom dg = dense_geom(f, l->off[b]);
+      make_items(cin, l->geom[b], f, 0, dg, f, 0, ncomp, ~0u);
+      make_items(cout, dg, f, 0, l->geom[b], f, 0, ncomp, ~0u);
+    }
+    int st = l->conv_in.upload(cin);
+    if (!st) st = l->conv_out.upload(cout);
+    if (st) { sgc_level_destroy(l); return st; }
+  }
   e = cudaMalloc(&l->d_geom, sizeof(FabGeom) * (size_t)nbox);
   if (e == cudaSuccess) e = cudaMemcpy(l->d_geom, l->geom.data(), sizeof(FabGeom) * (size_t)nbox, cudaMemcpyHostToDevice);
   // sweep work table for the generic kernel: (box, y0, z0) tiles of the valid region
@@ -327,6 +383,8 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
 int sgc_level_destroy(sgc_level_t l) {
   if (!l) return 0;
   if (rt().ready) cudaStreamSynchronize(rt().compute);
+  l->conv_in.release();
+  l->conv_out.release();
   if (l->d_base) cudaFree(l->d_base);
   if (l->d_geom) cudaFree(l->d_geom);
   if (l->d_work) cudaFree(l->d_work);
@@ -342,30 +400,58 @@ long long sgc_level_fab_offset(sgc_level_t l, int box) {
 }
 void* sgc_level_device_ptr(sgc_level_t l, int box) {
   if (!l || box < 0 || box >= l->nbox) return nullptr;
-  return (char*)l->d_arena + l->off[box] * l->esz;
+  return (char*)l->d_arena + l->geom[box].off * l->esz;     // main block of the fab (split-x layout)
+}
+
+static int ensure_stage(size_t bytes) {
+  Runtime& r = rt();
+  if (r.stage_bytes >= bytes) return 0;
+  SGC_CUDA(cudaStreamSynchronize(r.compute));
+  if (r.d_stage) cudaFree(r.d_stage);
+  r.d_stage = nullptr; r.stage_bytes = 0;
+  SGC_CUDA(cudaMalloc(&r.d_stage, bytes));
+  r.stage_bytes = bytes;
+  return 0;
+}
+
+// one fab <-> dense reference-order buffer at element 0 of `buf`
+static int convert_box(sgc_level_s* l, int box, void* buf, bool to_device) {
+  const IBox f = l->boxes[box].grown(l->ng);
+  const FabGeom dg = dense_geom(f, 0);
+  std::vector<CopyItem> v;
+  if (to_device) make_items(v, l->geom[box], f, 0, dg, f, 0, l->ncomp, ~0u);
+  else make_items(v, dg, f, 0, l->geom[box], f, 0, l->ncomp, ~0u);
+  CopyTable t;
+  int st = t.upload(v);
+  if (!st) st = to_device ? launch_copy(t, l->d_arena, buf, l->esz, rt().compute)
+                          : launch_copy(t, buf, l->d_arena, l->esz, rt().compute);
+  if (!st) cudaStreamSynchronize(rt().compute);
+  t.release();
+  return st;
 }
 
 int sgc_level_upload(sgc_level_t l, int box, const void* host) {
   SGC_REQUIRE_RT();
   if (!l || !host || box < -1 || box >= l->nbox) return fail(SGC_ERR_ARG, "sgc_level_upload: bad argument");
-  if (box < 0) {
-    SGC_CUDA(cudaMemcpyAsync(l->d_arena, host, (size_t)l->elems * l->esz, cudaMemcpyHostToDevice, rt().compute));
-  } else {
-    SGC_CUDA(cudaMemcpyAsync((char*)l->d_arena + l->off[box] * l->esz, host,
-                             (size_t)l->geom[box].cs * l->ncomp * l->esz, cudaMemcpyHostToDevice, rt().compute));
-  }
-  return 0;
+  const long long n = box < 0 ? l->elems : (long long)l->geom[box].n[0] * l->geom[box].n[1] * l->geom[box].n[2] * l->ncomp;
+  int st = ensure_stage((size_t)n * l->esz);
+  if (st) return st;
+  // H2D in the reference's memory order, then one batched kernel into the split-x arena
+  SGC_CUDA(cudaMemcpyAsync(rt().d_stage, host, (size_t)n * l->esz, cudaMemcpyHostToDevice, rt().compute));
+  if (box < 0) return launch_copy(l->conv_in, l->d_arena, rt().d_stage, l->esz, rt().compute);
+  return convert_box(l, box, rt().d_stage, true);
 }
 
 int sgc_level_download(sgc_level_t l, int box, void* host) {
   SGC_REQUIRE_RT();
   if (!l || !host || box < -1 || box >= l->nbox) return fail(SGC_ERR_ARG, "sgc_level_download: bad argument");
-  if (box < 0) {
-    SGC_CUDA(cudaMemcpyAsync(host, l->d_arena, (size_t)l->elems * l->esz, cudaMemcpyDeviceToHost, rt().compute));
-  } else {
-    SGC_CUDA(cudaMemcpyAsync(host, (char*)l->d_arena + l->off[box] * l->esz,
-                             (size_t)l->geom[box].cs * l->ncomp * l->esz, cudaMemcpyDeviceToHost, rt().compute));
-  }
+  const long long n = box < 0 ? l->elems : (long long)l->geom[box].n[0] * l->geom[box].n[1] * l->geom[box].n[2] * l->ncomp;
+  int st = ensure_stage((size_t)n * l->esz);
+  if (st) return st;
+  st = box < 0 ? launch_copy(l->conv_out, rt().d_stage, l->d_arena, l->esz, rt().compute)
+               : convert_box(l, box, rt().d_stage, false);
+  if (st) return st;
+  SGC_CUDA(cudaMemcpyAsync(host, rt().d_stage, (size_t)n * l->esz, cudaMemcpyDeviceToHost, rt().compute));
   SGC_CUDA(cudaStreamSynchronize(rt().compute));
   return 0;
 }
@@ -374,14 +460,18 @@ int sgc_level_setval(sgc_level_t l, int box, int comp, const void* value) {
   SGC_REQUIRE_RT();
   if (!l || !value || box < -1 || box >= l->nbox || comp < -1 || comp >= l->ncomp)
     return fail(SGC_ERR_ARG, "sgc_level_setval: bad argument");
-  if (comp < 0) {
-    if (box < 0) return launch_fill(l->d_arena, l->elems, l->esz, value, rt().compute);
-    return launch_fill((char*)l->d_arena + l->off[box] * l->esz, l->geom[box].cs * l->ncomp, l->esz, value, rt().compute);
-  }
   const int b0 = box < 0 ? 0 : box, b1 = box < 0 ? l->nbox : box + 1;
+  if (comp < 0 && box < 0) {
+    int st = launch_fill(l->d_arena, l->main_elems, l->esz, value, rt().compute);
+    if (!st && l->arena_elems > l->xg_base)
+      st = launch_fill((char*)l->d_arena + l->xg_base * l->esz, l->arena_elems - l->xg_base, l->esz, value, rt().compute);
+    return st;
+  }
   for (int b = b0; b < b1; ++b) {
-    const int st = launch_fill((char*)l->d_arena + (l->off[b] + comp * l->geom[b].cs) * l->esz, l->geom[b].cs, l->esz,
-                               value, rt().compute);
+    const FabGeom& g = l->geom[b];
+    const int c0 = comp < 0 ? 0 : comp, nc = comp < 0 ? l->ncomp : 1;
+    int st = launch_fill((char*)l->d_arena + (g.off + c0 * g.cs) * l->esz, g.cs * nc, l->esz, value, rt().compute);
+    if (!st && g.xcs) st = launch_fill((char*)l->d_arena + (g.xoff + c0 * g.xcs) * l->esz, g.xcs * nc, l->esz, value, rt().compute);
     if (st) return st;
   }
   return 0;
@@ -404,7 +494,8 @@ int sgc_fab_copy(sgc_level_t dst, int dst_box, const int dlo[3], const int dhi[3
   if (!fab_contains(gd, dr) || !fab_contains(gs, sr)) return fail(SGC_ERR_ARG, "sgc_fab_copy: region outside fab");
   if (dst_comp < 0 || src_comp < 0 || ncomp < 1 || dst_comp + ncomp > dst->ncomp || src_comp + ncomp > src->ncomp)
     return fail(SGC_ERR_ARG, "sgc_fab_copy: component range");
-  std::vector<CopyItem> v(1, make_item(gd, dr, dst_comp, gs, sr, src_comp, ncomp, comp_flags));
+  std::vector<CopyItem> v;
+  make_items(v, gd, dr, dst_comp, gs, sr, src_comp, ncomp, comp_flags);
   CopyTable t;
   int st = t.upload(v);
   if (!st) st = launch_copy(t, dst->d_arena, src->d_arena, dst->esz, rt().compute);
@@ -428,7 +519,7 @@ static int linear_io(sgc_level_t l, int box, const int rlo[3], const int rhi[3],
   for (int c = c0; c < c1; ++c) {
     if (!(c >= 32 || ((flags >> c) & 1u))) continue;
     const FabGeom bg = dense_geom(r, pos);
-    v.push_back(out ? make_item(bg, r, 0, g, r, c, 1, ~0u) : make_item(g, r, c, bg, r, 0, 1, ~0u));
+    if (out) make_items(v, bg, r, 0, g, r, c, 1, ~0u); else make_items(v, g, r, c, bg, r, 0, 1, ~0u);
     pos += r.size();
   }
   if (pos == 0) return 0;
@@ -488,7 +579,7 @@ static int upload_local_items(sgc_plan_s* p, sgc_level_s* l) {
     if (dr.empty()) continue;
     if (!fab_contains(l->geom[ld], dr) || !fab_contains(l->geom[ls], sr))
       return fail(SGC_ERR_ARG, "plan: motion item region outside its fab (nghost of the level too small?)");
-    v.push_back(make_item(l->geom[ld], dr, p->c0, l->geom[ls], sr, p->c0, p->nc, it.comp_flags));
+    make_items(v, l->geom[ld], dr, p->c0, l->geom[ls], sr, p->c0, p->nc, it.comp_flags);
   }
   p->n_boundary_boxes = 0;
   for (char c : p->box_is_boundary) p->n_boundary_boxes += c;

@@ -13,25 +13,51 @@
 
 namespace sgc {
 
-// One entry of the device box table: where fab b lives and which cells are valid.
+// ---------------------------------------------------------------------------------------------
+// Device layout of a fab ("split-x").  The reference stores a fab as one Fortran array over the
+// box grown by nghost (BaseFab.H:277-313), so consecutive valid rows are separated by 2*nghost
+// ghost cells and every row of a sweep's output starts and ends inside a 32-byte DRAM sector
+// shared with ghost cells: measured on B200, writing such rows runs at 2.5 TB/s against 5.3 TB/s
+// for dense rows (profiles/micro/store_patterns.cu).  On the device a fab is therefore two blocks:
+//   main : x restricted to the VALID columns, y and z over the grown box:
+//            main[c*cs + (k*n1 + j)*mx + (i - ngx)],  mx = n0 - 2*ngx
+//          rows are dense (64 doubles = 512 B for a 64^3 box), so a sweep writes whole sectors;
+//   xg   : the 2*ngx ghost columns in x, as [side/ghost layer g][k][j]:
+//            xg[c*xcs + (g*n2 + k)*n1 + j],  g = i for the low side, i - mx for the high side
+//          so the x-halo of one z-plane is one contiguous strip per side.
+// (i,j,k) are fab-relative (0-based from the grown box's lower corner).  Host memory always uses
+// the reference order; sgc_level_upload/download convert.  A dense buffer (pack buffers, the
+// upload staging area) is the same struct with ngx = 0.
+// ---------------------------------------------------------------------------------------------
 struct FabGeom {
-  long long off;   // element offset of the fab's first element (comp 0) in the level arena
-  long long cs;    // component stride = n[0]*n[1]*n[2]   (BaseFab::getComponentStride)
+  long long off;   // element offset of the main block (comp 0) in the level arena
+  long long xoff;  // element offset of the xg block (comp 0)
+  long long cs;    // main component stride = mx*n1*n2
+  long long xcs;   // xg component stride = 2*ngx*n1*n2
   int lo[3];       // lower corner of the fab box (= valid box grown by nghost)
-  int n[3];        // extents of the fab box; x pitch = n[0], plane pitch = n[0]*n[1]
+  int n[3];        // extents of the fab box
   int vlo[3];      // lower corner of the valid box
   int vn[3];       // extents of the valid box
+  int ngx;         // ghost columns per side kept in the xg block
+  int mx;          // x extent of the main block = n[0] - 2*ngx
 };
 
-// One region copy dst[region, c] = src[region + shift, c] — a Motion2Way, a BaseFab::copy, a
-// linearOut/linearIn (the buffer side is a dense box) or a physical-BC face copy.
+__host__ __device__ inline long long fab_index(const FabGeom& g, int i, int j, int k, int c) {
+  const int vi = i - g.ngx;
+  if (vi >= 0 && vi < g.mx) return g.off + c * g.cs + ((long long)k * g.n[1] + j) * g.mx + vi;
+  const int gi = vi < 0 ? i : i - g.mx;
+  return g.xoff + c * g.xcs + ((long long)gi * g.n[2] + k) * g.n[1] + j;
+}
+
+// One strided region copy dst[x,y,z,c] = src[x,y,z,c] — (a piece of) a Motion2Way, a
+// BaseFab::copy, a linearOut/linearIn, an upload/download conversion or a physical-BC face copy.
 struct CopyItem {
-  long long dst;   // element offset of the region origin, component c0, in the dst arena
+  long long dst;   // element offset of the region origin, first component, in the dst arena
   long long src;   // same in the src arena
   long long dcs, scs;   // component strides
   int nx, ny, nz, nc;   // region extents and number of components
-  int dsy, dsz;    // dst row / plane pitch (elements)
-  int ssy, ssz;    // src row / plane pitch
+  int dsx, dsy, dsz;    // dst strides (elements) along x, y, z
+  int ssx, ssy, ssz;    // src strides
   unsigned flags;  // component mask, bit = absolute destination component (BaseFab.cpp:320)
   int c0;          // first destination component (for the mask test)
 };
@@ -46,6 +72,14 @@ struct CopyTable {
   void release();
   int upload(const std::vector<CopyItem>& items);
 };
+
+// geometry helpers (sgc_device.cu)
+FabGeom level_fab_geom(const IBox& valid, int ng, long long off, long long xoff);
+FabGeom dense_geom(const IBox& reg, long long off);
+bool fab_contains(const FabGeom& g, const IBox& r);
+// append the pieces of dst[dreg, dcomp..] = src[sreg, scomp..] (regions in index space, equal extents)
+void make_items(std::vector<CopyItem>& out, const FabGeom& gd, const IBox& dreg, int dcomp, const FabGeom& gs,
+                const IBox& sreg, int scomp, int nc, unsigned flags);
 
 constexpr int kCopyChunk = 2048;       // cells per CTA of the batched copy kernel
 constexpr int kCopyThreads = 256;
@@ -62,6 +96,8 @@ struct ProfScope {          // RAII: records the pair around one launch when pro
 };
 
 struct Runtime {
+  void* d_stage = nullptr;              // reference-order staging area for upload / download
+  size_t stage_bytes = 0;
   bool profiling = false;
   ProfLog prof[2];
   bool ready = false;
@@ -101,7 +137,11 @@ struct sgc_level_s {
   long long elems = 0;                  // total elements, all fabs and comps
   long long lead = 0;                   // elements of padding before fab 0 in the arena
   void* d_base = nullptr;               // cudaMalloc'ed block
-  void* d_arena = nullptr;              // = d_base + lead*esz : fab b at element off[b]
+  void* d_arena = nullptr;              // = d_base + lead*esz; main blocks of all fabs, then all xg blocks
+  long long main_elems = 0;             // elements in the main region (xg region starts here, padded)
+  long long xg_base = 0;                // element offset of the xg region in the arena
+  long long arena_elems = 0;            // main + xg (+ padding)
+  sgc::CopyTable conv_in, conv_out;     // reference-order staging <-> split-x arena, whole level
   sgc::FabGeom* d_geom = nullptr;
   std::vector<sgc::FabGeom> geom;
   bool uniform = true;                  // all fabs have the same extents

@@ -45,8 +45,8 @@ k_copy_items(const CopyItem* __restrict__ items, const long long* __restrict__ c
     const unsigned c = r / nz;
     const unsigned dc = I->c0 + c;
     if (dc < 32u && !((I->flags >> dc) & 1u)) continue;
-    const long long d = I->dst + c * I->dcs + x + (long long)y * I->dsy + (long long)z * I->dsz;
-    const long long s = I->src + c * I->scs + x + (long long)y * I->ssy + (long long)z * I->ssz;
+    const long long d = I->dst + c * I->dcs + (long long)x * I->dsx + (long long)y * I->dsy + (long long)z * I->dsz;
+    const long long s = I->src + c * I->scs + (long long)x * I->ssx + (long long)y * I->ssy + (long long)z * I->ssz;
     dst_arena[d] = src_arena[s];
   }
 }
@@ -146,7 +146,9 @@ __device__ __forceinline__ double d2(double p, double c, double m) {
   return __dadd_rn(__dsub_rn(p, __dmul_rn(2.0, c)), m);
 }
 
-// AUX: 0 none, 1 = read old value of out (read-modify-write), 2 = third level with in geometry
+// AUX: 0 none, 1 = read old value of out (read-modify-write), 2 = third level with in geometry.
+// Fabs are in the split-x device layout: x neighbours of the first / last valid column of the
+// input fab come from its xg block, everything else from the main block (fab_index()).
 template <class Op, int AUX>
 __global__ void __launch_bounds__(kTileX * kTileY)
 k_sweep7(const int* __restrict__ work, const FabGeom* __restrict__ gin, const FabGeom* __restrict__ gout,
@@ -156,29 +158,35 @@ k_sweep7(const int* __restrict__ work, const FabGeom* __restrict__ gin, const Fa
   const int y = y0 + threadIdx.y;
   if (y >= GO.vn[1]) return;
   const int zend = min(z0 + kTileZ, GO.vn[2]);
-  const long long isy = GI.n[0], isz = (long long)GI.n[0] * GI.n[1];
-  const long long osy = GO.n[0], osz = (long long)GO.n[0] * GO.n[1];
-  // offsets of valid cell (0, y, z0) of this box in the in / out fabs
-  const long long ibase = GI.off + (GO.vlo[0] - GI.lo[0]) + (GO.vlo[1] + y - GI.lo[1]) * isy +
-                          (long long)(GO.vlo[2] + z0 - GI.lo[2]) * isz;
-  const long long obase = GO.off + (GO.vlo[0] - GO.lo[0]) + (GO.vlo[1] + y - GO.lo[1]) * osy +
-                          (long long)(GO.vlo[2] + z0 - GO.lo[2]) * osz;
+  // fab-relative coordinates of valid cell (0, y, z0) of this box in the in / out fabs
+  const int ix0 = GO.vlo[0] - GI.lo[0], iy = GO.vlo[1] + y - GI.lo[1], iz0 = GO.vlo[2] + z0 - GI.lo[2];
+  const int ox0 = GO.vlo[0] - GO.lo[0], oy = GO.vlo[1] + y - GO.lo[1], oz0 = GO.vlo[2] + z0 - GO.lo[2];
   for (int x = threadIdx.x; x < GO.vn[0]; x += kTileX) {
-    const double* __restrict__ p = in + ibase + x;
-    double* __restrict__ q = out + obase + x;
-    const double* __restrict__ a = (AUX == 2) ? aux + ibase + x : nullptr;
-    double zm = __ldg(p - isz), c = __ldg(p);
+    const int ix = ix0 + x;
+    // the centre column and its y / z neighbours live in one block of the in fab; strides there:
+    const bool cmain = (ix >= GI.ngx) && (ix < GI.ngx + GI.mx);
+    const long long sy = cmain ? GI.mx : 1, sz = cmain ? (long long)GI.mx * GI.n[1] : GI.n[1];
+    const double* __restrict__ p = in + fab_index(GI, ix, iy, iz0, 0);
+    const double* __restrict__ pxm = in + fab_index(GI, ix - 1, iy, iz0, 0);
+    const double* __restrict__ pxp = in + fab_index(GI, ix + 1, iy, iz0, 0);
+    const bool mmain = (ix - 1 >= GI.ngx) && (ix - 1 < GI.ngx + GI.mx), pmain = (ix + 1 >= GI.ngx) && (ix + 1 < GI.ngx + GI.mx);
+    const long long szm = mmain ? (long long)GI.mx * GI.n[1] : GI.n[1], szp = pmain ? (long long)GI.mx * GI.n[1] : GI.n[1];
+    double* __restrict__ q = out + fab_index(GO, ox0 + x, oy, oz0, 0);
+    const bool omain = (ox0 + x >= GO.ngx) && (ox0 + x < GO.ngx + GO.mx);
+    const long long osz = omain ? (long long)GO.mx * GO.n[1] : GO.n[1];
+    const double* __restrict__ a = (AUX == 2) ? aux + fab_index(GI, ix, iy, iz0, 0) : nullptr;
+    double zm = __ldg(p - sz), c = __ldg(p);
     for (int z = z0; z < zend; ++z) {
-      const double zp = __ldg(p + isz);
-      const double tx = d2(__ldg(p + 1), c, __ldg(p - 1));
-      const double ty = d2(__ldg(p + isy), c, __ldg(p - isy));
+      const double zp = __ldg(p + sz);
+      const double tx = d2(__ldg(pxp), c, __ldg(pxm));
+      const double ty = d2(__ldg(p + sy), c, __ldg(p - sy));
       const double tz = d2(zp, c, zm);
       double av = 0.0;
       if (AUX == 1) av = *q;
-      if (AUX == 2) { av = __ldg(a); a += isz; }
+      if (AUX == 2) { av = __ldg(a); a += sz; }
       *q = op(c, tx, ty, tz, av);
       zm = c; c = zp;
-      p += isz; q += osz;
+      p += sz; pxm += szm; pxp += szp; q += osz;
     }
   }
 }

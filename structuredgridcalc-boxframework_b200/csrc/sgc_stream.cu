@@ -1,26 +1,29 @@
 // sgc_stream.cu — the bandwidth-tuned 7-point sweep for uniform levels (BASELINE configs 2-5).
 //
-// Data model exploited: all fabs of a level are contiguous in one arena, each in the reference's
-// Fortran order with its ghost shell INSIDE the fab (LevelData.H:266-271).  A z-plane of a fab
-// (n0*n1 doubles, halo rows and columns included) is therefore one contiguous run of bytes, and
-// the whole level is one uniform sequence of planes: plane q = (box q / n2, fab plane q % n2).
+// Data model exploited (split-x device layout, sgc_device.h): the main blocks of all fabs of a level
+// are contiguous, each a stack of z-planes of n1 dense rows of the VALID x columns, so the whole
+// level is one homogeneous sequence of planes: plane q = (box q / n2, fab plane q % n2); the two
+// x-ghost columns of a plane are one contiguous strip of n1 values per side in the fab's xg block.
 //
-// Kernel shape (persistent, one CTA per SM):
-//   * the plane sequence of the launch is cut into `gridDim.x` contiguous ranges of stages
-//     (a stage = PS planes); CTA c streams its range through a ring of NS stages in shared memory;
-//   * loads are 1-D bulk async copies (cp.async.bulk, the TMA engine: SASS UBLKCP) of one whole
-//     stage each, completion signalled on an mbarrier per ring slot; NS-3 stages (~100 KB) are in
-//     flight per SM while three are being read, which covers HBM latency at full bandwidth
-//     without tying up registers;
-//   * every thread owns CPT columns (x,y) of the box and marches along z: the centre and z-1
-//     values roll through registers, z+1 / x±1 / y±1 come from shared memory (conflict-free:
-//     lanes of a warp read consecutive doubles); results go straight to global memory, a warp
-//     storing 32 consecutive doubles of one row;
+// Kernel shape (persistent, one CTA per SM, warp specialised):
+//   * the plane sequence of the launch is cut into `gridDim.x` contiguous ranges of stages (a stage
+//     = PS planes); CTA c streams its range through a ring of NS stages in shared memory;
+//   * a producer warp issues, per stage, three 1-D bulk async copies (cp.async.bulk, the TMA
+//     engine: SASS UBLKCP) — the planes and the two x-ghost strips — completing on one `full`
+//     mbarrier per ring slot; NS-2 stages (~140 KB) are in flight per SM, which covers HBM latency
+//     at full bandwidth without tying up registers;
+//   * consumer warps never synchronise with each other: every thread owns CPT columns (x,y) and
+//     marches along z with the centre and z-1 values rolling through registers; z+1, x±1 and y±1
+//     come from shared memory (conflict-free: lanes of a warp read consecutive doubles); a ring
+//     slot goes back to the producer through an `empty` mbarrier counting one arrival per warp;
+//   * results go straight to global memory as dense rows: a warp stores 32 consecutive doubles,
+//     rows are 512 B aligned for a 64^3 box, so every DRAM sector is written whole (the reference
+//     layout would leave two partial sectors per row: 2.5 vs 5.3 TB/s, profiles/micro);
 //   * ghost planes are loaded (they carry the z halo) but produce no output, so crossing from one
 //     fab to the next needs no special case; a range that starts or ends inside a fab re-reads one
 //     stage of its neighbour range (2 x 148 planes per launch, < 1 % extra traffic).
 //
-// HBM traffic per cell-update: (n0*n1*n2)/(vnx*vny*vnz)*8 B read (66^3/64^3 -> 8.77 B) + 8 B
+// HBM traffic per cell-update: n1*n2*(vnx+2)/(vnx*vny*vnz)*8 B read (66^3/64^3 -> 8.77 B) + 8 B
 // written; the algorithmic figure used for the roofline is 16 B.
 #include <cstdint>
 #include <cstdlib>
@@ -76,20 +79,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // never used by the product path): 1 = plain copy of the centre value, 2 = loads only, 3 = stores only.
 template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1)
-k_heat_stream(const double* __restrict__ in, double* __restrict__ out, int nstages, int n2, double f, int fma) {
+k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_xg, double* __restrict__ out_main,
+              int nstages, int n2, double f, int fma) {
   constexpr int NT = NCW * 32;                   // consumer threads
-  constexpr int N0 = VNX + 2 * NG, N1 = VNY + 2 * NG;
-  constexpr int PLANE = N0 * N1;                 // elements per plane
-  constexpr int STAGE = PS * PLANE;              // elements per stage
-  constexpr uint32_t STAGE_BYTES = STAGE * 8u;
+  constexpr int N1 = VNY + 2 * NG;
+  constexpr int PLANE = VNX * N1;                // elements per main plane (dense rows, y ghosts included)
+  constexpr int STRIP = NG * N1;                 // elements per x-ghost strip of one plane and side
+  constexpr int STAGE = PS * (PLANE + 2 * STRIP);   // elements per ring slot: planes | low strips | high strips
+  constexpr uint32_t MAIN_BYTES = PS * PLANE * 8u, STRIP_BYTES = PS * STRIP * 8u;
   constexpr int COLS = VNX * VNY;
   constexpr int CPT = (COLS + NT - 1) / NT;      // columns per consumer thread
-  static_assert(STAGE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  static_assert(NG == 1, "one ghost layer");
+  static_assert(MAIN_BYTES % 16 == 0 && STRIP_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  static_assert(NT % VNX == 0, "a thread keeps the same x for all its columns");
   static_assert(NS >= 3, "two stages are being read while at least one is in flight");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE * 8);
   uint64_t* empty = full + NS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -111,24 +118,39 @@ k_heat_stream(const double* __restrict__ in, double* __restrict__ out, int nstag
     // ---------------- producer: one lane keeps the ring full ----------------
     if (lane == 0) {
       int slot = 0, round = 0;                   // ring slot of stage t is (t - l_begin) % NS
+      int kz = (int)(((long long)l_begin * PS) % n2);          // fab plane of the stage's first plane
+      long long box = ((long long)l_begin * PS) / n2;
+      const long long xfab = (long long)2 * STRIP * n2;        // xg block elements per fab
       for (int t = l_begin; t < l_end; ++t) {
         if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
-        if (MODE == 3) { mbar_arrive(full + slot); if (++slot == NS) { slot = 0; ++round; } continue; }
-        mbar_expect_tx(full + slot, STAGE_BYTES);
-        bulk_g2s(ring + (size_t)slot * STAGE, in + (size_t)t * STAGE, STAGE_BYTES, full + slot);
+        if (MODE == 3) {
+          mbar_arrive(full + slot);
+        } else {
+          double* dst = ring + (size_t)slot * STAGE;
+          const double* xg = in_xg + box * xfab + (long long)kz * STRIP;
+          mbar_expect_tx(full + slot, MAIN_BYTES + 2 * STRIP_BYTES);
+          bulk_g2s(dst, in_main + (size_t)t * (PS * PLANE), MAIN_BYTES, full + slot);
+          bulk_g2s(dst + PS * PLANE, xg, STRIP_BYTES, full + slot);
+          bulk_g2s(dst + PS * PLANE + PS * STRIP, xg + (long long)n2 * STRIP, STRIP_BYTES, full + slot);
+        }
         if (++slot == NS) { slot = 0; ++round; }
+        kz += PS;
+        if (kz >= n2) { kz = 0; ++box; }
       }
     }
     return;
   }
 
   // ---------------- consumers ----------------
-  int soff[CPT];
+  const int xi = tid % VNX;                             // this thread's x in every column it owns
+  const bool at_lo = (xi == 0), at_hi = (xi == VNX - 1);
+  int soff[CPT], srow[CPT];
 #pragma unroll
   for (int m = 0; m < CPT; ++m) {
     const int idx = tid + m * NT;
-    const int i = idx % VNX, j = idx / VNX;
-    soff[m] = (idx < COLS) ? (j + NG) * N0 + (i + NG) : -1;
+    const int j = idx / VNX;
+    srow[m] = j + NG;
+    soff[m] = (idx < COLS) ? (j + NG) * VNX + xi : -1;
   }
   const int p_lo = s_begin * PS, p_hi = s_end * PS;   // planes whose output this CTA owns
   int q = l_begin * PS;                                // plane being read as the "z+1" plane
@@ -136,17 +158,20 @@ k_heat_stream(const double* __restrict__ in, double* __restrict__ out, int nstag
   int slot = 0, prev_slot = 0;
   uint32_t phase = 0;
   double cc[CPT], zm[CPT];                             // column values at planes q-1 and q-2
-  const double* prev = ring;
+  const double* prev = ring;                           // plane q-1 and its two x-ghost strips
+  const double* prev_lo = ring;
+  const double* prev_hi = ring;
   bool prev_out = false;
 
   for (int t = l_begin; t < l_end; ++t) {
     mbar_wait(full + slot, (phase >> slot) & 1u);
     phase ^= 1u << slot;
+    const double* __restrict__ sbase = ring + (size_t)slot * STAGE;
 #pragma unroll
     for (int p = 0; p < PS; ++p) {
-      const double* __restrict__ cur = ring + (size_t)(slot * PS + p) * PLANE;
+      const double* __restrict__ cur = sbase + p * PLANE;
       const bool emit = prev_out && (q - 1 >= p_lo) && (q - 1 < p_hi);
-      double* __restrict__ po = out + (size_t)(q - 1) * PLANE;
+      double* __restrict__ po = out_main + (size_t)(q - 1) * PLANE;
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
         if (soff[m] < 0) continue;
@@ -157,8 +182,10 @@ k_heat_stream(const double* __restrict__ in, double* __restrict__ out, int nstag
         else if (emit) {
           const double c = cc[m];
           const double twoc = __dmul_rn(2.0, c);
-          const double tx = sd2(prev[o + 1], twoc, prev[o - 1]);
-          const double ty = sd2(prev[o + N0], twoc, prev[o - N0]);
+          const double* pxm = at_lo ? prev_lo + srow[m] : prev + (o - 1);
+          const double* pxp = at_hi ? prev_hi + srow[m] : prev + (o + 1);
+          const double tx = sd2(*pxp, twoc, *pxm);
+          const double ty = sd2(prev[o + VNX], twoc, prev[o - VNX]);
           const double tz = sd2(zp, twoc, zm[m]);
           const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
           po[o] = fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
@@ -167,6 +194,8 @@ k_heat_stream(const double* __restrict__ in, double* __restrict__ out, int nstag
         cc[m] = zp;
       }
       prev = cur;
+      prev_lo = sbase + PS * PLANE + p * STRIP;
+      prev_hi = sbase + PS * PLANE + PS * STRIP + p * STRIP;
       prev_out = (kz >= NG) && (kz < n2 - NG);
       ++q;
       if (++kz == n2) kz = 0;
@@ -181,8 +210,9 @@ k_heat_stream(const double* __restrict__ in, double* __restrict__ out, int nstag
 }
 
 template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0>
-static int launch_cfg(const double* in, double* out, int nstages, int n2, double f, int fma, cudaStream_t s) {
-  constexpr size_t smem = (size_t)NS * PS * (VNX + 2 * NG) * (VNY + 2 * NG) * 8 + 2 * NS * 8;
+static int launch_cfg(const double* in_main, const double* in_xg, double* out_main, int nstages, int n2, double f,
+                      int fma, cudaStream_t s) {
+  constexpr size_t smem = (size_t)NS * PS * ((size_t)VNX * (VNY + 2 * NG) + 2 * NG * (VNY + 2 * NG)) * 8 + 2 * NS * 8;
   static bool configured = false;
   auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE>;
   if (!configured) {
@@ -191,7 +221,7 @@ static int launch_cfg(const double* in, double* out, int nstages, int n2, double
   }
   int grid = rt().sm_count;
   if (grid > nstages) grid = nstages;
-  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in, out, nstages, n2, f, fma);
+  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
@@ -204,21 +234,21 @@ int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0) return 1;
   const int vnx = g.vn[0], vny = g.vn[1], n2 = g.n[2];
-  const long long fab = g.cs;
-  const double* in = (const double*)u->d_arena + (long long)box_begin * fab;
-  double* out = (double*)unew->d_arena + (long long)box_begin * fab;
+  const double* in_main = (const double*)u->d_arena + (long long)box_begin * g.cs;
+  const double* in_xg = (const double*)u->d_arena + u->xg_base + (long long)box_begin * g.xcs;
+  double* out = (double*)unew->d_arena + (long long)box_begin * g.cs;
   const long long planes = (long long)(box_end - box_begin) * n2;
   if (planes > 0x7fffffffLL) return 1;
   if (getenv("SGC_NO_STREAM")) return 1;
 #define SGC_STREAM_CASE(VX, VY, PS_, NS_, NCW_)                                                      \
   if (vnx == VX && vny == VY && n2 % PS_ == 0)                                                       \
-    return launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in, out, (int)(planes / PS_), n2, f, fma, s)
+    return launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, s)
   if (const char* m = getenv("SGC_STREAM_MODE")) {      // diagnostics only
     if (vnx == 64 && vny == 64) {
       const int ns = (int)(planes);
-      if (m[0] == '1') return launch_cfg<64, 64, 1, 1, 6, 16, 1>(in, out, ns, n2, f, fma, s);
-      if (m[0] == '2') return launch_cfg<64, 64, 1, 1, 6, 16, 2>(in, out, ns, n2, f, fma, s);
-      if (m[0] == '3') return launch_cfg<64, 64, 1, 1, 6, 16, 3>(in, out, ns, n2, f, fma, s);
+      if (m[0] == '1') return launch_cfg<64, 64, 1, 1, 6, 16, 1>(in_main, in_xg, out, ns, n2, f, fma, s);
+      if (m[0] == '2') return launch_cfg<64, 64, 1, 1, 6, 16, 2>(in_main, in_xg, out, ns, n2, f, fma, s);
+      if (m[0] == '3') return launch_cfg<64, 64, 1, 1, 6, 16, 3>(in_main, in_xg, out, ns, n2, f, fma, s);
     }
   }
   SGC_STREAM_CASE(64, 64, 1, 6, 16);
