@@ -189,7 +189,7 @@ def run_reference_arm(a):
                          "sweep_ms_per_sweep": split["sweep_ms"] / sample_sweeps, "probe": probe},
         "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(a, n):
@@ -201,8 +201,30 @@ def workload_config(a, n):
 
 
 # ------------------------------------------------------------------------------ our arm
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else a library prints (NCCL's version
+    banner, torchrun notices) was redirected to stderr by quiet_stdout()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     a = parse()
+    quiet_stdout()
     if a.impl == "reference":
         return run_reference_arm(a)
 
@@ -303,6 +325,11 @@ def main():
     for _ in range(A.size()):
         ref_sum += float(pin_in.array[off:off + m ** 3].reshape(m, m, m)[1:-1, 1:-1, 1:-1].sum())
         off += m ** 3
+    if dist is not None:
+        import torch
+        t = torch.tensor([mask_sum, ref_sum], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        mask_sum, ref_sum = float(t[0]), float(t[1])
     conserved = abs(mask_sum - ref_sum) <= 1e-9 * abs(ref_sum)
 
     # roofline of the dominant kernel (the sweep): algorithmic bytes per launch / mean launch time
@@ -367,7 +394,7 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches), "device": name, "sm_count": sms,
                 "plan_build_ms": plan_ms, "motion_items": cp.numMotionItem(), "remote_items": cp.numRemoteItem(),
                 "sum_conserved": bool(conserved)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         sgc.comm_finalize()

@@ -206,6 +206,9 @@ int sgc_heat_sweep(sgc_level_t unew, sgc_level_t u, double f, unsigned flags);
 /* Only boxes [box_begin, box_end) — used to overlap interior boxes with the halo transfer.   */
 int sgc_heat_sweep_range(sgc_level_t unew, sgc_level_t u, double f, unsigned flags,
                          int box_begin, int box_end);
+/* Boxes [a0,a1) and [b0,b1) (a1 <= b0) in ONE launch — the two boundary box layers of a z-slab. */
+int sgc_heat_sweep_ranges(sgc_level_t unew, sgc_level_t u, double f, unsigned flags,
+                          int a0, int a1, int b0, int b1);
 
 /* The PR1 driver's update (laplacian.cpp:94-108): for iter < niter, for dir in x,y,z:
  *   B -= coef*((A[i+e_dir]-2A[i])+A[i-e_dir])

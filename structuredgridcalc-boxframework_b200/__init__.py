@@ -28,7 +28,7 @@ SYMBOLS = [
     "sgc_level_download", "sgc_level_setval", "sgc_fab_copy", "sgc_fab_linear_out", "sgc_fab_linear_in",
     "sgc_plan_create_exchange", "sgc_plan_create_items", "sgc_plan_destroy", "sgc_plan_num_items",
     "sgc_plan_num_remote_items", "sgc_plan_num_cells", "sgc_exchange", "sgc_exchange_begin", "sgc_exchange_end",
-    "sgc_plan_create_bc_zero_gradient", "sgc_heat_sweep", "sgc_heat_sweep_range", "sgc_laplacian_apply",
+    "sgc_plan_create_bc_zero_gradient", "sgc_heat_sweep", "sgc_heat_sweep_range", "sgc_heat_sweep_ranges", "sgc_laplacian_apply",
     "sgc_wave_step", "sgc_heat_run", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
     "sgc_comm_rank", "sgc_halo_describe",
 ]
@@ -108,6 +108,7 @@ def lib():
         getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
     L.sgc_heat_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint]
     L.sgc_heat_sweep_range.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint, C.c_int, C.c_int]
+    L.sgc_heat_sweep_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
     L.sgc_laplacian_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_uint]
     L.sgc_wave_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint]
     L.sgc_heat_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint, C.c_int, C.POINTER(C.c_int)]
@@ -423,6 +424,8 @@ class Copier:
 def heat_sweep(unew, u, f, flags=SGC_FMA, box_range=None):
     if box_range is None:
         check(lib().sgc_heat_sweep(unew.h, u.h, f, flags))
+    elif len(box_range) == 4:
+        check(lib().sgc_heat_sweep_ranges(unew.h, u.h, f, flags, *box_range))
     else:
         check(lib().sgc_heat_sweep_range(unew.h, u.h, f, flags, box_range[0], box_range[1]))
 

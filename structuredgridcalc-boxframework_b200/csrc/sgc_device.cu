@@ -3,6 +3,7 @@
 // the multi-rank transport in sgc_comm.cu).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sgc_device.h"
@@ -26,6 +27,8 @@ int sweep_tile_z();
 // streaming sweep (returns 1 when it does not apply to this geometry, 0 when launched, <0 on error)
 int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int box_begin, int box_end,
                        cudaStream_t s);
+int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
+                        cudaStream_t s);
 // multi-rank transport (sgc_comm.cu)
 int comm_plan_setup(sgc_plan_s* plan, sgc_level_s* level, const Grid& g, unsigned periodic, unsigned trim);
 void comm_plan_release(sgc_plan_s* plan);
@@ -197,8 +200,16 @@ int sgc_init(int device) {
     return fail(SGC_ERR_UNSUPPORTED, "sgc_init: kernels are built for sm_100a only; device is sm_" +
                                          std::to_string(p.major) + std::to_string(p.minor));
   r.sm_count = p.multiProcessorCount;
-  SGC_CUDA(cudaStreamCreateWithFlags(&r.compute, cudaStreamNonBlocking));
-  SGC_CUDA(cudaStreamCreateWithFlags(&r.comm, cudaStreamNonBlocking));
+  // The x-face items of an exchange read one 8-byte value per 512-byte row; with the default L2 fetch
+  // granularity every such read drags a 128-byte line out of DRAM (ncu: 583 MB read for 104 MB of
+  // ghost cells).  Ask for sector-sized fetches; the streaming kernels move whole lines anyway.
+  if (!getenv("SGC_KEEP_L2_GRANULARITY")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+  // the comm stream (pack, NCCL send/recv) outranks the compute stream so that its few CTAs are
+  // placed as soon as an SM has room, instead of queueing behind a persistent sweep
+  int prio_lo = 0, prio_hi = 0;
+  SGC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  SGC_CUDA(cudaStreamCreateWithPriority(&r.compute, cudaStreamNonBlocking, prio_lo));
+  SGC_CUDA(cudaStreamCreateWithPriority(&r.comm, cudaStreamNonBlocking, prio_hi));
   r.device = device;
   r.launches = 0;
   r.ready = true;
@@ -776,30 +787,45 @@ int sgc_wave_step(sgc_level_t unp1, sgc_level_t un, sgc_level_t unm1, double fac
                              rt().compute);
 }
 
+int sgc_heat_sweep_ranges(sgc_level_t nxt, sgc_level_t cur, double f, unsigned flags, int a0, int a1, int b0, int b1) {
+  SGC_REQUIRE_RT();
+  int st = check_sweep(nxt, cur, "sgc_heat_sweep_ranges");
+  if (st) return st;
+  if (a0 < 0 || a0 > a1 || a1 > b0 || b0 > b1 || b1 > nxt->nbox) return fail(SGC_ERR_ARG, "sgc_heat_sweep_ranges: box ranges");
+  {
+    ProfScope prof(0, rt().compute);
+    st = launch_heat_stream2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, a0, a1, b0, b1, rt().compute);
+  }
+  if (st <= 0) return st;
+  st = sgc_heat_sweep_range(nxt, cur, f, flags, a0, a1);
+  if (!st) st = sgc_heat_sweep_range(nxt, cur, f, flags, b0, b1);
+  return st;
+}
+
 int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags, int nstep, int* result_in_b) {
   SGC_REQUIRE_RT();
   if (!a || !b || !plan || nstep < 0) return fail(SGC_ERR_ARG, "sgc_heat_run: bad argument");
   if (!same_geometry(a, b)) return fail(SGC_ERR_GEOMETRY, "sgc_heat_run: the two levels must share geometry");
+  // Multi-rank schedule.  "split": halo in flight while the boxes without remote items sweep, then
+  // the boundary layers (two box ranges, one launch).  "whole": the halo only overlaps the batched
+  // local ghost copies, then one sweep over all boxes.  SGC_OVERLAP=0/1 overrides the default.
+  int b0 = 0, b1 = a->nbox;
+  bool split = false;
+  if (plan->nremote > 0 && plan->n_boundary_boxes < a->nbox) {
+    while (b0 < b1 && plan->box_is_boundary[b0]) ++b0;
+    while (b1 > b0 && plan->box_is_boundary[b1 - 1]) --b1;
+    split = true;
+    for (int i = b0; i < b1; ++i) if (plan->box_is_boundary[i]) split = false;   // boundary boxes must be the two ends
+    if (const char* e = getenv("SGC_OVERLAP")) split = split && e[0] != '0';
+  }
   sgc_level_t cur = a, nxt = b;
   for (int s = 0; s < nstep; ++s) {
     int st;
-    if (plan->nremote > 0 && plan->n_boundary_boxes < cur->nbox) {
-      // overlap: halo in flight while boxes without remote items sweep (boundary boxes are the
-      // first and last box layers of a z-slab partition, so interior boxes form one range)
+    if (split) {
       st = sgc_exchange_begin(cur, plan);
-      int b0 = 0, b1 = cur->nbox;
-      while (b0 < b1 && plan->box_is_boundary[b0]) ++b0;
-      while (b1 > b0 && plan->box_is_boundary[b1 - 1]) --b1;
-      bool contiguous = true;
-      for (int i = b0; i < b1; ++i) if (plan->box_is_boundary[i]) contiguous = false;
-      if (!st && contiguous) st = sgc_heat_sweep_range(nxt, cur, f, flags, b0, b1);
+      if (!st) st = sgc_heat_sweep_range(nxt, cur, f, flags, b0, b1);
       if (!st) st = sgc_exchange_end(cur, plan);
-      if (!st && contiguous) {
-        st = sgc_heat_sweep_range(nxt, cur, f, flags, 0, b0);
-        if (!st) st = sgc_heat_sweep_range(nxt, cur, f, flags, b1, cur->nbox);
-      } else if (!st) {
-        st = sgc_heat_sweep(nxt, cur, f, flags);
-      }
+      if (!st) st = sgc_heat_sweep_ranges(nxt, cur, f, flags, 0, b0, b1, cur->nbox);
     } else {
       st = sgc_exchange(cur, plan);
       if (!st) st = sgc_heat_sweep(nxt, cur, f, flags);

@@ -80,7 +80,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1)
 k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_xg, double* __restrict__ out_main,
-              int nstages, int n2, double f, int fma) {
+              int nstages, int n2, double f, int fma, int seam, int jump) {
+  // The launch covers the box range as a virtual stage sequence [0, nstages); stages >= seam live
+  // `jump` stages further on in memory (a second box range, e.g. the two boundary box layers of a
+  // z-slab).  Both ranges start and end on fab boundaries, so the seam sits between two ghost planes.
   constexpr int NT = NCW * 32;                   // consumer threads
   constexpr int N1 = VNY + 2 * NG;
   constexpr int PLANE = VNX * N1;                // elements per main plane (dense rows, y ghosts included)
@@ -118,10 +121,12 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
     // ---------------- producer: one lane keeps the ring full ----------------
     if (lane == 0) {
       int slot = 0, round = 0;                   // ring slot of stage t is (t - l_begin) % NS
-      int kz = (int)(((long long)l_begin * PS) % n2);          // fab plane of the stage's first plane
-      long long box = ((long long)l_begin * PS) / n2;
+      long long tr = l_begin + (l_begin >= seam ? jump : 0);   // real stage index
+      int kz = (int)((tr * PS) % n2);                          // fab plane of the stage's first plane
+      long long box = (tr * PS) / n2;
       const long long xfab = (long long)2 * STRIP * n2;        // xg block elements per fab
-      for (int t = l_begin; t < l_end; ++t) {
+      for (int t = l_begin; t < l_end; ++t, ++tr) {
+        if (t == seam && t != l_begin) { tr += jump; box = (tr * PS) / n2; kz = (int)((tr * PS) % n2); }
         if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
         if (MODE == 3) {
           mbar_arrive(full + slot);
@@ -129,7 +134,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
           double* dst = ring + (size_t)slot * STAGE;
           const double* xg = in_xg + box * xfab + (long long)kz * STRIP;
           mbar_expect_tx(full + slot, MAIN_BYTES + 2 * STRIP_BYTES);
-          bulk_g2s(dst, in_main + (size_t)t * (PS * PLANE), MAIN_BYTES, full + slot);
+          bulk_g2s(dst, in_main + (size_t)tr * (PS * PLANE), MAIN_BYTES, full + slot);
           bulk_g2s(dst + PS * PLANE, xg, STRIP_BYTES, full + slot);
           bulk_g2s(dst + PS * PLANE + PS * STRIP, xg + (long long)n2 * STRIP, STRIP_BYTES, full + slot);
         }
@@ -153,8 +158,9 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
     soff[m] = (idx < COLS) ? (j + NG) * VNX + xi : -1;
   }
   const int p_lo = s_begin * PS, p_hi = s_end * PS;   // planes whose output this CTA owns
-  int q = l_begin * PS;                                // plane being read as the "z+1" plane
-  int kz = q % n2;                                     // its index inside its fab
+  int q = l_begin * PS;                                // plane being read as the "z+1" plane (virtual index)
+  long long qr = (long long)(l_begin + (l_begin >= seam ? jump : 0)) * PS;   // its real index in memory
+  int kz = (int)(qr % n2);                             // its index inside its fab
   int slot = 0, prev_slot = 0;
   uint32_t phase = 0;
   double cc[CPT], zm[CPT];                             // column values at planes q-1 and q-2
@@ -164,6 +170,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   bool prev_out = false;
 
   for (int t = l_begin; t < l_end; ++t) {
+    if (t == seam && t != l_begin) qr += (long long)jump * PS;
     mbar_wait(full + slot, (phase >> slot) & 1u);
     phase ^= 1u << slot;
     const double* __restrict__ sbase = ring + (size_t)slot * STAGE;
@@ -171,7 +178,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
     for (int p = 0; p < PS; ++p) {
       const double* __restrict__ cur = sbase + p * PLANE;
       const bool emit = prev_out && (q - 1 >= p_lo) && (q - 1 < p_hi);
-      double* __restrict__ po = out_main + (size_t)(q - 1) * PLANE;
+      double* __restrict__ po = out_main + (size_t)(qr - 1) * PLANE;
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
         if (soff[m] < 0) continue;
@@ -197,7 +204,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
       prev_lo = sbase + PS * PLANE + p * STRIP;
       prev_hi = sbase + PS * PLANE + PS * STRIP + p * STRIP;
       prev_out = (kz >= NG) && (kz < n2 - NG);
-      ++q;
+      ++q; ++qr;
       if (++kz == n2) kz = 0;
     }
     if (t > l_begin) {                           // stage t-1 is no longer read by this warp
@@ -211,7 +218,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
 
 template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0>
 static int launch_cfg(const double* in_main, const double* in_xg, double* out_main, int nstages, int n2, double f,
-                      int fma, cudaStream_t s) {
+                      int fma, int seam, int jump, cudaStream_t s) {
   constexpr size_t smem = (size_t)NS * PS * ((size_t)VNX * (VNY + 2 * NG) + 2 * NG * (VNY + 2 * NG)) * 8 + 2 * NS * 8;
   static bool configured = false;
   auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE>;
@@ -221,34 +228,40 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
   }
   int grid = rt().sm_count;
   if (grid > nstages) grid = nstages;
-  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma);
+  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma, seam, jump);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
 }
 
-// returns 1 when the geometry is not covered (caller falls back to the table-driven kernel)
-int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int box_begin, int box_end,
-                       cudaStream_t s) {
+// Sweeps boxes [a0,a1) and [b0,b1) (a1 <= b0; the second range may be empty) in ONE launch.
+// Returns 1 when the geometry is not covered (caller falls back to the table-driven kernel).
+int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
+                        cudaStream_t s) {
   if (!u->uniform || !unew->uniform || u->ncomp != 1 || unew->ncomp != 1 || u->ng != unew->ng || u->ng != 1) return 1;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0) return 1;
+  if (a1 == a0) { a0 = b0; a1 = b1; b0 = b1 = a1; }
+  if (b1 == b0) b0 = b1 = a1;
   const int vnx = g.vn[0], vny = g.vn[1], n2 = g.n[2];
-  const double* in_main = (const double*)u->d_arena + (long long)box_begin * g.cs;
-  const double* in_xg = (const double*)u->d_arena + u->xg_base + (long long)box_begin * g.xcs;
-  double* out = (double*)unew->d_arena + (long long)box_begin * g.cs;
-  const long long planes = (long long)(box_end - box_begin) * n2;
-  if (planes > 0x7fffffffLL) return 1;
+  const double* in_main = (const double*)u->d_arena + (long long)a0 * g.cs;
+  const double* in_xg = (const double*)u->d_arena + u->xg_base + (long long)a0 * g.xcs;
+  double* out = (double*)unew->d_arena + (long long)a0 * g.cs;
+  const long long planesA = (long long)(a1 - a0) * n2, planesB = (long long)(b1 - b0) * n2;
+  const long long planes = planesA + planesB, gap = (long long)(b0 - a1) * n2;
+  if (planes <= 0) return 0;
+  if (planes + gap > 0x7fffffffLL) return 1;
   if (getenv("SGC_NO_STREAM")) return 1;
 #define SGC_STREAM_CASE(VX, VY, PS_, NS_, NCW_)                                                      \
   if (vnx == VX && vny == VY && n2 % PS_ == 0)                                                       \
-    return launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, s)
+    return launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
+                                                 (int)(planesA / PS_), (int)(gap / PS_), s)
   if (const char* m = getenv("SGC_STREAM_MODE")) {      // diagnostics only
     if (vnx == 64 && vny == 64) {
-      const int ns = (int)(planes);
-      if (m[0] == '1') return launch_cfg<64, 64, 1, 1, 6, 16, 1>(in_main, in_xg, out, ns, n2, f, fma, s);
-      if (m[0] == '2') return launch_cfg<64, 64, 1, 1, 6, 16, 2>(in_main, in_xg, out, ns, n2, f, fma, s);
-      if (m[0] == '3') return launch_cfg<64, 64, 1, 1, 6, 16, 3>(in_main, in_xg, out, ns, n2, f, fma, s);
+      const int ns = (int)(planes), sm = (int)planesA, jp = (int)gap;
+      if (m[0] == '1') return launch_cfg<64, 64, 1, 1, 6, 16, 1>(in_main, in_xg, out, ns, n2, f, fma, sm, jp, s);
+      if (m[0] == '2') return launch_cfg<64, 64, 1, 1, 6, 16, 2>(in_main, in_xg, out, ns, n2, f, fma, sm, jp, s);
+      if (m[0] == '3') return launch_cfg<64, 64, 1, 1, 6, 16, 3>(in_main, in_xg, out, ns, n2, f, fma, sm, jp, s);
     }
   }
   SGC_STREAM_CASE(64, 64, 1, 6, 16);
@@ -257,6 +270,11 @@ int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int
   SGC_STREAM_CASE(8, 8, 10, 24, 2);
 #undef SGC_STREAM_CASE
   return 1;
+}
+
+int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int box_begin, int box_end,
+                       cudaStream_t s) {
+  return launch_heat_stream2(unew, u, f, fma, box_begin, box_end, box_end, box_end, s);
 }
 
 }  // namespace sgc

@@ -384,6 +384,28 @@ def test_wave_and_zero_gradient_bc(g, golden, oracle):
         assert np.array_equal(got[lev.fab_offset(b):lev.fab_offset(b) + lev.fab_elems(b)], f.ravel()), b
 
 
+def test_sweep_box_ranges_streaming_kernel(g, oracle):
+    # the streaming kernel on sub-ranges and on two ranges in one launch (boundary box layers)
+    rng = np.random.default_rng(11)
+    for mb, nbz in ((16, 6), (64, 3), (32, 4), (8, 5)):
+        dlo, dhi = (0, 0, 0), (2 * mb - 1, mb - 1, nbz * mb - 1)
+        dbl, a = make_level(g, dlo, dhi, (mb,) * 3, 1, 1)
+        b = g.LevelData(dbl, 1, 1)
+        u, v = rng.standard_normal(a.elems), rng.standard_normal(a.elems)
+        a.upload(u)
+        want = v.copy()
+        oracle.level_heat_sweep(dbl.boxes, 1, u, want, 0.3, 1)
+        n = a.size()
+        for rngs in ((0, n), (1, n - 1), (0, 2, n - 2, n), (0, 1, 3, 4), (2, 2, 3, n), (0, 3, 3, 3)):
+            b.upload(v)
+            g.heat_sweep(b, a, 0.3, box_range=rngs)
+            got = b.download()
+            sel = set(range(rngs[0], rngs[1])) | (set(range(rngs[2], rngs[3])) if len(rngs) == 4 else set())
+            for k in range(n):
+                s = slice(a.fab_offset(k), a.fab_offset(k) + a.fab_elems(k))
+                assert np.array_equal(got[s], want[s] if k in sel else v[s]), (mb, rngs, k)
+
+
 # ------------------------------------------------------------------ full-size, size-independent properties
 def test_full_size_C2_properties(g, oracle):
     """BASELINE configs[1] shape (512^3 in 64^3 boxes is 2.4 GB for two levels; run 256^3 here and the
