@@ -200,10 +200,6 @@ int sgc_init(int device) {
     return fail(SGC_ERR_UNSUPPORTED, "sgc_init: kernels are built for sm_100a only; device is sm_" +
                                          std::to_string(p.major) + std::to_string(p.minor));
   r.sm_count = p.multiProcessorCount;
-  // The x-face items of an exchange read one 8-byte value per 512-byte row; with the default L2 fetch
-  // granularity every such read drags a 128-byte line out of DRAM (ncu: 583 MB read for 104 MB of
-  // ghost cells).  Ask for sector-sized fetches; the streaming kernels move whole lines anyway.
-  if (!getenv("SGC_KEEP_L2_GRANULARITY")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
   // the comm stream (pack, NCCL send/recv) outranks the compute stream so that its few CTAs are
   // placed as soon as an SM has room, instead of queueing behind a persistent sweep
   int prio_lo = 0, prio_hi = 0;
