@@ -178,6 +178,10 @@ struct sgc_plan_s {
   std::vector<char> box_is_boundary;
   cudaEvent_t ev_local = nullptr, ev_halo = nullptr, ev_ready = nullptr;
   bool in_flight = false;
+  // fused ghost fill (sweep pushes boundary cells into the neighbours' ghosts): destination local
+  // box per (box, direction code), -1 where there is no local motion item
+  int* d_push = nullptr;
+  bool fusable = false;
 };
 
 struct sgc_event_s {

@@ -31,6 +31,10 @@
 
 #include "sgc_device.h"
 
+#ifndef SGC_NCW64
+#define SGC_NCW64 16     // consumer warps of the 64x64 instance
+#endif
+
 namespace sgc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -55,6 +59,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // global -> shared bulk copy through the async proxy (TMA), completing `bytes` on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -77,10 +94,35 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // back-pressure, a late plane) do not stop the others.
 // MODE: 0 = the sweep.  1..3 are roofline diagnostics of the same pipeline (env SGC_STREAM_MODE,
 // never used by the product path): 1 = plain copy of the centre value, 2 = loads only, 3 = stores only.
-template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0>
+//
+// PUSH = fused ghost fill ("pull y/z, push x"): inside a step loop the separate exchange launch
+// disappears.
+//   * y and z halos are PULLED by the producer: instead of a fab's own ghost rows / ghost planes it
+//     bulk-copies the neighbouring fab's first / last valid row / plane (dense, whole sectors) into
+//     the same place of the ring slot — zero work for the consumer warps;
+//   * x halos are PUSHED by the consumers: the thread that computes the first / last cell of a row
+//     (one lane per warp) also stores it into the x neighbour's ghost strip, one predicated store
+//     per cell from the register that holds the result.  (Pulling x would read one 8-byte value per
+//     512-byte row, which costs a 128-byte DRAM access each: ncu shows 583 MB read for 104 MB of
+//     ghost cells in the stand-alone exchange kernel.)
+// Where the plan has no local motion item (push.nbr == -1: physical boundary or a box owned by
+// another GPU) the fab's own ghost cells are used, exactly as without PUSH; they are kept current by
+// the BC / NCCL unpack.  Edge and corner ghosts are not needed by the 7-point stencil and are left
+// alone; sgc_heat_run restores the reference's ghost contents by running its last two steps unfused.
+struct PushArgs {
+  const int* nbr;        // [nbox][27] local box in direction code 13 + dx + 3 dy + 9 dz that has a local
+                         // motion item with this box, or -1 (domain boundary, trimmed, or remote owner)
+  double* out_level;     // arena base of the output level
+  const double* in_level;   // arena base of the input level
+  long long xg_base;     // element offset of the xg regions (same geometry for both levels)
+  int box0;              // local index of the first box of this launch
+  int mask;              // diagnostics: bit 0 = x-face pushes, bit 1 = y/z pulls (default 3)
+};
+
+template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1)
 k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_xg, double* __restrict__ out_main,
-              int nstages, int n2, double f, int fma, int seam, int jump) {
+              int nstages, int n2, double f, int fma, int seam, int jump, PushArgs push) {
   // The launch covers the box range as a virtual stage sequence [0, nstages); stages >= seam live
   // `jump` stages further on in memory (a second box range, e.g. the two boundary box layers of a
   // z-slab).  Both ranges start and end on fab boundaries, so the seam sits between two ghost planes.
@@ -122,45 +164,86 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
     if (lane == 0) {
       int slot = 0, round = 0;                   // ring slot of stage t is (t - l_begin) % NS
       long long tr = l_begin + (l_begin >= seam ? jump : 0);   // real stage index
-      int kz = (int)((tr * PS) % n2);                          // fab plane of the stage's first plane
-      long long box = (tr * PS) / n2;
       const long long xfab = (long long)2 * STRIP * n2;        // xg block elements per fab
+      int pb = -1, dym = -1, dyp = -1, dzm = -1, dzp = -1;     // cached pull sources of box pb
       for (int t = l_begin; t < l_end; ++t, ++tr) {
-        if (t == seam && t != l_begin) { tr += jump; box = (tr * PS) / n2; kz = (int)((tr * PS) % n2); }
+        if (t == seam && t != l_begin) tr += jump;
         if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
         if (MODE == 3) {
           mbar_arrive(full + slot);
         } else {
+          const long long pl = tr * PS;                        // first plane of the stage
+          const long long box = pl / n2;
+          const int kz0 = (int)(pl - box * n2);
           double* dst = ring + (size_t)slot * STAGE;
-          const double* xg = in_xg + box * xfab + (long long)kz * STRIP;
+          const double* xg = in_xg + box * xfab + (long long)kz0 * STRIP;
           mbar_expect_tx(full + slot, MAIN_BYTES + 2 * STRIP_BYTES);
-          bulk_g2s(dst, in_main + (size_t)tr * (PS * PLANE), MAIN_BYTES, full + slot);
+          if (!PUSH || !(push.mask & 2)) {
+            bulk_g2s(dst, in_main + (size_t)tr * (PS * PLANE), MAIN_BYTES, full + slot);
+          } else {
+            // pull: y-ghost rows and z-ghost planes come from the neighbours' valid cells
+            const int b = push.box0 + (int)box;
+            if (b != pb) {
+              pb = b;
+              const int* __restrict__ nb = push.nbr + (size_t)b * 27;
+              dym = __ldg(nb + 13 - 3); dyp = __ldg(nb + 13 + 3); dzm = __ldg(nb + 13 - 9); dzp = __ldg(nb + 13 + 9);
+            }
+            const long long fabm = (long long)PLANE * n2;
+            const int vnz_ = n2 - 2 * NG;
+#pragma unroll
+            for (int p = 0; p < PS; ++p) {
+              const int kz = kz0 + p;
+              double* d = dst + p * PLANE;
+              const double* own = push.in_level + b * fabm + (long long)kz * PLANE;
+              if (kz < NG) {                                   // low ghost plane <- -z neighbour's last valid planes
+                bulk_g2s(d, dzm >= 0 ? push.in_level + dzm * fabm + (long long)(kz + vnz_) * PLANE : own, PLANE * 8u, full + slot);
+              } else if (kz >= n2 - NG) {                      // high ghost plane <- +z neighbour's first valid planes
+                bulk_g2s(d, dzp >= 0 ? push.in_level + dzp * fabm + (long long)(kz - vnz_) * PLANE : own, PLANE * 8u, full + slot);
+              } else if (dym < 0 && dyp < 0) {
+                bulk_g2s(d, own, PLANE * 8u, full + slot);
+              } else {
+                constexpr uint32_t YG = NG * VNX * 8u, YV = VNY * VNX * 8u;
+                const double* lo = dym >= 0 ? push.in_level + dym * fabm + (long long)kz * PLANE + VNY * VNX : own;
+                const double* hi = dyp >= 0 ? push.in_level + dyp * fabm + (long long)kz * PLANE + NG * VNX
+                                            : own + (VNY + NG) * VNX;
+                bulk_g2s(d, lo, YG, full + slot);                              // ghost rows 0..NG-1
+                bulk_g2s(d + NG * VNX, own + NG * VNX, YV, full + slot);      // valid rows
+                bulk_g2s(d + (VNY + NG) * VNX, hi, YG, full + slot);          // ghost rows VNY+NG..
+              }
+            }
+          }
           bulk_g2s(dst + PS * PLANE, xg, STRIP_BYTES, full + slot);
           bulk_g2s(dst + PS * PLANE + PS * STRIP, xg + (long long)n2 * STRIP, STRIP_BYTES, full + slot);
         }
         if (++slot == NS) { slot = 0; ++round; }
-        kz += PS;
-        if (kz >= n2) { kz = 0; ++box; }
       }
     }
     return;
   }
 
   // ---------------- consumers ----------------
-  const int xi = tid % VNX;                             // this thread's x in every column it owns
+  // Thread tid owns the CPT columns (xi, j0 + m*ROWS), m = 0..CPT-1: the same x for all of them, so
+  // every shared-memory / global offset of column m is the offset of column 0 plus a compile-time
+  // constant (m*NT elements), which the compiler folds into the instructions' immediate fields.
+  static_assert(COLS % NT == 0, "columns divide evenly among the consumer threads");
+  constexpr int ROWS = NT / VNX;                        // rows covered by one m-slice
+  const int xi = tid % VNX, j0 = tid / VNX;
   const bool at_lo = (xi == 0), at_hi = (xi == VNX - 1);
-  int soff[CPT], srow[CPT];
-#pragma unroll
-  for (int m = 0; m < CPT; ++m) {
-    const int idx = tid + m * NT;
-    const int j = idx / VNX;
-    srow[m] = j + NG;
-    soff[m] = (idx < COLS) ? (j + NG) * VNX + xi : -1;
-  }
+  const int so0 = (j0 + NG) * VNX + xi;                 // offset of column 0 inside a plane
+  const int sr0 = j0 + NG;                              // its fab-relative row
+  // fused ghost fill: which faces of the box this thread's cells lie on
+  const int fx = at_lo ? -1 : (at_hi ? 1 : 0);
+  const long long fab_xg = (long long)2 * STRIP * n2;
+  double* xdst = nullptr;      // x-face destination strip of the current fab (threads on an x face only)
+  int pbox = -1;               // box whose destination is cached
+  int bcur = 0;                // box of plane q (tracked incrementally)
+
   const int p_lo = s_begin * PS, p_hi = s_end * PS;   // planes whose output this CTA owns
   int q = l_begin * PS;                                // plane being read as the "z+1" plane (virtual index)
   long long qr = (long long)(l_begin + (l_begin >= seam ? jump : 0)) * PS;   // its real index in memory
   int kz = (int)(qr % n2);                             // its index inside its fab
+  bcur = push.box0 + (int)(qr / n2);
+  int bprev = bcur;                                    // box of plane q-1
   int slot = 0, prev_slot = 0;
   uint32_t phase = 0;
   double cc[CPT], zm[CPT];                             // column values at planes q-1 and q-2
@@ -168,44 +251,66 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   const double* prev_lo = ring;
   const double* prev_hi = ring;
   bool prev_out = false;
+  int kz_prev = 0;                                     // fab plane index of plane q-1
 
   for (int t = l_begin; t < l_end; ++t) {
-    if (t == seam && t != l_begin) qr += (long long)jump * PS;
+    if (t == seam && t != l_begin) { qr += (long long)jump * PS; bcur = push.box0 + (int)(qr / n2); }
     mbar_wait(full + slot, (phase >> slot) & 1u);
     phase ^= 1u << slot;
     const double* __restrict__ sbase = ring + (size_t)slot * STAGE;
 #pragma unroll
     for (int p = 0; p < PS; ++p) {
-      const double* __restrict__ cur = sbase + p * PLANE;
+      const double* __restrict__ cur = sbase + p * PLANE + so0;      // column 0 of plane q
       const bool emit = prev_out && (q - 1 >= p_lo) && (q - 1 < p_hi);
-      double* __restrict__ po = out_main + (size_t)(qr - 1) * PLANE;
+      if (!emit) {
 #pragma unroll
-      for (int m = 0; m < CPT; ++m) {
-        if (soff[m] < 0) continue;
-        const int o = soff[m];
-        const double zp = cur[o];
-        if (MODE == 1 || MODE == 3) { if (emit) po[o] = cc[m]; }
-        else if (MODE == 2) { if (emit && zp == 1.2345e300) po[o] = zp; }
-        else if (emit) {
-          const double c = cc[m];
-          const double twoc = __dmul_rn(2.0, c);
-          const double* pxm = at_lo ? prev_lo + srow[m] : prev + (o - 1);
-          const double* pxp = at_hi ? prev_hi + srow[m] : prev + (o + 1);
-          const double tx = sd2(*pxp, twoc, *pxm);
-          const double ty = sd2(prev[o + VNX], twoc, prev[o - VNX]);
-          const double tz = sd2(zp, twoc, zm[m]);
-          const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
-          po[o] = fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+        for (int m = 0; m < CPT; ++m) { zm[m] = cc[m]; cc[m] = cur[m * NT]; }
+      } else {
+        double* __restrict__ po = out_main + (size_t)(qr - 1) * PLANE + so0;
+        const double* __restrict__ pc = prev + so0;
+        // x neighbours: from the plane, or from the strip for the first / last column
+        const double* __restrict__ pxm = at_lo ? prev_lo + sr0 : pc - 1;
+        const double* __restrict__ pxp = at_hi ? prev_hi + sr0 : pc + 1;
+        const int xmstep = at_lo ? ROWS : NT, xpstep = at_hi ? ROWS : NT;   // strips advance by rows, planes by NT
+        double* __restrict__ xrow = nullptr;
+        if (PUSH) {
+          if (bprev != pbox) {           // new fab: look up the x neighbour this thread pushes into
+            pbox = bprev;
+            const int Dx = (fx && (push.mask & 1)) ? __ldg(push.nbr + (size_t)pbox * 27 + 13 + fx) : -1;
+            // a +x push lands in the neighbour's LOW strip, a -x push in its HIGH strip
+            xdst = Dx >= 0 ? push.out_level + push.xg_base + Dx * fab_xg + (fx > 0 ? 0 : (long long)n2 * N1) + sr0 : nullptr;
+          }
+          if (xdst) xrow = xdst + (long long)kz_prev * N1;
         }
-        zm[m] = cc[m];
-        cc[m] = zp;
+#pragma unroll
+        for (int m = 0; m < CPT; ++m) {
+          const double zp = cur[m * NT];
+          const double c = cc[m];
+          double r;
+          if (MODE == 1 || MODE == 3) r = c;
+          else if (MODE == 2) r = zp;
+          else {
+            const double twoc = __dmul_rn(2.0, c);
+            const double tx = sd2(pxp[m * xpstep], twoc, pxm[m * xmstep]);
+            const double ty = sd2(pc[m * NT + VNX], twoc, pc[m * NT - VNX]);
+            const double tz = sd2(zp, twoc, zm[m]);
+            const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
+            r = fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+          }
+          if (MODE != 2 || zp == 1.2345e300) po[m * NT] = r;
+          if (PUSH) { if (xrow) xrow[m * ROWS] = r; }
+          zm[m] = c;
+          cc[m] = zp;
+        }
       }
-      prev = cur;
+      prev = sbase + p * PLANE;
       prev_lo = sbase + PS * PLANE + p * STRIP;
       prev_hi = sbase + PS * PLANE + PS * STRIP + p * STRIP;
       prev_out = (kz >= NG) && (kz < n2 - NG);
+      kz_prev = kz;
+      bprev = bcur;
       ++q; ++qr;
-      if (++kz == n2) kz = 0;
+      if (++kz == n2) { kz = 0; ++bcur; }
     }
     if (t > l_begin) {                           // stage t-1 is no longer read by this warp
       __syncwarp();
@@ -216,19 +321,19 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   }
 }
 
-template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0>
+template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false>
 static int launch_cfg(const double* in_main, const double* in_xg, double* out_main, int nstages, int n2, double f,
-                      int fma, int seam, int jump, cudaStream_t s) {
+                      int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs{nullptr, nullptr, nullptr, 0, 0, 3}) {
   constexpr size_t smem = (size_t)NS * PS * ((size_t)VNX * (VNY + 2 * NG) + 2 * NG * (VNY + 2 * NG)) * 8 + 2 * NS * 8;
   static bool configured = false;
-  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE>;
+  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE, PUSH>;
   if (!configured) {
     SGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int grid = rt().sm_count;
   if (grid > nstages) grid = nstages;
-  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma, seam, jump);
+  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma, seam, jump, push);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
@@ -237,7 +342,7 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
 // Sweeps boxes [a0,a1) and [b0,b1) (a1 <= b0; the second range may be empty) in ONE launch.
 // Returns 1 when the geometry is not covered (caller falls back to the table-driven kernel).
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
-                        cudaStream_t s) {
+                        cudaStream_t s, const int* d_push_nbr) {
   if (!u->uniform || !unew->uniform || u->ncomp != 1 || unew->ncomp != 1 || u->ng != unew->ng || u->ng != 1) return 1;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0) return 1;
@@ -252,29 +357,45 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
   if (planes <= 0) return 0;
   if (planes + gap > 0x7fffffffLL) return 1;
   if (getenv("SGC_NO_STREAM")) return 1;
+  const char* pm = getenv("SGC_PUSH_MASK");
+  const PushArgs pa{d_push_nbr, (double*)unew->d_arena, (const double*)u->d_arena, unew->xg_base, a0, pm ? atoi(pm) : 3};
 #define SGC_STREAM_CASE(VX, VY, PS_, NS_, NCW_)                                                      \
-  if (vnx == VX && vny == VY && n2 % PS_ == 0)                                                       \
+  if (vnx == VX && vny == VY && n2 % PS_ == 0) {                                                     \
+    if (d_push_nbr)                                                                                  \
+      return launch_cfg<VX, VY, 1, PS_, NS_, NCW_, 0, true>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
+                                                            (int)(planesA / PS_), (int)(gap / PS_), s, pa); \
     return launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
-                                                 (int)(planesA / PS_), (int)(gap / PS_), s)
+                                                 (int)(planesA / PS_), (int)(gap / PS_), s);         \
+  }
   if (const char* m = getenv("SGC_STREAM_MODE")) {      // diagnostics only
     if (vnx == 64 && vny == 64) {
       const int ns = (int)(planes), sm = (int)planesA, jp = (int)gap;
-      if (m[0] == '1') return launch_cfg<64, 64, 1, 1, 6, 16, 1>(in_main, in_xg, out, ns, n2, f, fma, sm, jp, s);
-      if (m[0] == '2') return launch_cfg<64, 64, 1, 1, 6, 16, 2>(in_main, in_xg, out, ns, n2, f, fma, sm, jp, s);
-      if (m[0] == '3') return launch_cfg<64, 64, 1, 1, 6, 16, 3>(in_main, in_xg, out, ns, n2, f, fma, sm, jp, s);
+      if (m[0] == '1') return launch_cfg<64, 64, 1, 1, 6, SGC_NCW64, 1>(in_main, in_xg, out, ns, n2, f, fma, sm, jp, s);
+      if (m[0] == '2') return launch_cfg<64, 64, 1, 1, 6, SGC_NCW64, 2>(in_main, in_xg, out, ns, n2, f, fma, sm, jp, s);
+      if (m[0] == '3') return launch_cfg<64, 64, 1, 1, 6, SGC_NCW64, 3>(in_main, in_xg, out, ns, n2, f, fma, sm, jp, s);
     }
   }
-  SGC_STREAM_CASE(64, 64, 1, 6, 16);
-  SGC_STREAM_CASE(32, 32, 2, 10, 16);
+  SGC_STREAM_CASE(64, 64, 1, 6, SGC_NCW64);
+  SGC_STREAM_CASE(32, 32, 2, 10, 8);
   SGC_STREAM_CASE(16, 16, 6, 12, 8);
   SGC_STREAM_CASE(8, 8, 10, 24, 2);
 #undef SGC_STREAM_CASE
   return 1;
 }
 
+// does a streaming instance exist for this pair of levels?
+bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u) {
+  if (!u->uniform || !unew->uniform || u->ncomp != 1 || unew->ncomp != 1 || u->ng != 1 || unew->ng != 1) return false;
+  const FabGeom& g = u->geom[0];
+  if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0 || getenv("SGC_NO_STREAM")) return false;
+  const int vx = g.vn[0], vy = g.vn[1], n2 = g.n[2];
+  return (vx == 64 && vy == 64) || (vx == 32 && vy == 32 && n2 % 2 == 0) || (vx == 16 && vy == 16 && n2 % 6 == 0) ||
+         (vx == 8 && vy == 8 && n2 % 10 == 0);
+}
+
 int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int box_begin, int box_end,
                        cudaStream_t s) {
-  return launch_heat_stream2(unew, u, f, fma, box_begin, box_end, box_end, box_end, s);
+  return launch_heat_stream2(unew, u, f, fma, box_begin, box_end, box_end, box_end, s, nullptr);
 }
 
 }  // namespace sgc
