@@ -149,6 +149,12 @@ int sgc_level_download(sgc_level_t level, int box, void* host);
  * comp = -1: all components.  `value` points at one element of elem_bytes bytes.           */
 int sgc_level_setval(sgc_level_t level, int box, int comp, const void* value);
 
+/* Whole-level device copy dst <- src (all fabs, all components, ghosts included); both levels
+ * must share geometry.  The device form of `for (dit) dst[dit].copy(src[dit].box(), src[dit])`
+ * (BaseFab::copy(box,src), BaseFab.cpp:254-271), as WavePatch::initialData does for unm1
+ * (WavePatch.cpp:129).  One cudaMemcpyAsync device-to-device on the compute stream.            */
+int sgc_level_copy(sgc_level_t dst, sgc_level_t src);
+
 /* BaseFab::copy(dstBox,dstComp,src,srcBox,srcComp,numComp,compFlags) (BaseFab.cpp:296-329)
  * between two device fabs; BaseFab::copy(box,src) (:254-271) is the same call with equal
  * regions, comps 0..ncomp.                                                                 */

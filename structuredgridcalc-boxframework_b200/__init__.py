@@ -25,7 +25,7 @@ SYMBOLS = [
     "sgc_launch_count", "sgc_profile_enable", "sgc_profile_read", "sgc_event_create", "sgc_event_destroy", "sgc_event_record", "sgc_event_elapsed_ms",
     "sgc_host_alloc", "sgc_host_free", "sgc_layout_define", "sgc_copier_define", "sgc_level_create",
     "sgc_level_destroy", "sgc_level_elems", "sgc_level_fab_offset", "sgc_level_device_ptr", "sgc_level_upload",
-    "sgc_level_download", "sgc_level_setval", "sgc_fab_copy", "sgc_fab_linear_out", "sgc_fab_linear_in",
+    "sgc_level_download", "sgc_level_setval", "sgc_level_copy", "sgc_fab_copy", "sgc_fab_linear_out", "sgc_fab_linear_in",
     "sgc_plan_create_exchange", "sgc_plan_create_items", "sgc_plan_destroy", "sgc_plan_num_items",
     "sgc_plan_num_remote_items", "sgc_plan_num_cells", "sgc_exchange", "sgc_exchange_begin", "sgc_exchange_end",
     "sgc_plan_create_bc_zero_gradient", "sgc_heat_sweep", "sgc_heat_sweep_range", "sgc_heat_sweep_ranges", "sgc_laplacian_apply",
@@ -94,6 +94,7 @@ def lib():
     L.sgc_level_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.sgc_level_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.sgc_level_setval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.sgc_level_copy.argtypes = [C.c_void_p, C.c_void_p]
     L.sgc_fab_copy.argtypes = [C.c_void_p, C.c_int, _i3, _i3, C.c_int, C.c_void_p, C.c_int, _i3, _i3, C.c_int, C.c_int,
                                C.c_uint]
     L.sgc_fab_linear_out.argtypes = [C.c_void_p, C.c_int, _i3, _i3, C.c_int, C.c_int, C.c_uint, C.c_void_p]
@@ -336,6 +337,10 @@ class LevelData:
     def setVal(self, value, comp=-1, box=-1):
         v = np.array([value], self.dtype)
         check(lib().sgc_level_setval(self.h, box, comp, v.ctypes.data))
+
+    def copyFrom(self, src):
+        """whole-level device copy (same geometry), ghosts included"""
+        check(lib().sgc_level_copy(self.h, src.h))
 
     def exchange(self, copier):
         check(lib().sgc_exchange(self.h, copier.h))

@@ -28,7 +28,7 @@ int sweep_tile_z();
 int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int box_begin, int box_end,
                        cudaStream_t s);
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
-                        cudaStream_t s, const int* d_push_nbr);
+                        cudaStream_t s, const int* d_push_nbr, int push_mask = 7);
 bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u);
 // multi-rank transport (sgc_comm.cu)
 int comm_plan_setup(sgc_plan_s* plan, sgc_level_s* level, const Grid& g, unsigned periodic, unsigned trim);
@@ -485,6 +485,16 @@ int sgc_level_setval(sgc_level_t l, int box, int comp, const void* value) {
   return 0;
 }
 
+int sgc_level_copy(sgc_level_t dst, sgc_level_t src) {
+  SGC_REQUIRE_RT();
+  if (!dst || !src) return fail(SGC_ERR_ARG, "sgc_level_copy: null level");
+  if (!same_geometry(dst, src)) return fail(SGC_ERR_GEOMETRY, "sgc_level_copy: levels must share geometry");
+  if (dst == src) return 0;
+  SGC_CUDA(cudaMemcpyAsync(dst->d_arena, src->d_arena, (size_t)dst->arena_elems * dst->esz, cudaMemcpyDeviceToDevice,
+                           rt().compute));
+  return 0;
+}
+
 int sgc_fab_copy(sgc_level_t dst, int dst_box, const int dlo[3], const int dhi[3], int dst_comp, sgc_level_t src,
                  int src_box, const int slo[3], const int shi[3], int src_comp, int ncomp, unsigned comp_flags) {
   SGC_REQUIRE_RT();
@@ -624,9 +634,9 @@ int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], 
       const int code = (1 - it.dir[0]) + 3 * (1 - it.dir[1]) + 9 * (1 - it.dir[2]);
       nbr[(size_t)S * 27 + code] = D;
     }
-    cudaError_t e = cudaMalloc(&p->d_push, sizeof(int) * nbr.size());
+    cudaError_t e = st ? cudaErrorUnknown : cudaMalloc(&p->d_push, sizeof(int) * nbr.size());
     if (e == cudaSuccess) e = cudaMemcpy(p->d_push, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) st = fail(SGC_ERR_CUDA, std::string("push table: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess && !st) st = fail(SGC_ERR_CUDA, std::string("push table: ") + cudaGetErrorString(e));
     p->fusable = (st == 0);
   }
   if (st) { sgc_plan_destroy(p); return st; }
@@ -807,7 +817,7 @@ int sgc_heat_sweep_ranges(sgc_level_t nxt, sgc_level_t cur, double f, unsigned f
   if (a0 < 0 || a0 > a1 || a1 > b0 || b0 > b1 || b1 > nxt->nbox) return fail(SGC_ERR_ARG, "sgc_heat_sweep_ranges: box ranges");
   {
     ProfScope prof(0, rt().compute);
-    st = launch_heat_stream2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, a0, a1, b0, b1, rt().compute, nullptr);
+    st = launch_heat_stream2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, a0, a1, b0, b1, rt().compute, nullptr, 0);
   }
   if (st <= 0) return st;
   st = sgc_heat_sweep_range(nxt, cur, f, flags, a0, a1);
@@ -817,9 +827,9 @@ int sgc_heat_sweep_ranges(sgc_level_t nxt, sgc_level_t cur, double f, unsigned f
 
 // streaming sweep of boxes [a0,a1) + [b0,b1) that also fills the ghosts of nxt's neighbours
 static int fused_sweep(sgc_level_t nxt, sgc_level_t cur, double f, unsigned flags, int a0, int a1, int b0, int b1,
-                       const int* d_push) {
+                       const int* d_push, int mask) {
   ProfScope prof(0, rt().compute);
-  const int st = launch_heat_stream2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, a0, a1, b0, b1, rt().compute, d_push);
+  const int st = launch_heat_stream2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, a0, a1, b0, b1, rt().compute, d_push, mask);
   return st > 0 ? fail(SGC_ERR_UNSUPPORTED, "fused sweep: no streaming kernel for this geometry") : st;
 }
 
@@ -848,22 +858,25 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
   // first, their halo packed and sent on the comm stream while the interior boxes sweep; the last
   // two steps run unfused, which leaves BOTH levels bit-identical, ghost cells included, to
   // nstep x { exchange ; sweep } (the fused steps do not maintain edge / corner / y / z ghosts).
-  // (boxes narrower than 32 cells stay unfused: their pulled y rows are 64-128 byte copies, which makes
-  // the producer issue-bound — measured 120 vs 149 Gcell/s on 16^3 boxes)
+  // Only boxes at least 32 cells wide run fused.  Measured on 16^3 boxes (32 768 of them): every
+  // 8th cell of a row lies on an x face, so the single-lane x pushes double the sweep time, and the
+  // pulled y rows are 128-byte copies that make the producer issue-bound: 120-137 Gcell/s fused
+  // against 149 unfused.
   const bool fused = plan->fusable && nstep >= 3 && heat_stream_covers(b, a) && a->geom[0].vn[0] >= 32 &&
                      !getenv("SGC_NO_FUSE");
+  const int fmask = 7;                                 // bit 0 push x, bit 1 pull z, bit 2 pull y
   int s0 = 0;
   if (fused) {
     st = sgc_exchange(cur, plan);
     for (; s0 < nstep - 2 && !st; ++s0) {
       if (plan->nremote > 0) {
-        if (split) st = fused_sweep(nxt, cur, f, flags, 0, b0, b1, cur->nbox, plan->d_push);
-        else st = fused_sweep(nxt, cur, f, flags, 0, cur->nbox, cur->nbox, cur->nbox, plan->d_push);
+        if (split) st = fused_sweep(nxt, cur, f, flags, 0, b0, b1, cur->nbox, plan->d_push, fmask);
+        else st = fused_sweep(nxt, cur, f, flags, 0, cur->nbox, cur->nbox, cur->nbox, plan->d_push, fmask);
         if (!st) st = comm_exchange_begin(nxt, plan);            // pack nxt's boundary cells, send/recv
-        if (!st && split) st = fused_sweep(nxt, cur, f, flags, b0, b1, b1, b1, plan->d_push);
+        if (!st && split) st = fused_sweep(nxt, cur, f, flags, b0, b1, b1, b1, plan->d_push, fmask);
         if (!st) st = comm_exchange_end(nxt, plan);              // unpack into nxt's remote-facing ghosts
       } else {
-        st = fused_sweep(nxt, cur, f, flags, 0, cur->nbox, cur->nbox, cur->nbox, plan->d_push);
+        st = fused_sweep(nxt, cur, f, flags, 0, cur->nbox, cur->nbox, cur->nbox, plan->d_push, fmask);
       }
       std::swap(cur, nxt);
     }

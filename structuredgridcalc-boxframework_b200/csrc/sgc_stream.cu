@@ -116,7 +116,7 @@ struct PushArgs {
   const double* in_level;   // arena base of the input level
   long long xg_base;     // element offset of the xg regions (same geometry for both levels)
   int box0;              // local index of the first box of this launch
-  int mask;              // diagnostics: bit 0 = x-face pushes, bit 1 = y/z pulls (default 3)
+  int mask;              // bit 0 = push x faces, bit 1 = pull z planes, bit 2 = pull y rows
 };
 
 template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false>
@@ -178,7 +178,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
           double* dst = ring + (size_t)slot * STAGE;
           const double* xg = in_xg + box * xfab + (long long)kz0 * STRIP;
           mbar_expect_tx(full + slot, MAIN_BYTES + 2 * STRIP_BYTES);
-          if (!PUSH || !(push.mask & 2)) {
+          if (!PUSH || !(push.mask & 6)) {
             bulk_g2s(dst, in_main + (size_t)tr * (PS * PLANE), MAIN_BYTES, full + slot);
           } else {
             // pull: y-ghost rows and z-ghost planes come from the neighbours' valid cells
@@ -186,7 +186,9 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
             if (b != pb) {
               pb = b;
               const int* __restrict__ nb = push.nbr + (size_t)b * 27;
-              dym = __ldg(nb + 13 - 3); dyp = __ldg(nb + 13 + 3); dzm = __ldg(nb + 13 - 9); dzp = __ldg(nb + 13 + 9);
+              const bool py = (push.mask & 4) != 0, pz = (push.mask & 2) != 0;
+              dym = py ? __ldg(nb + 13 - 3) : -1; dyp = py ? __ldg(nb + 13 + 3) : -1;
+              dzm = pz ? __ldg(nb + 13 - 9) : -1; dzp = pz ? __ldg(nb + 13 + 9) : -1;
             }
             const long long fabm = (long long)PLANE * n2;
             const int vnz_ = n2 - 2 * NG;
@@ -323,7 +325,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
 
 template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false>
 static int launch_cfg(const double* in_main, const double* in_xg, double* out_main, int nstages, int n2, double f,
-                      int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs{nullptr, nullptr, nullptr, 0, 0, 3}) {
+                      int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs{nullptr, nullptr, nullptr, 0, 0, 0}) {
   constexpr size_t smem = (size_t)NS * PS * ((size_t)VNX * (VNY + 2 * NG) + 2 * NG * (VNY + 2 * NG)) * 8 + 2 * NS * 8;
   static bool configured = false;
   auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE, PUSH>;
@@ -342,7 +344,7 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
 // Sweeps boxes [a0,a1) and [b0,b1) (a1 <= b0; the second range may be empty) in ONE launch.
 // Returns 1 when the geometry is not covered (caller falls back to the table-driven kernel).
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
-                        cudaStream_t s, const int* d_push_nbr) {
+                        cudaStream_t s, const int* d_push_nbr, int push_mask) {
   if (!u->uniform || !unew->uniform || u->ncomp != 1 || unew->ncomp != 1 || u->ng != unew->ng || u->ng != 1) return 1;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0) return 1;
@@ -358,7 +360,7 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
   if (planes + gap > 0x7fffffffLL) return 1;
   if (getenv("SGC_NO_STREAM")) return 1;
   const char* pm = getenv("SGC_PUSH_MASK");
-  const PushArgs pa{d_push_nbr, (double*)unew->d_arena, (const double*)u->d_arena, unew->xg_base, a0, pm ? atoi(pm) : 3};
+  const PushArgs pa{d_push_nbr, (double*)unew->d_arena, (const double*)u->d_arena, unew->xg_base, a0, pm ? atoi(pm) : push_mask};
 #define SGC_STREAM_CASE(VX, VY, PS_, NS_, NCW_)                                                      \
   if (vnx == VX && vny == VY && n2 % PS_ == 0) {                                                     \
     if (d_push_nbr)                                                                                  \
@@ -395,7 +397,7 @@ bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u) {
 
 int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int box_begin, int box_end,
                        cudaStream_t s) {
-  return launch_heat_stream2(unew, u, f, fma, box_begin, box_end, box_end, box_end, s, nullptr);
+  return launch_heat_stream2(unew, u, f, fma, box_begin, box_end, box_end, box_end, s, nullptr, 0);
 }
 
 }  // namespace sgc

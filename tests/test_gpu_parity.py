@@ -57,6 +57,20 @@ def test_upload_download_roundtrip_and_setval(g, oracle):
     assert (got[0] == 7.0).all() and (got[1] == -1.25).all()
 
 
+def test_level_copy(g):
+    rng = np.random.default_rng(12)
+    dbl, a = make_level(g, (0, 0, 0), (15, 7, 7), (4, 4, 4), 2, 1)
+    b = g.LevelData(dbl, 2, 1)
+    u = rng.standard_normal(a.elems)
+    a.upload(u)
+    b.setVal(-3.0)
+    b.copyFrom(a)
+    assert np.array_equal(b.download(), u) and np.array_equal(a.download(), u)
+    _, c = make_level(g, (0, 0, 0), (15, 7, 7), (4, 4, 4), 1, 1)
+    with pytest.raises(g.SgcError):
+        c.copyFrom(a)
+
+
 def test_int_and_byte_fabs(g, oracle):
     # BaseFab<int> on an offset box (testBaseFab.cpp:114-140) and BaseFab<char>/<bool>
     rng = np.random.default_rng(1)
