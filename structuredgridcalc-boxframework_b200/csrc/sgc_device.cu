@@ -865,6 +865,8 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
   const bool fused = plan->fusable && nstep >= 3 && heat_stream_covers(b, a) && a->geom[0].vn[0] >= 32 &&
                      !getenv("SGC_NO_FUSE");
   const int fmask = 7;                                 // bit 0 push x, bit 1 pull z, bit 2 pull y
+  const char* cs = getenv("SGC_COMM_SMS");
+  const int comm_sms = cs ? atoi(cs) : 8;              // SMs left to pack / NCCL / unpack during the interior sweep
   int s0 = 0;
   if (fused) {
     st = sgc_exchange(cur, plan);
@@ -873,7 +875,11 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
         if (split) st = fused_sweep(nxt, cur, f, flags, 0, b0, b1, cur->nbox, plan->d_push, fmask);
         else st = fused_sweep(nxt, cur, f, flags, 0, cur->nbox, cur->nbox, cur->nbox, plan->d_push, fmask);
         if (!st) st = comm_exchange_begin(nxt, plan);            // pack nxt's boundary cells, send/recv
+        // the interior sweep is persistent (one CTA per SM, 209 KB of shared memory each): leave a few
+        // SMs free, otherwise NCCL's CTAs cannot be placed until it ends and the halo is not overlapped
+        rt().sweep_grid_cap = rt().sm_count - comm_sms;
         if (!st && split) st = fused_sweep(nxt, cur, f, flags, b0, b1, b1, b1, plan->d_push, fmask);
+        rt().sweep_grid_cap = 0;
         if (!st) st = comm_exchange_end(nxt, plan);              // unpack into nxt's remote-facing ghosts
       } else {
         st = fused_sweep(nxt, cur, f, flags, 0, cur->nbox, cur->nbox, cur->nbox, plan->d_push, fmask);

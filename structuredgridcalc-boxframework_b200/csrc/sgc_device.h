@@ -106,6 +106,7 @@ struct Runtime {
   cudaStream_t compute = nullptr;
   cudaStream_t comm = nullptr;
   long long launches = 0;
+  int sweep_grid_cap = 0;               // > 0: persistent sweeps use at most this many CTAs (leaves SMs to NCCL)
 };
 Runtime& rt();
 
@@ -173,10 +174,9 @@ struct sgc_plan_s {
     long long send_elems = 0, recv_elems = 0;
   };
   std::vector<Peer> peers;
-  std::vector<int> interior_boxes_first;  // not used yet
   int n_boundary_boxes = 0;               // boxes with at least one remote item
   std::vector<char> box_is_boundary;
-  cudaEvent_t ev_local = nullptr, ev_halo = nullptr, ev_ready = nullptr;
+  cudaEvent_t ev_halo = nullptr, ev_ready = nullptr;    // halo received / data to exchange produced
   bool in_flight = false;
   // fused ghost fill (sweep pushes boundary cells into the neighbours' ghosts): destination local
   // box per (box, direction code), -1 where there is no local motion item

@@ -334,6 +334,7 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
     configured = true;
   }
   int grid = rt().sm_count;
+  if (rt().sweep_grid_cap > 0 && rt().sweep_grid_cap < grid) grid = rt().sweep_grid_cap;
   if (grid > nstages) grid = nstages;
   kern<<<grid, (NCW + 1) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma, seam, jump, push);
   rt().launches++;

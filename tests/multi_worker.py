@@ -87,8 +87,9 @@ def run_gpu(rank, world, local_rank):
     ids = [sgc.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     sgc.comm_init(world, rank, ids[0])
-    for dlo, dhi, mb, per, f, nstep in (((0, 0, 0), (31, 31, 63), (16, 16, 16), 7, 0.125, 12),
-                                        ((0, 0, 0), (63, 63, 127), (64, 64, 64), 7, 1.0 / 6.0, 6),
+    for dlo, dhi, mb, per, f, nstep in (((0, 0, 0), (31, 31, 32 * world - 1), (16, 16, 16), 7, 0.125, 12),
+                                        ((0, 0, 0), (63, 63, 64 * world - 1), (64, 64, 64), 7, 1.0 / 6.0, 6),
+                                        ((0, 0, 0), (63, 31, 64 * world - 1), (32, 32, 32), 3, 0.125, 9),
                                         ((0, 0, 0), (15, 15, 8 * world - 1), (8, 8, 8), 0, 0.125, 5),
                                         ((0, 0, 0), (11, 7, 10 * world - 1), (6, 4, 5), 3, 0.2, 4)):
         dbl = sgc.DisjointBoxLayout(sgc.Box(dlo, dhi), mb, world, rank)

@@ -41,3 +41,37 @@ def test_multirank_nccl_halo_parity():
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     out = _launch("gpu", 2)
     assert out.count("gpu multi-rank parity ok") == 2
+
+
+@pytest.mark.gpu
+def test_cpp_facade_driver_two_ranks(oracle, tmp_path):
+    """apps/levelheat (written against the C++ facade, DisjointBoxLayout::initMPI + NCCL id through
+    $SGC_COMM_FILE) as two processes on two GPUs; each rank's hash of its boxes against the oracle."""
+    import json
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    exe = os.path.join(ROOT, "apps", "_build", "levelheat")
+    if not os.path.exists(exe):
+        pytest.skip("apps/_build/levelheat not built")
+    n, bs, nstep, world = 64, 32, 20, 2
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, SGC_RANK=str(r), SGC_NPROC=str(world), SGC_DEVICE=str(r),
+                   SGC_COMM_FILE=str(tmp_path / "ncclid"))
+        procs.append(subprocess.Popen([exe, str(n), str(bs), str(nstep)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    dlo, dhi, mb = (0, 0, 0), (n - 1, n - 1, n * world - 1), (bs,) * 3
+    boxes, owner, _ = oracle.layout(dlo, dhi, mb, world)
+    u = oracle.fill_hash(boxes, 1, 0.0)
+    oracle.level_heat(dlo, dhi, mb, 1, 7, 0, 0.125, nstep, u, 1)
+    m = bs + 2
+    for r, (p, (out, err)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, out + err
+        line = json.loads(out.strip().splitlines()[-1])
+        assert line["rank"] == r and line["nproc"] == world
+        chunks = [u[b * m ** 3:(b + 1) * m ** 3].reshape(m, m, m)[1:-1, 1:-1, 1:-1].ravel()
+                  for b in range(len(boxes)) if owner[b] == r]
+        assert line["local_fnv1a64"] == "%016x" % oracle.fnv1a64(np.concatenate(chunks)), (r, line)
