@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sweeps", type=int, default=100, help="sweeps per step (config: 100)")
-    ap.add_argument("--domain", type=int, default=512, help="cells per side per GPU")
+    ap.add_argument("--domain", type=int, default=512, help="cells per side per GPU (x, y and z-per-GPU)")
+    ap.add_argument("--domain-z", type=int, default=0,
+                    help="z cells per GPU if different from --domain (C4: --domain 1024 --domain-z 128)")
     ap.add_argument("--box", type=int, default=64)
     ap.add_argument("--f", type=float, default=0.125)
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -193,11 +195,12 @@ def run_reference_arm(a):
 
 
 def workload_config(a, n):
+    zper = a.domain_z or a.domain
     return {"workload": "C2: %dx%dx%d level in %d^3 boxes, 1 ghost, periodic xyz, %d x {exchange; 7-pt heat sweep} per step"
-                        % (a.domain, a.domain, a.domain * n, a.box, a.sweeps),
-            "domain": [a.domain, a.domain, a.domain * n], "box": a.box, "nghost": 1, "ncomp": 1,
+                        % (a.domain, a.domain, zper * n, a.box, a.sweeps),
+            "domain": [a.domain, a.domain, zper * n], "box": a.box, "nghost": 1, "ncomp": 1,
             "sweeps_per_step": a.sweeps, "f": a.f, "periodic": "xyz", "partition": "z-slabs, owner = idx/(nbox/N)",
-            "l2_policy": "inputs larger than L2 (2 x %.2f GB per GPU)" % (((a.domain // a.box) ** 3) * (a.box + 2) ** 3 * 8 / 1e9)}
+            "l2_policy": "inputs larger than L2 (2 x %.2f GB per GPU)" % (((a.domain // a.box) ** 2 * (zper // a.box)) * (a.box + 2) ** 3 * 8 / 1e9)}
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -239,6 +242,7 @@ def main():
         dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     n_gpus = world
 
+    zper = a.domain_z or a.domain
     from _loadpkg import load_package
     sgc = load_package()
     sgc.init(local_rank)
@@ -247,11 +251,11 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         sgc.comm_init(world, rank, ids[0])
 
-    dom = sgc.Box((0, 0, 0), (a.domain - 1, a.domain - 1, a.domain * world - 1))
+    dom = sgc.Box((0, 0, 0), (a.domain - 1, a.domain - 1, zper * world - 1))
     dbl = sgc.DisjointBoxLayout(dom, a.box, world, rank)
     A = sgc.LevelData(dbl, 1, 1)
     B = sgc.LevelData(dbl, 1, 1)
-    cells_local = float(a.domain) ** 3
+    cells_local = float(a.domain) ** 2 * zper
     cells_total = cells_local * world
 
     pin_in = sgc.PinnedBuffer(A.elems)

@@ -51,6 +51,7 @@ class Oracle:
         L.sgco_level_heat_sweep.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_int]
         L.sgco_level_heat.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_double, C.c_int,
                                       C.c_int, _dp, _dp]
+        L.sgco_level_wave_sweep.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_int]
         L.sgco_laplacian.argtypes = [C.c_int, C.c_int, _dp, _dp]
         L.sgco_wave.argtypes = [_i3, _i3, C.c_double, C.c_int, C.c_int, _dp, _dp]
         L.sgco_bc_zero_gradient.argtypes = [_i3, _i3, C.c_int, _dp]
@@ -110,6 +111,10 @@ class Oracle:
     def level_heat_sweep(self, boxes, ng, u, unew, f, contract=1):
         boxes = np.ascontiguousarray(boxes, np.int32)
         self.lib.sgco_level_heat_sweep(boxes, len(boxes), ng, u, unew, f, contract)
+
+    def level_wave_sweep(self, boxes, ng, un, unm1, unp1, factor, contract=1):
+        boxes = np.ascontiguousarray(boxes, np.int32)
+        self.lib.sgco_level_wave_sweep(boxes, len(boxes), ng, un, unm1, unp1, factor, contract)
 
     def level_heat(self, dlo, dhi, maxbox, ng, periodic, trim, f, nstep, fabs, contract=1):
         t = np.zeros(3)

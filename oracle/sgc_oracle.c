@@ -503,6 +503,20 @@ void sgco_wave_box(const int* flo, const int* fhi, const double* un, const doubl
         }
 }
 
+/* the same update over every box of a level (1 comp, ng ghosts, ghosts of un already filled) */
+void sgco_level_wave_sweep(const int* boxes6, int nbox, int ng, const double* un, const double* unm1,
+                           double* unp1, double factor, int contract)
+{
+  long off = 0;
+  for (int b = 0; b < nbox; ++b)
+    {
+      obox fb = mk(boxes6 + 6*b, boxes6 + 6*b + 3);
+      box_grow(&fb, ng);
+      sgco_wave_box(fb.lo, fb.hi, un + off, unm1 + off, unp1 + off, boxes6 + 6*b, boxes6 + 6*b + 3, factor, contract);
+      off += box_size(&fb);
+    }
+}
+
 /* nstep x { BC ; update ; rotate } on one box (WavePatch::advance, WavePatch.cpp:136-254).
  * u0 = u^n, u1 = u^{n-1} on grow(domain,1); on exit u0 = latest, u1 = previous.           */
 void sgco_wave(const int* dlo, const int* dhi, double factor, int nstep, int contract,

@@ -30,6 +30,7 @@ int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
                         cudaStream_t s, const int* d_push_nbr, int push_mask = 7);
 bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u);
+int launch_wave_stream(sgc_level_s* unp1, sgc_level_s* un, sgc_level_s* unm1, double f, int fma, cudaStream_t s);
 // multi-rank transport (sgc_comm.cu)
 int comm_plan_setup(sgc_plan_s* plan, sgc_level_s* level, const Grid& g, unsigned periodic, unsigned trim);
 void comm_plan_release(sgc_plan_s* plan);
@@ -805,6 +806,9 @@ int sgc_wave_step(sgc_level_t unp1, sgc_level_t un, sgc_level_t unm1, double fac
   if (st) return st;
   if (!unm1 || !same_geometry(un, unm1)) return fail(SGC_ERR_GEOMETRY, "sgc_wave_step: un and unm1 must share geometry");
   if (unm1 == unp1) return fail(SGC_ERR_ARG, "sgc_wave_step: unp1 must not alias unm1");
+  ProfScope prof(0, rt().compute);
+  st = launch_wave_stream(unp1, un, unm1, factor, (flags & SGC_FMA) ? 1 : 0, rt().compute);
+  if (st <= 0) return st;
   return launch_wave_generic(unp1->d_work, 0, unp1->nwork, un->d_geom, unp1->d_geom, (const double*)un->d_arena,
                              (double*)unp1->d_arena, (const double*)unm1->d_arena, factor, (flags & SGC_FMA) ? 1 : 0,
                              rt().compute);

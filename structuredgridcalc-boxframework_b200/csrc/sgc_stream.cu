@@ -119,10 +119,14 @@ struct PushArgs {
   int mask;              // bit 0 = push x faces, bit 1 = pull z planes, bit 2 = pull y rows
 };
 
-template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false>
+// OP: 0 = heat / Jacobi (unew = u + f*S), 1 = leap-frog wave (unp1 = 2 un - unm1 + f*Tx + f*Ty + f*Tz,
+// WavePatch.cpp:226-244).  For the wave every ring slot also carries the valid rows of unm1 for the
+// planes that are emitted when the slot arrives (one more bulk copy per plane; read back with LDS).
+template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1)
 k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_xg, double* __restrict__ out_main,
-              int nstages, int n2, double f, int fma, int seam, int jump, PushArgs push) {
+              int nstages, int n2, double f, int fma, int seam, int jump, PushArgs push,
+              const double* __restrict__ aux_main) {
   // The launch covers the box range as a virtual stage sequence [0, nstages); stages >= seam live
   // `jump` stages further on in memory (a second box range, e.g. the two boundary box layers of a
   // z-slab).  Both ranges start and end on fab boundaries, so the seam sits between two ghost planes.
@@ -130,8 +134,10 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   constexpr int N1 = VNY + 2 * NG;
   constexpr int PLANE = VNX * N1;                // elements per main plane (dense rows, y ghosts included)
   constexpr int STRIP = NG * N1;                 // elements per x-ghost strip of one plane and side
-  constexpr int STAGE = PS * (PLANE + 2 * STRIP);   // elements per ring slot: planes | low strips | high strips
-  constexpr uint32_t MAIN_BYTES = PS * PLANE * 8u, STRIP_BYTES = PS * STRIP * 8u;
+  constexpr int AUXP = (OP == 1) ? VNX * VNY : 0;   // elements of the third level carried per plane (valid rows)
+  constexpr int STAGE = PS * (PLANE + 2 * STRIP + AUXP);   // ring slot: planes | low strips | high strips | aux rows
+  constexpr int AUX_OFF = PS * (PLANE + 2 * STRIP);
+  constexpr uint32_t MAIN_BYTES = PS * PLANE * 8u, STRIP_BYTES = PS * STRIP * 8u, AUX_BYTES = PS * AUXP * 8u;
   constexpr int COLS = VNX * VNY;
   constexpr int CPT = (COLS + NT - 1) / NT;      // columns per consumer thread
   static_assert(NG == 1, "one ghost layer");
@@ -177,7 +183,16 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
           const int kz0 = (int)(pl - box * n2);
           double* dst = ring + (size_t)slot * STAGE;
           const double* xg = in_xg + box * xfab + (long long)kz0 * STRIP;
-          mbar_expect_tx(full + slot, MAIN_BYTES + 2 * STRIP_BYTES);
+          mbar_expect_tx(full + slot, MAIN_BYTES + 2 * STRIP_BYTES + AUX_BYTES);
+          if (OP == 1) {
+            // unm1 valid rows of planes pl-1 .. pl+PS-2 (the planes emitted while this stage is read);
+            // the very first plane of the level has no predecessor: load plane 0 instead (never used)
+#pragma unroll
+            for (int p = 0; p < PS; ++p) {
+              const long long ap = (pl + p > 0) ? pl + p - 1 : 0;
+              bulk_g2s(dst + AUX_OFF + p * AUXP, aux_main + ap * PLANE + NG * VNX, AUXP * 8u, full + slot);
+            }
+          }
           if (!PUSH || !(push.mask & 6)) {
             bulk_g2s(dst, in_main + (size_t)tr * (PS * PLANE), MAIN_BYTES, full + slot);
           } else {
@@ -270,6 +285,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
       } else {
         double* __restrict__ po = out_main + (size_t)(qr - 1) * PLANE + so0;
         const double* __restrict__ pc = prev + so0;
+        const double* __restrict__ pa = sbase + AUX_OFF + p * AUXP + (so0 - NG * VNX);   // OP 1: unm1 of plane q-1
         // x neighbours: from the plane, or from the strip for the first / last column
         const double* __restrict__ pxm = at_lo ? prev_lo + sr0 : pc - 1;
         const double* __restrict__ pxp = at_hi ? prev_hi + sr0 : pc + 1;
@@ -296,8 +312,14 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
             const double tx = sd2(pxp[m * xpstep], twoc, pxm[m * xmstep]);
             const double ty = sd2(pc[m * NT + VNX], twoc, pc[m * NT - VNX]);
             const double tz = sd2(zp, twoc, zm[m]);
-            const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
-            r = fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+            if (OP == 0) {
+              const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
+              r = fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+            } else {
+              r = __dsub_rn(twoc, pa[m * NT]);
+              if (fma) { r = __fma_rn(f, tx, r); r = __fma_rn(f, ty, r); r = __fma_rn(f, tz, r); }
+              else { r = __dadd_rn(r, __dmul_rn(f, tx)); r = __dadd_rn(r, __dmul_rn(f, ty)); r = __dadd_rn(r, __dmul_rn(f, tz)); }
+            }
           }
           if (MODE != 2 || zp == 1.2345e300) po[m * NT] = r;
           if (PUSH) { if (xrow) xrow[m * ROWS] = r; }
@@ -323,12 +345,15 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   }
 }
 
-template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false>
+template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0>
 static int launch_cfg(const double* in_main, const double* in_xg, double* out_main, int nstages, int n2, double f,
-                      int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs{nullptr, nullptr, nullptr, 0, 0, 0}) {
-  constexpr size_t smem = (size_t)NS * PS * ((size_t)VNX * (VNY + 2 * NG) + 2 * NG * (VNY + 2 * NG)) * 8 + 2 * NS * 8;
+                      int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs{nullptr, nullptr, nullptr, 0, 0, 0},
+                      const double* aux_main = nullptr) {
+  constexpr size_t smem = (size_t)NS * PS * ((size_t)VNX * (VNY + 2 * NG) + 2 * NG * (VNY + 2 * NG) +
+                                             (OP == 1 ? (size_t)VNX * VNY : 0)) * 8 + 2 * NS * 8;
+  static_assert(smem <= 232448, "ring exceeds the 227 KB of shared memory a CTA can have");
   static bool configured = false;
-  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE, PUSH>;
+  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE, PUSH, OP>;
   if (!configured) {
     SGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
@@ -336,7 +361,7 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
   int grid = rt().sm_count;
   if (rt().sweep_grid_cap > 0 && rt().sweep_grid_cap < grid) grid = rt().sweep_grid_cap;
   if (grid > nstages) grid = nstages;
-  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma, seam, jump, push);
+  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma, seam, jump, push, aux_main);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
@@ -383,6 +408,34 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
   SGC_STREAM_CASE(16, 16, 6, 12, 8);
   SGC_STREAM_CASE(8, 8, 10, 24, 2);
 #undef SGC_STREAM_CASE
+  return 1;
+}
+
+// Leap-frog wave step over all boxes with the streaming pipeline; 1 when the geometry is not covered.
+int launch_wave_stream(sgc_level_s* unp1, sgc_level_s* un, sgc_level_s* unm1, double f, int fma, cudaStream_t s) {
+  if (!un->uniform || un->ncomp != 1 || unp1->ncomp != 1 || unm1->ncomp != 1 || un->ng != 1 || unp1->ng != 1 ||
+      unm1->ng != 1 || getenv("SGC_NO_STREAM"))
+    return 1;
+  const FabGeom& g = un->geom[0];
+  if (memcmp(g.n, unp1->geom[0].n, sizeof g.n) != 0 || memcmp(g.n, unm1->geom[0].n, sizeof g.n) != 0 || !unp1->uniform ||
+      !unm1->uniform)
+    return 1;
+  const int vnx = g.vn[0], vny = g.vn[1], n2 = g.n[2];
+  const long long planes = (long long)un->nbox * n2;
+  if (planes > 0x7fffffffLL) return 1;
+  const double* in_main = (const double*)un->d_arena;
+  const double* in_xg = in_main + un->xg_base;
+  double* out = (double*)unp1->d_arena;
+  const double* aux = (const double*)unm1->d_arena;
+  const PushArgs none{nullptr, nullptr, nullptr, 0, 0, 0};
+#define SGC_WAVE_CASE(VX, VY, PS_, NS_, NCW_)                                                                   \
+  if (vnx == VX && vny == VY && n2 % PS_ == 0)                                                                  \
+    return launch_cfg<VX, VY, 1, PS_, NS_, NCW_, 0, false, 1>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
+                                                              (int)(planes / PS_), 0, s, none, aux)
+  SGC_WAVE_CASE(64, 64, 1, 3, 16);
+  SGC_WAVE_CASE(32, 32, 2, 6, 8);
+  SGC_WAVE_CASE(16, 16, 6, 7, 8);
+#undef SGC_WAVE_CASE
   return 1;
 }
 

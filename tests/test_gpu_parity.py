@@ -398,6 +398,30 @@ def test_wave_and_zero_gradient_bc(g, golden, oracle):
         assert np.array_equal(got[lev.fab_offset(b):lev.fab_offset(b) + lev.fab_elems(b)], f.ravel()), b
 
 
+def test_wave_level_streaming_and_generic(g, oracle):
+    # leap-frog update on box-decomposed levels (streaming instances 64/32/16 and the generic kernel),
+    # both FMA modes, against the oracle's per-box restatement of WavePatch.cpp:226-244
+    rng = np.random.default_rng(13)
+    for mb, nb in (((64, 64, 64), (1, 1, 2)), ((32, 32, 32), (2, 1, 2)), ((16, 16, 16), (2, 2, 3)), ((6, 4, 5), (2, 2, 2))):
+        dlo = (0, 0, 0)
+        dhi = tuple(mb[d] * nb[d] - 1 for d in range(3))
+        dbl, un = make_level(g, dlo, dhi, mb, 1, 1)
+        unm1, unp1 = g.LevelData(dbl, 1, 1), g.LevelData(dbl, 1, 1)
+        a, b, c = (rng.standard_normal(un.elems) for _ in range(3))
+        cp = g.Copier().defineExchangeLD(un, 7, 0)
+        items = oracle.copier_items(dlo, dhi, mb, 1, 7, 0)
+        for contract in (1, 0):
+            un.upload(a); unm1.upload(b); unp1.upload(c)
+            un.exchange(cp)
+            g.wave_step(unp1, un, unm1, 0.07, g.SGC_FMA if contract else 0)
+            wa = a.copy()
+            oracle.level_exchange(dbl.boxes, 1, 1, items, wa)
+            want = c.copy()
+            oracle.level_wave_sweep(dbl.boxes, 1, wa, b, want, 0.07, contract)
+            assert np.array_equal(unp1.download(), want), (mb, contract)
+            assert np.array_equal(unm1.download(), b)
+
+
 def test_sweep_box_ranges_streaming_kernel(g, oracle):
     # the streaming kernel on sub-ranges and on two ranges in one launch (boundary box layers)
     rng = np.random.default_rng(11)
