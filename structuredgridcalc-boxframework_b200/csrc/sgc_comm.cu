@@ -15,6 +15,7 @@
 #include <nccl.h>   // types only; no link-time dependency
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "sgc_device.h"
@@ -30,6 +31,7 @@ struct NcclApi {
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -63,6 +65,7 @@ static int load_nccl() {
   SGC_SYM(Recv, "ncclRecv");
   SGC_SYM(GroupStart, "ncclGroupStart");
   SGC_SYM(GroupEnd, "ncclGroupEnd");
+  SGC_SYM(AllReduce, "ncclAllReduce");
   SGC_SYM(GetErrorString, "ncclGetErrorString");
 #undef SGC_SYM
   return 0;
@@ -192,6 +195,146 @@ int comm_exchange_end(sgc_level_s* l, sgc_plan_s* p) {
     const int st = launch_copy(q.unpack, l->d_arena, q.d_recv, l->esz, r.compute);
     if (st) return st;
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory halo session for a fused step loop on a z-slab partition.
+//
+// The reference moves a halo as: pack on the sender, MPI message, unpack on the receiver
+// (LevelData.H:488-561).  On one NVSwitch node the receiving GPU can instead READ the neighbour's
+// cells where they lie: the arenas of the two ping-pong levels are exported with cudaIpcGetMemHandle,
+// the handles travel once (ncclSend/Recv), and the sweep's TMA producer bulk-copies the neighbour's
+// first / last valid plane over NVLink into its ring slot.  Ordering: after every sweep a rank bumps a
+// counter in its own memory (k_signal, stream-ordered behind the sweep); the neighbour's producer
+// lane spins on that counter (volatile system-scope loads, bounded) before its first remote copy.
+// Each kernel only ever waits for a sweep the neighbour launched earlier without waiting on us, so
+// there is no cycle; the planes a neighbour reads are exactly those whose computation needed the
+// remote plane, so they are never overwritten too early.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_signal(unsigned long long* flag, unsigned long long value) {
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long*>(flag) = value;
+  __threadfence_system();
+}
+
+struct P2PMsg {
+  cudaIpcMemHandle_t lev[2];
+  cudaIpcMemHandle_t flag;
+  unsigned long long counter;
+};
+
+void comm_p2p_release(sgc_plan_s* p) {
+  sgc_plan_s::P2P& S = p->p2p;
+  for (int k = 0; k < 2; ++k) {
+    for (int l = 0; l < 2; ++l)
+      if (S.peer_base[k][l]) { cudaIpcCloseMemHandle(S.peer_base[k][l]); S.peer_base[k][l] = nullptr; }
+    if (S.peer_flag_base[k]) { cudaIpcCloseMemHandle(S.peer_flag_base[k]); S.peer_flag_base[k] = nullptr; }
+  }
+  if (S.d_flag) cudaFree(S.d_flag);
+  if (S.d_err) cudaFree(S.d_err);
+  if (S.d_rz) cudaFree(S.d_rz);
+  S = sgc_plan_s::P2P();
+}
+
+int comm_p2p_signal(sgc_plan_s* p, unsigned long long value, cudaStream_t s) {
+  k_signal<<<1, 1, 0, s>>>(p->p2p.d_flag, value);
+  rt().launches++;
+  SGC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int comm_p2p_check(sgc_plan_s* p) {
+  unsigned int err = 0;
+  SGC_CUDA(cudaMemcpyAsync(&err, p->p2p.d_err, sizeof err, cudaMemcpyDeviceToHost, rt().compute));
+  SGC_CUDA(cudaStreamSynchronize(rt().compute));
+  if (err) return fail(SGC_ERR_COMM, "peer-memory halo: timed out waiting for a neighbouring GPU's sweep");
+  return 0;
+}
+
+// Returns 0 when the call went through (p->p2p.ready tells whether the session is usable on EVERY
+// rank — decided by an all-reduce, so all ranks take the same path); < 0 on hard errors.
+int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {
+  sgc_plan_s::P2P& S = p->p2p;
+  if (S.tried && ((S.lev[0] == a && S.lev[1] == b) || (S.lev[0] == b && S.lev[1] == a))) return 0;
+  Comm& c = cm();
+  if (!c.ready || c.nproc < 2) return 0;
+  comm_p2p_release(p);
+  S.tried = true;
+  S.lev[0] = a;
+  S.lev[1] = b;
+  Runtime& r = rt();
+  // 1. which boxes have a z neighbour on another rank, and is every remote FACE a z face?
+  int ok = 1;
+  std::vector<int> rz((size_t)a->nbox * 2, -1);
+  const int bpp = a->nbox;
+  for (const sgc_motion_item& it : p->items) {
+    if (it.recv_proc == it.send_proc) continue;
+    const int codim = abs(it.dir[0]) + abs(it.dir[1]) + abs(it.dir[2]);
+    if (codim != 1) continue;                       // edges / corners are not needed inside the loop
+    if (it.dir[2] == 0) { ok = 0; break; }          // a remote x or y face: keep the NCCL schedule
+    int slot = -1;
+    for (int k = 0; k < S.npeer; ++k) if (S.peer_rank[k] == it.send_proc) slot = k;
+    if (slot < 0) {
+      if (S.npeer == 2) { ok = 0; break; }
+      slot = S.npeer++;
+      S.peer_rank[slot] = it.send_proc;
+    }
+    const int rbox = it.send_box - it.send_proc * bpp;
+    rz[(size_t)(it.recv_box - a->gidx0) * 2 + (it.dir[2] < 0 ? 0 : 1)] = (slot << 28) | rbox;
+  }
+  // 2. our side of the session
+  P2PMsg mine, theirs[2];
+  memset(&mine, 0, sizeof mine);
+  if (ok) {
+    ok = cudaMalloc(&S.d_flag, 256) == cudaSuccess && cudaMalloc(&S.d_err, 256) == cudaSuccess &&
+         cudaMalloc(&S.d_rz, sizeof(int) * rz.size()) == cudaSuccess;
+    if (ok) {
+      cudaMemset(S.d_flag, 0, 256);
+      cudaMemset(S.d_err, 0, 256);
+      cudaMemcpy(S.d_rz, rz.data(), sizeof(int) * rz.size(), cudaMemcpyHostToDevice);
+      ok = cudaIpcGetMemHandle(&mine.lev[0], a->d_base) == cudaSuccess &&
+           cudaIpcGetMemHandle(&mine.lev[1], b->d_base) == cudaSuccess &&
+           cudaIpcGetMemHandle(&mine.flag, S.d_flag) == cudaSuccess;
+    }
+    cudaGetLastError();
+  }
+  // 3. agree globally before anything rank-to-rank happens
+  int* d_ok = nullptr;
+  SGC_CUDA(cudaMalloc(&d_ok, 256));
+  SGC_CUDA(cudaMemcpy(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice));
+  SGC_NCCL(c.api.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c.comm, r.comm));
+  SGC_CUDA(cudaStreamSynchronize(r.comm));
+  SGC_CUDA(cudaMemcpy(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost));
+  if (ok) {
+    // 4. swap handles with the z neighbours and map their memory
+    P2PMsg* d_msg = nullptr;
+    SGC_CUDA(cudaMalloc(&d_msg, sizeof(P2PMsg) * 3));
+    SGC_CUDA(cudaMemcpy(d_msg, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    SGC_NCCL(c.api.GroupStart());
+    for (int k = 0; k < S.npeer; ++k) {
+      SGC_NCCL(c.api.Send(d_msg, sizeof(P2PMsg), ncclChar, S.peer_rank[k], c.comm, r.comm));
+      SGC_NCCL(c.api.Recv(d_msg + 1 + k, sizeof(P2PMsg), ncclChar, S.peer_rank[k], c.comm, r.comm));
+    }
+    SGC_NCCL(c.api.GroupEnd());
+    SGC_CUDA(cudaStreamSynchronize(r.comm));
+    SGC_CUDA(cudaMemcpy(theirs, d_msg + 1, sizeof(P2PMsg) * 2, cudaMemcpyDeviceToHost));
+    cudaFree(d_msg);
+    for (int k = 0; k < S.npeer && ok; ++k) {
+      for (int l = 0; l < 2 && ok; ++l)
+        ok = cudaIpcOpenMemHandle(&S.peer_base[k][l], theirs[k].lev[l], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      if (ok) ok = cudaIpcOpenMemHandle(&S.peer_flag_base[k], theirs[k].flag, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    }
+    cudaGetLastError();
+    // 5. and agree again (a failed mapping on one rank must switch every rank back to NCCL)
+    SGC_CUDA(cudaMemcpy(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice));
+    SGC_NCCL(c.api.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c.comm, r.comm));
+    SGC_CUDA(cudaStreamSynchronize(r.comm));
+    SGC_CUDA(cudaMemcpy(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_ok);
+  S.ready = ok != 0;
+  S.counter = 0;
   return 0;
 }
 

@@ -28,7 +28,12 @@ int sweep_tile_z();
 int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int box_begin, int box_end,
                        cudaStream_t s);
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
-                        cudaStream_t s, const int* d_push_nbr, int push_mask = 7);
+                        cudaStream_t s, const PushArgs* fuse);
+// peer-memory halo session (sgc_comm.cu)
+int comm_p2p_setup(sgc_plan_s* plan, sgc_level_s* a, sgc_level_s* b);
+void comm_p2p_release(sgc_plan_s* plan);
+int comm_p2p_signal(sgc_plan_s* plan, unsigned long long value, cudaStream_t s);
+int comm_p2p_check(sgc_plan_s* plan);
 bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u);
 int launch_wave_stream(sgc_level_s* unp1, sgc_level_s* un, sgc_level_s* unm1, double f, int fma, cudaStream_t s);
 // multi-rank transport (sgc_comm.cu)
@@ -700,6 +705,7 @@ int sgc_plan_destroy(sgc_plan_t p) {
   if (rt().ready) { cudaStreamSynchronize(rt().compute); cudaStreamSynchronize(rt().comm); }
   p->local.release();
   if (p->d_push) cudaFree(p->d_push);
+  comm_p2p_release(p);
   comm_plan_release(p);
   delete p;
   return 0;
@@ -821,7 +827,7 @@ int sgc_heat_sweep_ranges(sgc_level_t nxt, sgc_level_t cur, double f, unsigned f
   if (a0 < 0 || a0 > a1 || a1 > b0 || b0 > b1 || b1 > nxt->nbox) return fail(SGC_ERR_ARG, "sgc_heat_sweep_ranges: box ranges");
   {
     ProfScope prof(0, rt().compute);
-    st = launch_heat_stream2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, a0, a1, b0, b1, rt().compute, nullptr, 0);
+    st = launch_heat_stream2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, a0, a1, b0, b1, rt().compute, nullptr);
   }
   if (st <= 0) return st;
   st = sgc_heat_sweep_range(nxt, cur, f, flags, a0, a1);
@@ -831,9 +837,14 @@ int sgc_heat_sweep_ranges(sgc_level_t nxt, sgc_level_t cur, double f, unsigned f
 
 // streaming sweep of boxes [a0,a1) + [b0,b1) that also fills the ghosts of nxt's neighbours
 static int fused_sweep(sgc_level_t nxt, sgc_level_t cur, double f, unsigned flags, int a0, int a1, int b0, int b1,
-                       const int* d_push, int mask) {
+                       const int* d_push, int mask, const PushArgs* remote = nullptr) {
   ProfScope prof(0, rt().compute);
-  const int st = launch_heat_stream2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, a0, a1, b0, b1, rt().compute, d_push, mask);
+  PushArgs pa;
+  memset(&pa, 0, sizeof pa);
+  if (remote) pa = *remote;
+  pa.nbr = d_push;
+  pa.mask = mask;
+  const int st = launch_heat_stream2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, a0, a1, b0, b1, rt().compute, &pa);
   return st > 0 ? fail(SGC_ERR_UNSUPPORTED, "fused sweep: no streaming kernel for this geometry") : st;
 }
 
@@ -873,7 +884,33 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
   const int comm_sms = cs ? atoi(cs) : 8;              // SMs left to pack / NCCL / unpack during the interior sweep
   int s0 = 0;
   if (fused) {
+    // Multi-GPU, z-slab partitions: the z ghost planes facing another GPU are pulled by the sweep's
+    // producer straight out of that GPU's memory (cudaIpc-mapped arenas over NVLink), gated by a
+    // progress counter the neighbour bumps after each of its sweeps — no pack / NCCL / unpack and
+    // ONE launch per step.  SGC_P2P=0 keeps the NCCL schedule below.
+    const char* pe = getenv("SGC_P2P");
+    const bool p2p = plan->nremote > 0 && !(pe && pe[0] == '0') && comm_p2p_setup(plan, a, b) == 0 && plan->p2p.ready;
     st = sgc_exchange(cur, plan);
+    if (p2p && !st) {
+      sgc_plan_s::P2P& S = plan->p2p;
+      for (; s0 < nstep - 2 && !st; ++s0) {
+        PushArgs ra;
+        memset(&ra, 0, sizeof ra);
+        const int li = (cur == S.lev[0]) ? 0 : 1;               // which of the session's levels is the input
+        ra.rz = S.d_rz;
+        for (int k = 0; k < S.npeer; ++k) {
+          ra.peer_in[k] = (const double*)((char*)S.peer_base[k][li] + cur->lead * cur->esz);
+          ra.peer_flag[k] = (const unsigned long long*)S.peer_flag_base[k];
+        }
+        ra.wait_value = S.counter;                              // peers have finished their previous sweep
+        ra.err = S.d_err;
+        st = fused_sweep(nxt, cur, f, flags, 0, cur->nbox, cur->nbox, cur->nbox, plan->d_push, fmask, &ra);
+        if (!st) st = comm_p2p_signal(plan, ++S.counter, rt().compute);
+        std::swap(cur, nxt);
+      }
+      if (!st) st = comm_p2p_check(plan);
+      if (st) return st;
+    }
     for (; s0 < nstep - 2 && !st; ++s0) {
       if (plan->nremote > 0) {
         if (split) st = fused_sweep(nxt, cur, f, flags, 0, b0, b1, cur->nbox, plan->d_push, fmask);

@@ -124,6 +124,23 @@ Runtime& rt();
                                        "(this library has no CPU fallback)");               \
   } while (0)
 
+// Arguments of the fused ghost fill of the streaming sweep (sgc_stream.cu).
+struct PushArgs {
+  const int* nbr;        // [nbox][27] local box in direction code 13 + dx + 3 dy + 9 dz that has a local
+                         // motion item with this box, or -1 (domain boundary, trimmed, or remote owner)
+  double* out_level;     // arena base of the output level            (filled in by the launcher)
+  const double* in_level;   // arena base of the input level          (filled in by the launcher)
+  long long xg_base;     // element offset of the xg regions          (filled in by the launcher)
+  int box0;              // local index of the first box of the launch (filled in by the launcher)
+  int mask;              // bit 0 = push x faces, bit 1 = pull z planes, bit 2 = pull y rows
+  // z halo straight out of the neighbouring GPU's memory (NVLink peer access, z-slab partitions):
+  const int* rz;                             // [nbox][2] (-z, +z): (peer slot << 28) | box index on the peer, or -1
+  const double* peer_in[2];                  // the peers' input-level arenas (cudaIpc-mapped)
+  const unsigned long long* peer_flag[2];    // the peers' progress counters (cudaIpc-mapped)
+  unsigned long long wait_value;             // counter value that makes the peers' input level readable
+  unsigned int* err;                         // set to 1 when a wait timed out
+};
+
 // launchers implemented in sgc_kernels.cu
 int launch_copy(const CopyTable& t, void* dst_arena, const void* src_arena, int esz, cudaStream_t s);
 int launch_fill(void* p, long long n, int esz, const void* value, cudaStream_t s);
@@ -182,6 +199,20 @@ struct sgc_plan_s {
   // box per (box, direction code), -1 where there is no local motion item
   int* d_push = nullptr;
   bool fusable = false;
+  // peer-memory halo session (sgc_comm.cu): the two ping-pong levels of a step loop, their arenas on
+  // the z neighbours mapped through cudaIpc, and progress counters
+  struct P2P {
+    bool tried = false, ready = false;
+    sgc_level_s* lev[2] = {nullptr, nullptr};
+    int npeer = 0;
+    int peer_rank[2] = {-1, -1};
+    void* peer_base[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [peer slot][level] opened allocations
+    void* peer_flag_base[2] = {nullptr, nullptr};
+    unsigned long long* d_flag = nullptr;    // this rank's counter (cudaMalloc, exported)
+    unsigned int* d_err = nullptr;
+    int* d_rz = nullptr;                     // [nbox][2]
+    unsigned long long counter = 0;          // value last signalled
+  } p2p;
 };
 
 struct sgc_event_s {

@@ -109,15 +109,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // another GPU) the fab's own ghost cells are used, exactly as without PUSH; they are kept current by
 // the BC / NCCL unpack.  Edge and corner ghosts are not needed by the 7-point stencil and are left
 // alone; sgc_heat_run restores the reference's ghost contents by running its last two steps unfused.
-struct PushArgs {
-  const int* nbr;        // [nbox][27] local box in direction code 13 + dx + 3 dy + 9 dz that has a local
-                         // motion item with this box, or -1 (domain boundary, trimmed, or remote owner)
-  double* out_level;     // arena base of the output level
-  const double* in_level;   // arena base of the input level
-  long long xg_base;     // element offset of the xg regions (same geometry for both levels)
-  int box0;              // local index of the first box of this launch
-  int mask;              // bit 0 = push x faces, bit 1 = pull z planes, bit 2 = pull y rows
-};
 
 // OP: 0 = heat / Jacobi (unew = u + f*S), 1 = leap-frog wave (unp1 = 2 un - unm1 + f*Tx + f*Ty + f*Tz,
 // WavePatch.cpp:226-244).  For the wave every ring slot also carries the valid rows of unm1 for the
@@ -172,6 +163,8 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
       long long tr = l_begin + (l_begin >= seam ? jump : 0);   // real stage index
       const long long xfab = (long long)2 * STRIP * n2;        // xg block elements per fab
       int pb = -1, dym = -1, dyp = -1, dzm = -1, dzp = -1;     // cached pull sources of box pb
+      int rzm = -1, rzp = -1;                                  // remote z neighbours of box pb (peer memory)
+      bool waited[2] = {false, false};
       for (int t = l_begin; t < l_end; ++t, ++tr) {
         if (t == seam && t != l_begin) tr += jump;
         if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
@@ -204,6 +197,8 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
               const bool py = (push.mask & 4) != 0, pz = (push.mask & 2) != 0;
               dym = py ? __ldg(nb + 13 - 3) : -1; dyp = py ? __ldg(nb + 13 + 3) : -1;
               dzm = pz ? __ldg(nb + 13 - 9) : -1; dzp = pz ? __ldg(nb + 13 + 9) : -1;
+              rzm = (pz && push.rz) ? __ldg(push.rz + 2 * b) : -1;
+              rzp = (pz && push.rz) ? __ldg(push.rz + 2 * b + 1) : -1;
             }
             const long long fabm = (long long)PLANE * n2;
             const int vnz_ = n2 - 2 * NG;
@@ -212,10 +207,30 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
               const int kz = kz0 + p;
               double* d = dst + p * PLANE;
               const double* own = push.in_level + b * fabm + (long long)kz * PLANE;
-              if (kz < NG) {                                   // low ghost plane <- -z neighbour's last valid planes
-                bulk_g2s(d, dzm >= 0 ? push.in_level + dzm * fabm + (long long)(kz + vnz_) * PLANE : own, PLANE * 8u, full + slot);
-              } else if (kz >= n2 - NG) {                      // high ghost plane <- +z neighbour's first valid planes
-                bulk_g2s(d, dzp >= 0 ? push.in_level + dzp * fabm + (long long)(kz - vnz_) * PLANE : own, PLANE * 8u, full + slot);
+              if (kz < NG || kz >= n2 - NG) {
+                // ghost plane <- the z neighbour's last (low side) / first (high side) valid planes:
+                // a local fab, a fab in the neighbouring GPU's memory, or (no neighbour) the own ghosts
+                const bool low = kz < NG;
+                const int dl = low ? dzm : dzp, rr = low ? rzm : rzp;
+                const long long skz = low ? kz + vnz_ : kz - vnz_;
+                const double* src = own;
+                if (dl >= 0) src = push.in_level + dl * fabm + skz * PLANE;
+                else if (rr >= 0) {
+                  const int ps = rr >> 28;
+                  if (!waited[ps]) {       // the peer must have finished writing the level we read
+                    const volatile unsigned long long* fl = push.peer_flag[ps];
+                    long long spins = 0;
+                    while (*fl < push.wait_value) {
+                      if (++spins > (1LL << 20)) { *push.err = 1u; break; }    // ~3 s: report, never hang
+                      __nanosleep(64);
+                    }
+                    __threadfence_system();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    waited[ps] = true;
+                  }
+                  src = push.peer_in[ps] + (long long)(rr & 0x0fffffff) * fabm + skz * PLANE;
+                }
+                bulk_g2s(d, src, PLANE * 8u, full + slot);
               } else if (dym < 0 && dyp < 0) {
                 bulk_g2s(d, own, PLANE * 8u, full + slot);
               } else {
@@ -347,7 +362,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
 
 template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0>
 static int launch_cfg(const double* in_main, const double* in_xg, double* out_main, int nstages, int n2, double f,
-                      int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs{nullptr, nullptr, nullptr, 0, 0, 0},
+                      int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs(),
                       const double* aux_main = nullptr) {
   constexpr size_t smem = (size_t)NS * PS * ((size_t)VNX * (VNY + 2 * NG) + 2 * NG * (VNY + 2 * NG) +
                                              (OP == 1 ? (size_t)VNX * VNY : 0)) * 8 + 2 * NS * 8;
@@ -370,7 +385,7 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
 // Sweeps boxes [a0,a1) and [b0,b1) (a1 <= b0; the second range may be empty) in ONE launch.
 // Returns 1 when the geometry is not covered (caller falls back to the table-driven kernel).
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
-                        cudaStream_t s, const int* d_push_nbr, int push_mask) {
+                        cudaStream_t s, const PushArgs* fuse) {
   if (!u->uniform || !unew->uniform || u->ncomp != 1 || unew->ncomp != 1 || u->ng != unew->ng || u->ng != 1) return 1;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0) return 1;
@@ -385,11 +400,17 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
   if (planes <= 0) return 0;
   if (planes + gap > 0x7fffffffLL) return 1;
   if (getenv("SGC_NO_STREAM")) return 1;
-  const char* pm = getenv("SGC_PUSH_MASK");
-  const PushArgs pa{d_push_nbr, (double*)unew->d_arena, (const double*)u->d_arena, unew->xg_base, a0, pm ? atoi(pm) : push_mask};
+  PushArgs pa;
+  memset(&pa, 0, sizeof pa);
+  if (fuse) pa = *fuse;
+  pa.out_level = (double*)unew->d_arena;
+  pa.in_level = (const double*)u->d_arena;
+  pa.xg_base = unew->xg_base;
+  pa.box0 = a0;
+  if (const char* pm = getenv("SGC_PUSH_MASK")) pa.mask = atoi(pm);      // diagnostics
 #define SGC_STREAM_CASE(VX, VY, PS_, NS_, NCW_)                                                      \
   if (vnx == VX && vny == VY && n2 % PS_ == 0) {                                                     \
-    if (d_push_nbr)                                                                                  \
+    if (fuse)                                                                                        \
       return launch_cfg<VX, VY, 1, PS_, NS_, NCW_, 0, true>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
                                                             (int)(planesA / PS_), (int)(gap / PS_), s, pa); \
     return launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
@@ -427,7 +448,8 @@ int launch_wave_stream(sgc_level_s* unp1, sgc_level_s* un, sgc_level_s* unm1, do
   const double* in_xg = in_main + un->xg_base;
   double* out = (double*)unp1->d_arena;
   const double* aux = (const double*)unm1->d_arena;
-  const PushArgs none{nullptr, nullptr, nullptr, 0, 0, 0};
+  PushArgs none;
+  memset(&none, 0, sizeof none);
 #define SGC_WAVE_CASE(VX, VY, PS_, NS_, NCW_)                                                                   \
   if (vnx == VX && vny == VY && n2 % PS_ == 0)                                                                  \
     return launch_cfg<VX, VY, 1, PS_, NS_, NCW_, 0, false, 1>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
@@ -451,7 +473,7 @@ bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u) {
 
 int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int box_begin, int box_end,
                        cudaStream_t s) {
-  return launch_heat_stream2(unew, u, f, fma, box_begin, box_end, box_end, box_end, s, nullptr, 0);
+  return launch_heat_stream2(unew, u, f, fma, box_begin, box_end, box_end, box_end, s, nullptr);
 }
 
 }  // namespace sgc
