@@ -55,7 +55,11 @@ enum { SGC_PERIODIC_X = 1, SGC_PERIODIC_Y = 2, SGC_PERIODIC_Z = 4 };
  * reference's g++ build emits (-ffp-contract=fast); without it the product and the
  * sum round separately (= -ffp-contract=off).  Either way the association order is the
  * reference loop's: ((u[+e]-2u)+u[-e]) per direction, x then y then z.                    */
-enum { SGC_FMA = 1 };
+enum { SGC_FMA = 1,
+       /* sgc_wave_step only: evaluate the update in the form of the shipped wave app's pencil path,
+        * unp1 = (2 un - unm1) + factor*(Tz + (Ty + Tx))  (MD_DIRSUM, WavePatch.cpp:194-206), instead
+        * of the scalar form with three separate accumulations (WavePatch.cpp:226-244).           */
+       SGC_WAVE_DIRSUM = 2 };
 
 typedef struct sgc_level_s* sgc_level_t;   /* device-resident LevelData<BaseFab<T>>      */
 typedef struct sgc_plan_s*  sgc_plan_t;    /* device-resident Copier (exchange plan)      */

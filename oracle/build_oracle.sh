@@ -41,7 +41,13 @@ $CXX $COMMON $REL                   -shared -o "$OUT/libsgcref.so"       $LIBSRC
 $CXX $COMMON $REL -ffp-contract=off -shared -o "$OUT/libsgcref_nofma.so" $LIBSRC "$HERE/ref_shim.cpp"
 $CXX $COMMON $REL -fopenmp          -shared -o "$OUT/libsgcref_omp.so"   $LIBSRC "$HERE/ref_shim.cpp"
 $CXX $COMMON -O1 -g                 -shared -o "$OUT/libsgcref_dbg.so"   $LIBSRC "$HERE/ref_shim.cpp"
-echo "[oracle] built _ref/libsgcref{,_nofma,_omp,_dbg}.so from $REF_DIR"
+# the shipped wave time stepper (WavePatch, USE_VEX pencil path); cgnslib.h is included
+# unconditionally by WavePatch.cpp:15 -> an empty stub on the include path
+mkdir -p "$OUT/stub"
+: > "$OUT/stub/cgnslib.h"
+W="$REF_DIR/application/wave"
+$CXX $COMMON $REL -I"$OUT/stub" -I"$W" -shared -o "$OUT/libsgcref_wave.so" $LIBSRC "$W/WavePatch.cpp" "$HERE/ref_wave_shim.cpp"
+echo "[oracle] built _ref/libsgcref{,_nofma,_omp,_dbg,_wave}.so from $REF_DIR"
 
 # the reference's own serial tests, asserts live (no -DRELEASE)
 T="$REF_DIR/lib/test/BoxFramework"

@@ -141,6 +141,22 @@ def main():
         meta["wave"].append(dict(key=name, dlo=dlo, dhi=dhi, factor=factor, nstep=8,
                                  contract=0 if variant == "_nofma" else 1))
 
+    # the SHIPPED wave time stepper (WavePatch::advance, USE_VEX pencil path) — valid cells are the contract
+    if po.have_reference("_wave"):
+        W = po.ReferenceWave()
+        meta["wavepatch"] = []
+        for name, h, nstep, init in (("wp16_hash", 16, 8, "hash"), ("wp13_hash", 13, 5, "hash"), ("wp16_pulse", 16, 10, "pulse")):
+            if init == "hash":
+                boxes = np.array([[0, 0, 0, h - 1, h - 1, h - 1]], np.int32)
+                u_init = O.fill_hash(boxes, 1, 0.0)
+                um1_init = u_init + rng.integers(0, 8, u_init.size) / 64.0
+            else:
+                u_init, um1_init, _ = W.run(h, 0.125, 0)          # WavePatch::initialData (sin^6 pulse)
+            un, unm1, factor = W.run(h, 0.125, nstep, u_init, um1_init)
+            arrays[name + "_u_init"], arrays[name + "_um1_init"] = u_init, um1_init
+            arrays[name + "_un"], arrays[name + "_unm1"] = un, unm1
+            meta["wavepatch"].append(dict(key=name, h=h, nstep=nstep, cfl=0.125, factor=factor, init=init))
+
     with open(os.path.join(OUT, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1)
     np.savez_compressed(os.path.join(OUT, "golden.npz"), **arrays)

@@ -54,6 +54,7 @@ class Oracle:
         L.sgco_level_wave_sweep.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp, _dp, C.c_double, C.c_int]
         L.sgco_laplacian.argtypes = [C.c_int, C.c_int, _dp, _dp]
         L.sgco_wave.argtypes = [_i3, _i3, C.c_double, C.c_int, C.c_int, _dp, _dp]
+        L.sgco_wave_dirsum.argtypes = [_i3, _i3, C.c_double, C.c_int, C.c_int, _dp, _dp]
         L.sgco_bc_zero_gradient.argtypes = [_i3, _i3, C.c_int, _dp]
         L.sgco_level_fill_hash.argtypes = [_ip, C.c_int, C.c_int, C.c_double, _dp]
         L.sgco_level_gather.argtypes = [_i3, _i3, _ip, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]
@@ -130,6 +131,10 @@ class Oracle:
 
     def wave(self, dlo, dhi, factor, nstep, u0, u1, contract=1):
         self.lib.sgco_wave(i3(dlo), i3(dhi), factor, nstep, contract, u0, u1)
+
+    def wave_dirsum(self, dlo, dhi, factor, nstep, u0, u1, contract=1):
+        """the shipped wave app's pencil form (MD_DIRSUM), WavePatch.cpp:194-206"""
+        self.lib.sgco_wave_dirsum(i3(dlo), i3(dhi), factor, nstep, contract, u0, u1)
 
     def bc_zero_gradient(self, dlo, dhi, ng, u):
         self.lib.sgco_bc_zero_gradient(i3(dlo), i3(dhi), ng, u)
@@ -232,3 +237,23 @@ class Reference:
         out = np.zeros(6, np.int32)
         self.lib.sgcref_adjbox(i3(lo), i3(hi), ncell, d, side, out)
         return out
+
+
+class ReferenceWave:
+    """The reference's shipped WavePatch time stepper (oracle/_ref/libsgcref_wave.so)."""
+
+    def __init__(self):
+        self.lib = L = C.CDLL(ref_path("_wave"))
+        L.sgcref_wavepatch_run.argtypes = [C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, _dp, _dp,
+                                           C.POINTER(C.c_double)]
+
+    def run(self, h, cfl, nstep, u_init=None, um1_init=None):
+        n = (h + 2) ** 3
+        un, unm1 = np.zeros(n), np.zeros(n)
+        f = C.c_double()
+        if not os.path.isdir("plot"):
+            pass
+        self.lib.sgcref_wavepatch_run(h, cfl, nstep,
+                                      None if u_init is None else u_init.ctypes.data,
+                                      None if um1_init is None else um1_init.ctypes.data, un, unm1, C.byref(f))
+        return un, unm1, f.value

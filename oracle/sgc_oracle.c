@@ -503,6 +503,50 @@ void sgco_wave_box(const int* flo, const int* fhi, const double* un, const doubl
         }
 }
 
+/* Leap-frog update in the form of the shipped wave app's pencil path, WavePatch.cpp:194-206
+ * (USE_VEX is defined at :31): unp1 = 2 un - unm1 + factor*MD_DIRSUM(dir -> un[+e] - 2 un + un[-e]).
+ * MD_DIRSUM (BaseFabMacros.H:287-317) expands to f(3) + (f(2) + (f(1) + f(0))): f(3) has a zero
+ * offset and is exactly 0, so the sum is Tz + (Ty + Tx); the final multiply-add is
+ * one fma when contracted.                                                                    */
+void sgco_wave_box_dirsum(const int* flo, const int* fhi, const double* un, const double* unm1,
+                          double* unp1, const int* blo, const int* bhi, double factor, int contract)
+{
+  const obox fb = mk(flo, fhi);
+  const long st[3] = { 1, fb.hi[0] - fb.lo[0] + 1,
+                       (long)(fb.hi[0] - fb.lo[0] + 1)*(fb.hi[1] - fb.lo[1] + 1) };
+  for (int k = blo[2]; k <= bhi[2]; ++k)
+    for (int j = blo[1]; j <= bhi[1]; ++j)
+      for (int i = blo[0]; i <= bhi[0]; ++i)
+        {
+          const long c = fab_index(&fb, i, j, k, 0);
+          double T[3];
+          for (int d = 0; d < 3; ++d) T[d] = (un[c + st[d]] - 2*un[c]) + un[c - st[d]];
+          const double sum = T[2] + (T[1] + T[0]);
+          const double t1 = 2*un[c] - unm1[c];
+          unp1[c] = contract ? fma(factor, sum, t1) : t1 + factor*sum;
+        }
+}
+
+/* nstep x { BC ; dirsum update ; rotate } on one box = WavePatch::advance as shipped (valid cells). */
+void sgco_wave_dirsum(const int* dlo, const int* dhi, double factor, int nstep, int contract,
+                      double* u0, double* u1)
+{
+  obox fb = mk(dlo, dhi);
+  box_grow(&fb, 1);
+  const size_t bytes = sizeof(double)*(size_t)box_size(&fb);
+  double* buf[3] = { (double*)malloc(bytes), (double*)calloc(1, bytes), (double*)malloc(bytes) };
+  memcpy(buf[0], u0, bytes); memcpy(buf[2], u1, bytes);
+  int in = 0, inp1 = 1, inm1 = 2;
+  for (int s = 0; s < nstep; ++s)
+    {
+      sgco_bc_zero_gradient(dlo, dhi, 1, buf[in]);
+      sgco_wave_box_dirsum(fb.lo, fb.hi, buf[in], buf[inm1], buf[inp1], dlo, dhi, factor, contract);
+      const int t = inm1; inm1 = in; in = inp1; inp1 = t;
+    }
+  memcpy(u0, buf[in], bytes); memcpy(u1, buf[inm1], bytes);
+  free(buf[0]); free(buf[1]); free(buf[2]);
+}
+
 /* the same update over every box of a level (1 comp, ng ghosts, ghosts of un already filled) */
 void sgco_level_wave_sweep(const int* boxes6, int nbox, int ng, const double* un, const double* unm1,
                            double* unp1, double factor, int contract)

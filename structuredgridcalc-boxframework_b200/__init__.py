@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(HERE, "libsgc_b200.so")
 TrimCenter, TrimFace, TrimEdge, TrimCorner = 1, 2, 4, 8
 PeriodicX, PeriodicY, PeriodicZ = 1, 2, 4
 SGC_FMA = 1
+SGC_WAVE_DIRSUM = 2
 
 # every symbol include/sgc_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [

@@ -813,11 +813,11 @@ int sgc_wave_step(sgc_level_t unp1, sgc_level_t un, sgc_level_t unm1, double fac
   if (!unm1 || !same_geometry(un, unm1)) return fail(SGC_ERR_GEOMETRY, "sgc_wave_step: un and unm1 must share geometry");
   if (unm1 == unp1) return fail(SGC_ERR_ARG, "sgc_wave_step: unp1 must not alias unm1");
   ProfScope prof(0, rt().compute);
-  st = launch_wave_stream(unp1, un, unm1, factor, (flags & SGC_FMA) ? 1 : 0, rt().compute);
+  const int wf = (int)(flags & (SGC_FMA | SGC_WAVE_DIRSUM));      // bit 0 fma, bit 1 dirsum form
+  st = launch_wave_stream(unp1, un, unm1, factor, wf, rt().compute);
   if (st <= 0) return st;
   return launch_wave_generic(unp1->d_work, 0, unp1->nwork, un->d_geom, unp1->d_geom, (const double*)un->d_arena,
-                             (double*)unp1->d_arena, (const double*)unm1->d_arena, factor, (flags & SGC_FMA) ? 1 : 0,
-                             rt().compute);
+                             (double*)unp1->d_arena, (const double*)unm1->d_arena, factor, wf, rt().compute);
 }
 
 int sgc_heat_sweep_ranges(sgc_level_t nxt, sgc_level_t cur, double f, unsigned flags, int a0, int a1, int b0, int b1) {

@@ -129,14 +129,16 @@ struct LapOp {                        // niter x { b -= coef*Tx; b -= coef*Ty; b
     return b;
   }
 };
-struct WaveOp {                       // r = 2u - um1; r += f*Tx; r += f*Ty; r += f*Tz
-  double f; int fma;
+struct WaveOp {                       // r = 2u - um1; r += f*Tx; r += f*Ty; r += f*Tz   (or the MD_DIRSUM form)
+  double f; int fma;                  // fma: bit 0 = fused multiply-add, bit 1 = SGC_WAVE_DIRSUM
   __device__ __forceinline__ double operator()(double c, double tx, double ty, double tz, double um1) const {
     double r = __dsub_rn(__dmul_rn(2.0, c), um1);       // 2*c is exact: contraction-invariant
-    if (fma) { r = __fma_rn(f, tx, r); r = __fma_rn(f, ty, r); r = __fma_rn(f, tz, r); }
-    else {
-      r = __dadd_rn(r, __dmul_rn(f, tx)); r = __dadd_rn(r, __dmul_rn(f, ty)); r = __dadd_rn(r, __dmul_rn(f, tz));
+    if (fma & 2) {                                      // shipped pencil form: (2u - um1) + f*(Tz + (Ty + Tx))
+      const double sum = __dadd_rn(tz, __dadd_rn(ty, tx));
+      return (fma & 1) ? __fma_rn(f, sum, r) : __dadd_rn(r, __dmul_rn(f, sum));
     }
+    if (fma & 1) { r = __fma_rn(f, tx, r); r = __fma_rn(f, ty, r); r = __fma_rn(f, tz, r); return r; }
+    r = __dadd_rn(r, __dmul_rn(f, tx)); r = __dadd_rn(r, __dmul_rn(f, ty)); r = __dadd_rn(r, __dmul_rn(f, tz));
     return r;
   }
 };

@@ -329,10 +329,13 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
             const double tz = sd2(zp, twoc, zm[m]);
             if (OP == 0) {
               const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
-              r = fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+              r = (fma & 1) ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
             } else {
               r = __dsub_rn(twoc, pa[m * NT]);
-              if (fma) { r = __fma_rn(f, tx, r); r = __fma_rn(f, ty, r); r = __fma_rn(f, tz, r); }
+              if (fma & 2) {               // SGC_WAVE_DIRSUM: (2u - um1) + f*(Tz + (Ty + Tx))
+                const double sum = __dadd_rn(tz, __dadd_rn(ty, tx));
+                r = (fma & 1) ? __fma_rn(f, sum, r) : __dadd_rn(r, __dmul_rn(f, sum));
+              } else if (fma & 1) { r = __fma_rn(f, tx, r); r = __fma_rn(f, ty, r); r = __fma_rn(f, tz, r); }
               else { r = __dadd_rn(r, __dmul_rn(f, tx)); r = __dadd_rn(r, __dmul_rn(f, ty)); r = __dadd_rn(r, __dmul_rn(f, tz)); }
             }
           }

@@ -70,3 +70,18 @@ def test_levelheat_driver_facade_known_answer(oracle):
             off += m ** 3
         want = "%016x" % oracle.fnv1a64(np.concatenate(chunks))
         assert line["local_fnv1a64"] == want
+
+
+@pytest.mark.gpu
+def test_wave_driver_facade_matches_shipped_wavepatch(oracle, golden):
+    # apps/wave (C++ facade) against the golden vector produced by the reference's real WavePatch:
+    # same initial pulse, 10 leap-frog steps with zero-gradient BC, valid cells bit for bit
+    import numpy as np
+    meta, arr = golden
+    c = [x for x in meta["wavepatch"] if x["key"] == "wp16_pulse"][0]
+    r = _run("wave", str(c["h"]), str(c["nstep"]))
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    m = c["h"] + 2
+    want = arr["wp16_pulse_un"].reshape(m, m, m)[1:-1, 1:-1, 1:-1].copy()
+    assert line["un_valid_fnv1a64"] == "%016x" % oracle.fnv1a64(want)

@@ -398,6 +398,29 @@ def test_wave_and_zero_gradient_bc(g, golden, oracle):
         assert np.array_equal(got[lev.fab_offset(b):lev.fab_offset(b) + lev.fab_elems(b)], f.ravel()), b
 
 
+def test_shipped_wave_app_form(g, golden):
+    # the reference's shipped time stepper (WavePatch::advance, AVX pencil path): BC + update in the
+    # MD_DIRSUM form, valid cells bit-identical to the golden vectors produced by the real WavePatch
+    meta, arr = golden
+    for c in meta["wavepatch"]:
+        h = c["h"]
+        dom = g.Box((0, 0, 0), (h - 1,) * 3)
+        box = [[0, 0, 0, h - 1, h - 1, h - 1]]
+        lv = [g.LevelData(None, 1, 1, boxes=box) for _ in range(3)]
+        lv[0].upload(arr[c["key"] + "_u_init"]); lv[2].upload(arr[c["key"] + "_um1_init"]); lv[1].setVal(0.0)
+        bc = [g.Copier().defineBCZeroGradient(l, dom) for l in lv]
+        n, np1, nm1 = 0, 1, 2
+        for _ in range(c["nstep"]):
+            lv[n].exchange(bc[n])
+            g.wave_step(lv[np1], lv[n], lv[nm1], c["factor"], g.SGC_FMA | g.SGC_WAVE_DIRSUM)
+            n, np1, nm1 = np1, nm1, n
+        m = h + 2
+        for lev, key in ((lv[n], "_un"), (lv[nm1], "_unm1")):
+            got = lev.download().reshape(m, m, m)[1:-1, 1:-1, 1:-1]
+            want = arr[c["key"] + key].reshape(m, m, m)[1:-1, 1:-1, 1:-1]
+            assert np.array_equal(got, want), (c["key"], key)
+
+
 def test_wave_level_streaming_and_generic(g, oracle):
     # leap-frog update on box-decomposed levels (streaming instances 64/32/16 and the generic kernel),
     # both FMA modes, against the oracle's per-box restatement of WavePatch.cpp:226-244

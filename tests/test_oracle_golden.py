@@ -123,3 +123,20 @@ def test_wave_matches_reference_golden(oracle, golden):
         oracle.wave(c["dlo"], c["dhi"], c["factor"], c["nstep"], u0, u1, c["contract"])
         assert np.array_equal(u0, arr[c["key"] + "_u0"]), c["key"]
         assert np.array_equal(u1, arr[c["key"] + "_u1"]), c["key"]
+
+
+def _valid(a, h):
+    m = h + 2
+    return a.reshape(m, m, m)[1:-1, 1:-1, 1:-1]
+
+
+def test_shipped_wavepatch_matches_reference_golden(oracle, golden):
+    # WavePatch::advance as shipped (USE_VEX pencil path, MD_DIRSUM form): valid cells, bit for bit
+    meta, arr = golden
+    assert len(meta["wavepatch"]) >= 3
+    for c in meta["wavepatch"]:
+        h = c["h"]
+        u0, u1 = arr[c["key"] + "_u_init"].copy(), arr[c["key"] + "_um1_init"].copy()
+        oracle.wave_dirsum((0, 0, 0), (h - 1,) * 3, c["factor"], c["nstep"], u0, u1, 1)
+        assert np.array_equal(_valid(u0, h), _valid(arr[c["key"] + "_un"], h)), c["key"]
+        assert np.array_equal(_valid(u1, h), _valid(arr[c["key"] + "_unm1"], h)), c["key"]
