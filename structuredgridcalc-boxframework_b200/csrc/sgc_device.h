@@ -69,6 +69,7 @@ struct CopyTable {
   int nitem = 0;
   int nchunk = 0;
   long long ncell = 0;
+  bool strided_reads = false;          // a good share of the cells are single elements of long rows (x faces)
   void release();
   int upload(const std::vector<CopyItem>& items);
 };

@@ -45,5 +45,6 @@ def reference():
 @pytest.fixture(scope="session")
 def sgc():
     """The product: ctypes binding over the C ABI (fails loudly when the CUDA library is missing)."""
-    from _loadpkg import load_package
+    from _loadpkg import load_build, load_package
+    load_build().build()          # no-op when libsgc_b200.so is newer than its sources (nvcc cross-compiles without a GPU)
     return load_package()
