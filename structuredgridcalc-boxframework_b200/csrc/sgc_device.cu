@@ -879,12 +879,10 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
   // first, their halo packed and sent on the comm stream while the interior boxes sweep; the last
   // two steps run unfused, which leaves BOTH levels bit-identical, ghost cells included, to
   // nstep x { exchange ; sweep } (the fused steps do not maintain edge / corner / y / z ghosts).
-  // Only boxes at least 32 cells wide run fused.  Measured on 16^3 boxes (32 768 of them): every
-  // 8th cell of a row lies on an x face, so the single-lane x pushes double the sweep time, and the
-  // pulled y rows are 128-byte copies that make the producer issue-bound: 120-137 Gcell/s fused
-  // against 149 unfused.
-  const bool fused = plan->fusable && nstep >= 3 && heat_stream_covers(b, a) && a->geom[0].vn[0] >= 32 &&
-                     !getenv("SGC_NO_FUSE");
+  // Boxes at least 32 cells wide: x faces pushed by the consumers, y/z pulled by the producer.
+  // Narrower boxes: everything pulled — z planes by the producer, x strips and y rows by the gather
+  // warp (sgc_stream.cu) — because on 16^3 boxes every 8th cell lies on an x face.
+  const bool fused = plan->fusable && nstep >= 3 && heat_stream_covers(b, a) && !getenv("SGC_NO_FUSE");
   const int fmask = 7;                                 // bit 0 push x, bit 1 pull z, bit 2 pull y
   const char* cs = getenv("SGC_COMM_SMS");
   const int comm_sms = cs ? atoi(cs) : 8;              // SMs left to pack / NCCL / unpack during the interior sweep

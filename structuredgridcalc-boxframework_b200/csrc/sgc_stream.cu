@@ -37,6 +37,8 @@
 
 namespace sgc {
 
+constexpr int kGatherWarps = 4;   // helper warps of the narrow-box fused mode (GATHER)
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -113,8 +115,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // OP: 0 = heat / Jacobi (unew = u + f*S), 1 = leap-frog wave (unp1 = 2 un - unm1 + f*Tx + f*Ty + f*Tz,
 // WavePatch.cpp:226-244).  For the wave every ring slot also carries the valid rows of unm1 for the
 // planes that are emitted when the slot arrives (one more bulk copy per plane; read back with LDS).
-template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0>
-__global__ void __launch_bounds__((NCW + 1) * 32, 1)
+//
+// GATHER (narrow boxes, VNX < 32): pushing x faces costs a partial-warp store on every 8th cell and
+// pulled y rows would be 64-128 byte bulk copies, so a second helper warp GATHERS both instead: for
+// every stage its 32 lanes load the x-halo values (last / first valid column of the x neighbours)
+// and the y-ghost rows straight from the neighbouring fabs with ordinary loads and store them into
+// the ring slot, then arrive on the slot's `full` barrier next to the TMA transaction count.  With
+// 16^3 boxes a CTA walks the boxes of an x row back to back, so those lines are in L2 (they were, or
+// are about to be, streamed by the same CTA) and cost no extra DRAM traffic.
+template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0,
+          bool GATHER = false>
+__global__ void __launch_bounds__((NCW + 1 + (GATHER ? kGatherWarps : 0)) * 32, 1)
 k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_xg, double* __restrict__ out_main,
               int nstages, int n2, double f, int fma, int seam, int jump, PushArgs push,
               const double* __restrict__ aux_main) {
@@ -151,7 +162,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
 
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, NCW); }
+    for (int i = 0; i < NS; ++i) { mbar_init(full + i, GATHER ? 2 : 1); mbar_init(empty + i, NCW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -176,6 +187,33 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
           const int kz0 = (int)(pl - box * n2);
           double* dst = ring + (size_t)slot * STAGE;
           const double* xg = in_xg + box * xfab + (long long)kz0 * STRIP;
+          if (GATHER) {
+            // planes only: a ghost plane whole (from its z source), an interior plane's valid rows;
+            // the gather warp fills the y-ghost rows and the x strips
+            const int b = push.box0 + (int)box;
+            if (b != pb) {
+              pb = b;
+              const int* __restrict__ nb = push.nbr + (size_t)b * 27;
+              dzm = __ldg(nb + 13 - 9); dzp = __ldg(nb + 13 + 9);
+            }
+            const long long fabm = (long long)PLANE * n2;
+            const int vnz_ = n2 - 2 * NG;
+            uint32_t bytes = 0;
+#pragma unroll
+            for (int p = 0; p < PS; ++p) bytes += (kz0 + p < NG || kz0 + p >= n2 - NG) ? PLANE * 8u : VNY * VNX * 8u;
+            mbar_expect_tx(full + slot, bytes);
+#pragma unroll
+            for (int p = 0; p < PS; ++p) {
+              const int kz = kz0 + p;
+              double* d = dst + p * PLANE;
+              const double* own = push.in_level + b * fabm + (long long)kz * PLANE;
+              if (kz < NG) bulk_g2s(d, dzm >= 0 ? push.in_level + dzm * fabm + (long long)(kz + vnz_) * PLANE : own, PLANE * 8u, full + slot);
+              else if (kz >= n2 - NG) bulk_g2s(d, dzp >= 0 ? push.in_level + dzp * fabm + (long long)(kz - vnz_) * PLANE : own, PLANE * 8u, full + slot);
+              else bulk_g2s(d + NG * VNX, own + NG * VNX, VNY * VNX * 8u, full + slot);
+            }
+            if (++slot == NS) { slot = 0; ++round; }
+            continue;
+          }
           mbar_expect_tx(full + slot, MAIN_BYTES + 2 * STRIP_BYTES + AUX_BYTES);
           if (OP == 1) {
             // unm1 valid rows of planes pl-1 .. pl+PS-2 (the planes emitted while this stage is read);
@@ -253,6 +291,69 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
     return;
   }
 
+  if (GATHER && warp > NCW) {
+    // ---------------- gather warps: x strips and y-ghost rows from the neighbouring fabs ----------------
+    // kGatherWarps warps take the stages round-robin; each issues all loads of its stage in one batch
+    // (they are L2 round trips) before it stores them, so a stage costs one latency, spread over 4 warps.
+    const int gw = warp - NCW - 1;
+    const long long fabm = (long long)PLANE * n2, xfab = (long long)2 * STRIP * n2;
+    int pb = -1, dxm = -1, dxp = -1, dym = -1, dyp = -1;
+    constexpr int NXH = 2 * PS * VNY;              // x-halo values of a stage: (side, plane, valid row)
+    constexpr int NYH = 2 * PS * VNX;              // y-ghost values of a stage: (side, plane, x)
+    constexpr int IX = (NXH + 31) / 32, IY = (NYH + 31) / 32;
+    for (int t = l_begin + gw; t < l_end; t += kGatherWarps) {
+      const int rel = t - l_begin, slot = rel % NS, round = rel / NS;
+      const long long tr = t + (t >= seam ? jump : 0);
+      if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
+      const long long pl = tr * PS;
+      const long long box = pl / n2;
+      const int kz0 = (int)(pl - box * n2);
+      const int b = push.box0 + (int)box;
+      if (b != pb) {
+        pb = b;
+        const int* __restrict__ nb = push.nbr + (size_t)b * 27;
+        dxm = __ldg(nb + 12); dxp = __ldg(nb + 14); dym = __ldg(nb + 10); dyp = __ldg(nb + 16);
+      }
+      double* dst = ring + (size_t)slot * STAGE;
+      const double* ownmain = push.in_level + b * fabm;
+      const double* ownxg = push.in_level + push.xg_base + b * xfab;
+      double vx[IX], vy[IY];
+      int ox[IX], oy[IY];                          // destination offsets in the slot, -1 = nothing to do
+#pragma unroll
+      for (int it = 0; it < IX; ++it) {
+        const int idx = lane + 32 * it;
+        const int side = idx / (PS * VNY), rem = idx % (PS * VNY), p = rem / VNY, r = rem % VNY + NG;
+        const int kz = kz0 + p;
+        const bool live = idx < NXH && kz >= NG && kz < n2 - NG;   // edge ghosts are not needed by the stencil
+        const int D = side ? dxp : dxm;
+        const double* src = D >= 0 ? push.in_level + D * fabm + ((long long)kz * N1 + r) * VNX + (side ? 0 : VNX - 1)
+                                   : ownxg + ((long long)side * n2 + kz) * N1 + r;
+        ox[it] = live ? PS * PLANE + side * PS * STRIP + p * STRIP + r : -1;
+        vx[it] = live ? *src : 0.0;
+      }
+#pragma unroll
+      for (int it = 0; it < IY; ++it) {
+        const int idx = lane + 32 * it;
+        const int side = idx / (PS * VNX), rem = idx % (PS * VNX), p = rem / VNX, x = rem % VNX;
+        const int kz = kz0 + p;
+        const bool live = idx < NYH && kz >= NG && kz < n2 - NG;   // ghost planes are copied whole by the producer
+        const int D = side ? dyp : dym;
+        const int grow = side ? VNY + NG : 0;      // ghost row being filled (NG == 1)
+        const double* src = D >= 0 ? push.in_level + D * fabm + ((long long)kz * N1 + (side ? NG : VNY)) * VNX + x
+                                   : ownmain + ((long long)kz * N1 + grow) * VNX + x;
+        oy[it] = live ? p * PLANE + grow * VNX + x : -1;
+        vy[it] = live ? *src : 0.0;
+      }
+#pragma unroll
+      for (int it = 0; it < IX; ++it) if (ox[it] >= 0) dst[ox[it]] = vx[it];
+#pragma unroll
+      for (int it = 0; it < IY; ++it) if (oy[it] >= 0) dst[oy[it]] = vy[it];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + slot);
+    }
+    return;
+  }
+
   // ---------------- consumers ----------------
   // Thread tid owns the CPT columns (xi, j0 + m*ROWS), m = 0..CPT-1: the same x for all of them, so
   // every shared-memory / global offset of column m is the offset of column 0 plus a compile-time
@@ -306,7 +407,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
         const double* __restrict__ pxp = at_hi ? prev_hi + sr0 : pc + 1;
         const int xmstep = at_lo ? ROWS : NT, xpstep = at_hi ? ROWS : NT;   // strips advance by rows, planes by NT
         double* __restrict__ xrow = nullptr;
-        if (PUSH) {
+        if (PUSH && !GATHER) {
           if (bprev != pbox) {           // new fab: look up the x neighbour this thread pushes into
             pbox = bprev;
             const int Dx = (fx && (push.mask & 1)) ? __ldg(push.nbr + (size_t)pbox * 27 + 13 + fx) : -1;
@@ -340,7 +441,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
             }
           }
           if (MODE != 2 || zp == 1.2345e300) po[m * NT] = r;
-          if (PUSH) { if (xrow) xrow[m * ROWS] = r; }
+          if (PUSH && !GATHER) { if (xrow) xrow[m * ROWS] = r; }
           zm[m] = c;
           cc[m] = zp;
         }
@@ -363,7 +464,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   }
 }
 
-template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0>
+template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0, bool GATHER = false>
 static int launch_cfg(const double* in_main, const double* in_xg, double* out_main, int nstages, int n2, double f,
                       int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs(),
                       const double* aux_main = nullptr) {
@@ -371,7 +472,7 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
                                              (OP == 1 ? (size_t)VNX * VNY : 0)) * 8 + 2 * NS * 8;
   static_assert(smem <= 232448, "ring exceeds the 227 KB of shared memory a CTA can have");
   static bool configured = false;
-  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE, PUSH, OP>;
+  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE, PUSH, OP, GATHER>;
   if (!configured) {
     SGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
@@ -379,7 +480,7 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
   int grid = rt().sm_count;
   if (rt().sweep_grid_cap > 0 && rt().sweep_grid_cap < grid) grid = rt().sweep_grid_cap;
   if (grid > nstages) grid = nstages;
-  kern<<<grid, (NCW + 1) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma, seam, jump, push, aux_main);
+  kern<<<grid, (NCW + 1 + (GATHER ? kGatherWarps : 0)) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma, seam, jump, push, aux_main);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
@@ -414,8 +515,9 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
 #define SGC_STREAM_CASE(VX, VY, PS_, NS_, NCW_)                                                      \
   if (vnx == VX && vny == VY && n2 % PS_ == 0) {                                                     \
     if (fuse)                                                                                        \
-      return launch_cfg<VX, VY, 1, PS_, NS_, NCW_, 0, true>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
-                                                            (int)(planesA / PS_), (int)(gap / PS_), s, pa); \
+      return launch_cfg<VX, VY, 1, PS_, NS_, NCW_, 0, true, 0, (VX < 32)>(in_main, in_xg, out, (int)(planes / PS_), n2, \
+                                                                          f, fma, (int)(planesA / PS_),   \
+                                                                          (int)(gap / PS_), s, pa);       \
     return launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
                                                  (int)(planesA / PS_), (int)(gap / PS_), s);         \
   }
