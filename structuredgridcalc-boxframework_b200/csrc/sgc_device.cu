@@ -150,7 +150,8 @@ void make_items(std::vector<CopyItem>& out, const FabGeom& gd, const IBox& dreg,
   for (int c : cand)
     if (c > 0 && c < nx) cuts[ncut++] = c;
   cuts[ncut++] = nx;
-  std::sort(cuts, cuts + ncut);
+  for (int i = 1; i < ncut; ++i)                 // insertion sort of <= 6 cut positions
+    for (int j = i; j > 0 && cuts[j] < cuts[j - 1]; --j) std::swap(cuts[j], cuts[j - 1]);
   for (int p = 0; p + 1 < ncut; ++p) {
     const int x0 = cuts[p], x1 = cuts[p + 1];
     if (x1 <= x0) continue;

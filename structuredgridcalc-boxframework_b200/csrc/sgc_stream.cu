@@ -176,6 +176,32 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
       int pb = -1, dym = -1, dyp = -1, dzm = -1, dzp = -1;     // cached pull sources of box pb
       int rzm = -1, rzp = -1;                                  // remote z neighbours of box pb (peer memory)
       bool waited[2] = {false, false};
+      // where ghost plane kz of box b comes from: the z neighbour's last (low side) / first (high side)
+      // valid plane — a local fab, a fab in the neighbouring GPU's memory, or (no neighbour) the own ghosts
+      auto zsource = [&](int b, int kz) -> const double* {
+        const long long fabm = (long long)PLANE * n2;
+        const int vnz_ = n2 - 2 * NG;
+        const bool low = kz < NG;
+        const int dl = low ? dzm : dzp, rr = low ? rzm : rzp;
+        const long long skz = low ? kz + vnz_ : kz - vnz_;
+        if (dl >= 0) return push.in_level + dl * fabm + skz * PLANE;
+        if (rr >= 0) {
+          const int ps = rr >> 28;
+          if (!waited[ps]) {           // the peer must have finished writing the level we read
+            const volatile unsigned long long* fl = push.peer_flag[ps];
+            long long spins = 0;
+            while (*fl < push.wait_value) {
+              if (++spins > (1LL << 20)) { *push.err = 1u; break; }    // ~3 s: report, never hang
+              __nanosleep(64);
+            }
+            __threadfence_system();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            waited[ps] = true;
+          }
+          return push.peer_in[ps] + (long long)(rr & 0x0fffffff) * fabm + skz * PLANE;
+        }
+        return push.in_level + b * fabm + (long long)kz * PLANE;
+      };
       for (int t = l_begin; t < l_end; ++t, ++tr) {
         if (t == seam && t != l_begin) tr += jump;
         if (round > 0) mbar_wait(empty + slot, (round - 1) & 1u);
@@ -195,9 +221,10 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
               pb = b;
               const int* __restrict__ nb = push.nbr + (size_t)b * 27;
               dzm = __ldg(nb + 13 - 9); dzp = __ldg(nb + 13 + 9);
+              rzm = push.rz ? __ldg(push.rz + 2 * b) : -1;
+              rzp = push.rz ? __ldg(push.rz + 2 * b + 1) : -1;
             }
             const long long fabm = (long long)PLANE * n2;
-            const int vnz_ = n2 - 2 * NG;
             uint32_t bytes = 0;
 #pragma unroll
             for (int p = 0; p < PS; ++p) bytes += (kz0 + p < NG || kz0 + p >= n2 - NG) ? PLANE * 8u : VNY * VNX * 8u;
@@ -207,8 +234,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
               const int kz = kz0 + p;
               double* d = dst + p * PLANE;
               const double* own = push.in_level + b * fabm + (long long)kz * PLANE;
-              if (kz < NG) bulk_g2s(d, dzm >= 0 ? push.in_level + dzm * fabm + (long long)(kz + vnz_) * PLANE : own, PLANE * 8u, full + slot);
-              else if (kz >= n2 - NG) bulk_g2s(d, dzp >= 0 ? push.in_level + dzp * fabm + (long long)(kz - vnz_) * PLANE : own, PLANE * 8u, full + slot);
+              if (kz < NG || kz >= n2 - NG) bulk_g2s(d, zsource(b, kz), PLANE * 8u, full + slot);
               else bulk_g2s(d + NG * VNX, own + NG * VNX, VNY * VNX * 8u, full + slot);
             }
             if (++slot == NS) { slot = 0; ++round; }
@@ -239,36 +265,13 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
               rzp = (pz && push.rz) ? __ldg(push.rz + 2 * b + 1) : -1;
             }
             const long long fabm = (long long)PLANE * n2;
-            const int vnz_ = n2 - 2 * NG;
 #pragma unroll
             for (int p = 0; p < PS; ++p) {
               const int kz = kz0 + p;
               double* d = dst + p * PLANE;
               const double* own = push.in_level + b * fabm + (long long)kz * PLANE;
               if (kz < NG || kz >= n2 - NG) {
-                // ghost plane <- the z neighbour's last (low side) / first (high side) valid planes:
-                // a local fab, a fab in the neighbouring GPU's memory, or (no neighbour) the own ghosts
-                const bool low = kz < NG;
-                const int dl = low ? dzm : dzp, rr = low ? rzm : rzp;
-                const long long skz = low ? kz + vnz_ : kz - vnz_;
-                const double* src = own;
-                if (dl >= 0) src = push.in_level + dl * fabm + skz * PLANE;
-                else if (rr >= 0) {
-                  const int ps = rr >> 28;
-                  if (!waited[ps]) {       // the peer must have finished writing the level we read
-                    const volatile unsigned long long* fl = push.peer_flag[ps];
-                    long long spins = 0;
-                    while (*fl < push.wait_value) {
-                      if (++spins > (1LL << 20)) { *push.err = 1u; break; }    // ~3 s: report, never hang
-                      __nanosleep(64);
-                    }
-                    __threadfence_system();
-                    asm volatile("fence.proxy.async;" ::: "memory");
-                    waited[ps] = true;
-                  }
-                  src = push.peer_in[ps] + (long long)(rr & 0x0fffffff) * fabm + skz * PLANE;
-                }
-                bulk_g2s(d, src, PLANE * 8u, full + slot);
+                bulk_g2s(d, zsource(b, kz), PLANE * 8u, full + slot);
               } else if (dym < 0 && dyp < 0) {
                 bulk_g2s(d, own, PLANE * 8u, full + slot);
               } else {
