@@ -65,12 +65,12 @@ int main(int argc, char* argv[])
   SGC_SAFE_CALL(sgc_event_create(&e1));
   timer.start();
   SGC_SAFE_CALL(sgc_event_record(e0));
-  for (int it = 0; it != numIter; ++it)
-    {
-      bc[n].apply(u[n]);
-      StencilOps::waveStep(u[np1], u[n], u[nm1], factor, SGC_FMA | SGC_WAVE_DIRSUM);
-      const int t = nm1; nm1 = n; n = np1; np1 = t;
-    }
+  {
+    // the whole iteration group stays on the device (one BC plan serves the three equal-geometry levels)
+    int idx[3] = { n, np1, nm1 };
+    StencilOps::waveRun(u, idx, bc[0], factor, numIter, SGC_FMA | SGC_WAVE_DIRSUM);
+    n = idx[0]; np1 = idx[1]; nm1 = idx[2];
+  }
   SGC_SAFE_CALL(sgc_event_record(e1));
   SGC_SAFE_CALL(sgc_sync());
   timer.stop();

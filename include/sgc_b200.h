@@ -232,6 +232,15 @@ int sgc_laplacian_apply(sgc_level_t B, sgc_level_t A, double coef, int niter, in
  *   unp1 = 2*un - unm1; for dir: unp1 += factor*((un[+e]-2un)+un[-e])                         */
 int sgc_wave_step(sgc_level_t unp1, sgc_level_t un, sgc_level_t unm1, double factor, unsigned flags);
 
+/* nstep x { fill ghosts ; wave step ; rotate } on three device-resident levels — the body of
+ * WavePatch::advance repeated without leaving the device, i.e. driverAdvanceIterGroup
+ * (WavePatch_Cuda.cu:352-378: kernelBC; kernelRHS; swap indices).  levels[0] = un, [1] = the level
+ * to write (unp1), [2] = unm1 on entry; each step applies `exchange_plan` (interior / periodic
+ * ghosts; may be NULL) and `bc_plan` (physical-boundary ghosts; may be NULL) to un, then
+ * sgc_wave_step.  On return latest[0..2] = indices into levels[] of un, unp1-scratch, unm1.     */
+int sgc_wave_run(sgc_level_t levels[3], sgc_plan_t exchange_plan, sgc_plan_t bc_plan, double factor,
+                 unsigned flags, int nstep, int latest[3]);
+
 /* nstep x { exchange(plan) ; heat sweep } with ping-pong between a and b, device resident
  * (the shape of driverAdvanceIterGroup, WavePatch_Cuda.cu:352-378).  *result_in_b = 1 when the
  * last-written level is b.  With nproc > 1 each step overlaps the halo with interior boxes.   */

@@ -30,7 +30,7 @@ SYMBOLS = [
     "sgc_plan_create_exchange", "sgc_plan_create_items", "sgc_plan_destroy", "sgc_plan_num_items",
     "sgc_plan_num_remote_items", "sgc_plan_num_cells", "sgc_exchange", "sgc_exchange_begin", "sgc_exchange_end",
     "sgc_plan_create_bc_zero_gradient", "sgc_heat_sweep", "sgc_heat_sweep_range", "sgc_heat_sweep_ranges", "sgc_laplacian_apply",
-    "sgc_wave_step", "sgc_heat_run", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
+    "sgc_wave_step", "sgc_wave_run", "sgc_heat_run", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
     "sgc_comm_rank", "sgc_halo_describe",
 ]
 
@@ -113,6 +113,8 @@ def lib():
     L.sgc_heat_sweep_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
     L.sgc_laplacian_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_uint]
     L.sgc_wave_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint]
+    L.sgc_wave_run.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_double, C.c_uint, C.c_int,
+                               C.POINTER(C.c_int)]
     L.sgc_heat_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint, C.c_int, C.POINTER(C.c_int)]
     L.sgc_profile_read.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.sgc_event_create.argtypes = [C.POINTER(C.c_void_p)]
@@ -442,6 +444,14 @@ def laplacian_apply(B, A, coef=0.5, niter=16, fuse_iters=0, flags=SGC_FMA):
 
 def wave_step(unp1, un, unm1, factor, flags=SGC_FMA):
     check(lib().sgc_wave_step(unp1.h, un.h, unm1.h, factor, flags))
+
+
+def wave_run(levels, copier, bc, factor, nstep, flags=SGC_FMA):
+    """nstep x {exchange; BC; wave step; rotate}; returns (un, scratch, unm1) levels after the run."""
+    hs = (C.c_void_p * 3)(*[l.h for l in levels])
+    latest = (C.c_int * 3)()
+    check(lib().sgc_wave_run(hs, copier.h if copier else None, bc.h if bc else None, factor, flags, nstep, latest))
+    return tuple(levels[i] for i in latest)
 
 
 def heat_run(a, b, copier, f, nstep, flags=SGC_FMA):

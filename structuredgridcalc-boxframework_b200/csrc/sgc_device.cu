@@ -842,6 +842,23 @@ int sgc_heat_sweep_ranges(sgc_level_t nxt, sgc_level_t cur, double f, unsigned f
   return st;
 }
 
+int sgc_wave_run(sgc_level_t levels[3], sgc_plan_t exchange_plan, sgc_plan_t bc_plan, double factor, unsigned flags,
+                 int nstep, int latest[3]) {
+  SGC_REQUIRE_RT();
+  if (!levels || !levels[0] || !levels[1] || !levels[2] || nstep < 0) return fail(SGC_ERR_ARG, "sgc_wave_run: bad argument");
+  int n = 0, np1 = 1, nm1 = 2;
+  for (int s = 0; s < nstep; ++s) {
+    int st = 0;
+    if (exchange_plan) st = sgc_exchange(levels[n], exchange_plan);
+    if (!st && bc_plan) st = sgc_exchange(levels[n], bc_plan);
+    if (!st) st = sgc_wave_step(levels[np1], levels[n], levels[nm1], factor, flags);
+    if (st) return st;
+    const int t = nm1; nm1 = n; n = np1; np1 = t;      // unp1 -> un, un -> unm1 (WavePatch::advanceStepIndex)
+  }
+  if (latest) { latest[0] = n; latest[1] = np1; latest[2] = nm1; }
+  return 0;
+}
+
 // streaming sweep of boxes [a0,a1) + [b0,b1) that also fills the ghosts of nxt's neighbours
 static int fused_sweep(sgc_level_t nxt, sgc_level_t cur, double f, unsigned flags, int a0, int a1, int b0, int b1,
                        const int* d_push, int mask, const PushArgs* remote = nullptr) {

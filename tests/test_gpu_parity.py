@@ -421,6 +421,23 @@ def test_shipped_wave_app_form(g, golden):
             assert np.array_equal(got, want), (c["key"], key)
 
 
+def test_wave_run_device_resident_loop(g, golden):
+    # sgc_wave_run = nstep x {BC; update; rotate} on the device, against the real WavePatch golden vectors
+    meta, arr = golden
+    for c in meta["wavepatch"]:
+        h = c["h"]
+        dom = g.Box((0, 0, 0), (h - 1,) * 3)
+        box = [[0, 0, 0, h - 1, h - 1, h - 1]]
+        lv = [g.LevelData(None, 1, 1, boxes=box) for _ in range(3)]
+        lv[0].upload(arr[c["key"] + "_u_init"]); lv[2].upload(arr[c["key"] + "_um1_init"]); lv[1].setVal(0.0)
+        bc = g.Copier().defineBCZeroGradient(lv[0], dom)     # same geometry: one BC plan serves all three levels
+        un, _, unm1 = g.wave_run(lv, None, bc, c["factor"], c["nstep"], g.SGC_FMA | g.SGC_WAVE_DIRSUM)
+        m = h + 2
+        for lev, key in ((un, "_un"), (unm1, "_unm1")):
+            got = lev.download().reshape(m, m, m)[1:-1, 1:-1, 1:-1]
+            assert np.array_equal(got, arr[c["key"] + key].reshape(m, m, m)[1:-1, 1:-1, 1:-1]), (c["key"], key)
+
+
 def test_wave_level_streaming_and_generic(g, oracle):
     # leap-frog update on box-decomposed levels (streaming instances 64/32/16 and the generic kernel),
     # both FMA modes, against the oracle's per-box restatement of WavePatch.cpp:226-244
