@@ -117,10 +117,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // planes that are emitted when the slot arrives (one more bulk copy per plane; read back with LDS).
 //
 // GATHER (narrow boxes, VNX < 32): pushing x faces costs a partial-warp store on every 8th cell and
-// pulled y rows would be 64-128 byte bulk copies, so a second helper warp GATHERS both instead: for
-// every stage its 32 lanes load the x-halo values (last / first valid column of the x neighbours)
-// and the y-ghost rows straight from the neighbouring fabs with ordinary loads and store them into
-// the ring slot, then arrive on the slot's `full` barrier next to the TMA transaction count.  With
+// pulled y rows would be 64-128 byte bulk copies, so kGatherWarps extra helper warps GATHER both
+// instead: taking the stages round-robin, the 32 lanes of a gather warp load the x-halo values (last
+// / first valid column of the x neighbours) and the y-ghost rows straight from the neighbouring fabs
+// with ordinary loads (one batch per stage), store them into the ring slot, and arrive on the slot's
+// `full` barrier next to the TMA transaction count.  With
 // 16^3 boxes a CTA walks the boxes of an x row back to back, so those lines are in L2 (they were, or
 // are about to be, streamed by the same CTA) and cost no extra DRAM traffic.
 template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0,
