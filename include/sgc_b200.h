@@ -64,6 +64,7 @@ enum { SGC_FMA = 1,
 typedef struct sgc_level_s* sgc_level_t;   /* device-resident LevelData<BaseFab<T>>      */
 typedef struct sgc_plan_s*  sgc_plan_t;    /* device-resident Copier (exchange plan)      */
 typedef struct sgc_event_s* sgc_event_t;   /* cudaEvent on the compute stream             */
+typedef struct sgc_stream_s* sgc_stream_t; /* a transfer stream (cudaStream_t + its staging area) */
 
 /* One Motion2Way (Copier.H:37-160) as a POD. */
 typedef struct {
@@ -149,6 +150,23 @@ void* sgc_level_device_ptr(sgc_level_t level, int box);
  * order); otherwise one fab.  Upload is asynchronous when `host` is pinned; download blocks.  */
 int sgc_level_upload(sgc_level_t level, int box, const void* host);
 int sgc_level_download(sgc_level_t level, int box, void* host);
+
+/* LevelData::copyToDeviceAsync / copyToHostAsync(cudaStream_t) (LevelData.H:734-765,
+ * BaseFab.H:175-181) and the overlap of plot-data D2H with compute in wave.cpp:230-275.
+ * A transfer stream owns its own reference-order staging area, so whole-level transfers on it
+ * run beside the compute stream (kernels of all other entry points) and beside each other:
+ * batch i+1 uploads and batch i-1 downloads while batch i sweeps.  Both calls return after
+ * enqueueing; `host` must be pinned (sgc_host_alloc) and stay valid until the stream passed it.
+ * Ordering between streams is explicit, through events: sgc_event_record_stream marks a point
+ * of a stream, sgc_stream_wait_event makes work submitted LATER to `stream` start after that
+ * point.  A NULL stream argument names the library's compute stream.                         */
+int sgc_stream_create(sgc_stream_t* stream);
+int sgc_stream_destroy(sgc_stream_t stream);
+int sgc_stream_sync(sgc_stream_t stream);
+int sgc_event_record_stream(sgc_event_t ev, sgc_stream_t stream);
+int sgc_stream_wait_event(sgc_stream_t stream, sgc_event_t ev);
+int sgc_level_upload_async(sgc_level_t level, const void* host, sgc_stream_t stream);
+int sgc_level_download_async(sgc_level_t level, void* host, sgc_stream_t stream);
 /* LevelData::setVal / BaseFab::setVal (LevelData.H:352-383, BaseFab.cpp:219-246);
  * comp = -1: all components.  `value` points at one element of elem_bytes bytes.           */
 int sgc_level_setval(sgc_level_t level, int box, int comp, const void* value);

@@ -31,7 +31,8 @@ SYMBOLS = [
     "sgc_plan_num_remote_items", "sgc_plan_num_cells", "sgc_exchange", "sgc_exchange_begin", "sgc_exchange_end",
     "sgc_plan_create_bc_zero_gradient", "sgc_heat_sweep", "sgc_heat_sweep_range", "sgc_heat_sweep_ranges", "sgc_laplacian_apply",
     "sgc_wave_step", "sgc_wave_run", "sgc_heat_run", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
-    "sgc_comm_rank", "sgc_halo_describe",
+    "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
+    "sgc_level_upload_async", "sgc_level_download_async",
 ]
 
 
@@ -123,6 +124,13 @@ def lib():
     L.sgc_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     L.sgc_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.sgc_host_free.argtypes = [C.c_void_p]
+    L.sgc_stream_create.argtypes = [C.POINTER(C.c_void_p)]
+    L.sgc_stream_destroy.argtypes = [C.c_void_p]
+    L.sgc_event_record_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.sgc_stream_wait_event.argtypes = [C.c_void_p, C.c_void_p]
+    L.sgc_stream_sync.argtypes = [C.c_void_p]
+    L.sgc_level_upload_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sgc_level_download_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sgc_comm_unique_id.argtypes = [C.c_char_p]
     L.sgc_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
     _lib = L
@@ -170,8 +178,12 @@ class Event:
         self.h = C.c_void_p()
         check(lib().sgc_event_create(C.byref(self.h)))
 
-    def record(self):
-        check(lib().sgc_event_record(self.h))
+    def record(self, stream=None):
+        """mark the current end of `stream` (a Stream; None = the compute stream)"""
+        if stream is None:
+            check(lib().sgc_event_record(self.h))
+        else:
+            check(lib().sgc_event_record_stream(self.h, stream.h))
         return self
 
     def elapsed_ms(self, stop):
@@ -183,6 +195,34 @@ class Event:
         if getattr(self, "h", None) and _lib is not None:
             _lib.sgc_event_destroy(self.h)
             self.h = None
+
+
+class Stream:
+    """A transfer stream (LevelData::copyToDeviceAsync / copyToHostAsync take a cudaStream_t,
+    LevelData.H:734-765).  `COMPUTE` (None) names the library's compute stream in wait()."""
+    COMPUTE = None
+
+    def __init__(self):
+        self.h = C.c_void_p()
+        check(lib().sgc_stream_create(C.byref(self.h)))
+
+    def wait(self, event):
+        """work submitted to this stream from now on starts after `event`"""
+        check(lib().sgc_stream_wait_event(self.h, event.h))
+        return self
+
+    def sync(self):
+        check(lib().sgc_stream_sync(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.sgc_stream_destroy(self.h)
+            self.h = None
+
+
+def compute_wait(event):
+    """work submitted to the compute stream from now on starts after `event`"""
+    check(lib().sgc_stream_wait_event(None, event.h))
 
 
 class PinnedBuffer:
@@ -336,6 +376,17 @@ class LevelData:
             out = np.empty(n, self.dtype)
         check(lib().sgc_level_download(self.h, box, out.ctypes.data))
         return out
+
+    def uploadAsync(self, pinned, stream):
+        """whole-level H2D on a transfer stream; `pinned` is a PinnedBuffer that must outlive the copy"""
+        assert pinned.array.size == self.elems and pinned.array.dtype == self.dtype
+        check(lib().sgc_level_upload_async(self.h, pinned.ptr, stream.h))
+        return self
+
+    def downloadAsync(self, pinned, stream):
+        assert pinned.array.size == self.elems and pinned.array.dtype == self.dtype
+        check(lib().sgc_level_download_async(self.h, pinned.ptr, stream.h))
+        return self
 
     def setVal(self, value, comp=-1, box=-1):
         v = np.array([value], self.dtype)

@@ -220,6 +220,7 @@ int sgc_init(int device) {
   SGC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   SGC_CUDA(cudaStreamCreateWithPriority(&r.compute, cudaStreamNonBlocking, prio_lo));
   SGC_CUDA(cudaStreamCreateWithPriority(&r.comm, cudaStreamNonBlocking, prio_hi));
+  r.prio_hi = prio_hi;
   r.device = device;
   r.launches = 0;
   r.ready = true;
@@ -474,6 +475,79 @@ int sgc_level_download(sgc_level_t l, int box, void* host) {
   if (st) return st;
   SGC_CUDA(cudaMemcpyAsync(host, rt().d_stage, (size_t)n * l->esz, cudaMemcpyDeviceToHost, rt().compute));
   SGC_CUDA(cudaStreamSynchronize(rt().compute));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Transfer streams (LevelData::copyToDeviceAsync / copyToHostAsync, LevelData.H:734-765)
+// ---------------------------------------------------------------------------------------------
+int sgc_stream_create(sgc_stream_t* stream) {
+  SGC_REQUIRE_RT();
+  if (!stream) return fail(SGC_ERR_ARG, "null stream");
+  sgc_stream_s* x = new sgc_stream_s;
+  // like the comm stream: its conversion kernels should slip in between persistent sweeps
+  cudaError_t e = cudaStreamCreateWithPriority(&x->s, cudaStreamNonBlocking, rt().prio_hi);
+  if (e != cudaSuccess) { sgc_stream_destroy(x); return fail(SGC_ERR_CUDA, cudaGetErrorString(e)); }
+  *stream = x;
+  return 0;
+}
+
+int sgc_stream_destroy(sgc_stream_t x) {
+  if (!x) return 0;
+  if (x->s) { cudaStreamSynchronize(x->s); cudaStreamDestroy(x->s); }
+  if (x->d_stage) cudaFree(x->d_stage);
+  delete x;
+  return 0;
+}
+
+int sgc_event_record_stream(sgc_event_t ev, sgc_stream_t x) {
+  SGC_REQUIRE_RT();
+  if (!ev) return fail(SGC_ERR_ARG, "null event");
+  SGC_CUDA(cudaEventRecord(ev->ev, x ? x->s : rt().compute));
+  return 0;
+}
+
+int sgc_stream_wait_event(sgc_stream_t x, sgc_event_t ev) {
+  SGC_REQUIRE_RT();
+  if (!ev) return fail(SGC_ERR_ARG, "null event");
+  SGC_CUDA(cudaStreamWaitEvent(x ? x->s : rt().compute, ev->ev, 0));
+  return 0;
+}
+
+int sgc_stream_sync(sgc_stream_t x) {
+  SGC_REQUIRE_RT();
+  SGC_CUDA(cudaStreamSynchronize(x ? x->s : rt().compute));
+  return 0;
+}
+
+static int stream_stage(sgc_stream_s* x, size_t bytes) {
+  if (x->stage_bytes >= bytes) return 0;
+  SGC_CUDA(cudaStreamSynchronize(x->s));
+  if (x->d_stage) cudaFree(x->d_stage);
+  x->d_stage = nullptr; x->stage_bytes = 0;
+  SGC_CUDA(cudaMalloc(&x->d_stage, bytes));
+  x->stage_bytes = bytes;
+  return 0;
+}
+
+int sgc_level_upload_async(sgc_level_t l, const void* host, sgc_stream_t x) {
+  SGC_REQUIRE_RT();
+  if (!l || !host || !x) return fail(SGC_ERR_ARG, "sgc_level_upload_async: bad argument");
+  const size_t bytes = (size_t)l->elems * l->esz;
+  int st = stream_stage(x, bytes);
+  if (st) return st;
+  SGC_CUDA(cudaMemcpyAsync(x->d_stage, host, bytes, cudaMemcpyHostToDevice, x->s));
+  return launch_copy(l->conv_in, l->d_arena, x->d_stage, l->esz, x->s);
+}
+
+int sgc_level_download_async(sgc_level_t l, void* host, sgc_stream_t x) {
+  SGC_REQUIRE_RT();
+  if (!l || !host || !x) return fail(SGC_ERR_ARG, "sgc_level_download_async: bad argument");
+  const size_t bytes = (size_t)l->elems * l->esz;
+  int st = stream_stage(x, bytes);
+  if (!st) st = launch_copy(l->conv_out, x->d_stage, l->d_arena, l->esz, x->s);
+  if (st) return st;
+  SGC_CUDA(cudaMemcpyAsync(host, x->d_stage, bytes, cudaMemcpyDeviceToHost, x->s));
   return 0;
 }
 

@@ -106,6 +106,7 @@ struct Runtime {
   int sm_count = 0;
   cudaStream_t compute = nullptr;
   cudaStream_t comm = nullptr;
+  int prio_hi = 0;
   long long launches = 0;
   int sweep_grid_cap = 0;               // > 0: persistent sweeps use at most this many CTAs (leaves SMs to NCCL)
 };
@@ -218,4 +219,10 @@ struct sgc_plan_s {
 
 struct sgc_event_s {
   cudaEvent_t ev = nullptr;
+};
+
+struct sgc_stream_s {
+  cudaStream_t s = nullptr;
+  void* d_stage = nullptr;      // reference-order staging area of this stream's transfers
+  size_t stage_bytes = 0;
 };

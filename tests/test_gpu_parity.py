@@ -57,6 +57,55 @@ def test_upload_download_roundtrip_and_setval(g, oracle):
     assert (got[0] == 7.0).all() and (got[1] == -1.25).all()
 
 
+def test_async_transfer_streams_pipeline(g, oracle):
+    """LevelData::copyToDeviceAsync / copyToHostAsync (LevelData.H:734-765): batches streamed through
+    two transfer streams and the compute stream, ordered by events, give the same bits as the blocking
+    calls — whatever the interleaving."""
+    dlo, dhi, mb = (0, 0, 0), (31, 31, 31), (16, 16, 16)
+    dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
+    nset, nbatch, nstep = 2, 5, 6
+    sets = []
+    for _ in range(nset):
+        la, lb = g.LevelData(dbl, 1, 1), g.LevelData(dbl, 1, 1)
+        sets.append((la, lb, g.Copier().defineExchangeLD(la, 7, 0)))
+    n = sets[0][0].elems
+    rng = np.random.default_rng(5)
+    ins = [g.PinnedBuffer(n) for _ in range(nbatch)]
+    outs = [g.PinnedBuffer(n) for _ in range(nbatch)]
+    for b in ins:
+        b.array[:] = rng.integers(0, 1024, n) / 1024.0
+    up, down = g.Stream(), g.Stream()
+    ev_up = [g.Event() for _ in range(nset)]
+    ev_run = [g.Event() for _ in range(nset)]
+    ev_down = [g.Event() for _ in range(nset)]
+
+    def submit_upload(j):
+        k = j % nset
+        if j >= nset:
+            up.wait(ev_down[k])
+        sets[k][0].uploadAsync(ins[j], up)
+        ev_up[k].record(up)
+
+    submit_upload(0)
+    for j in range(nbatch):
+        k = j % nset
+        la, lb, cp = sets[k]
+        if j + 1 < nbatch:
+            submit_upload(j + 1)
+        g.compute_wait(ev_up[k])
+        lb.copyFrom(la)
+        res = g.heat_run(la, lb, cp, 0.125, nstep)
+        ev_run[k].record()
+        down.wait(ev_run[k])
+        res.downloadAsync(outs[j], down)
+        ev_down[k].record(down)
+    down.sync()
+    for j in range(nbatch):
+        want = ins[j].array.copy()
+        oracle.level_heat(dlo, dhi, mb, 1, 7, 0, 0.125, nstep, want, contract=0)
+        assert np.array_equal(outs[j].array, want), "batch %d" % j
+
+
 def test_level_copy(g):
     rng = np.random.default_rng(12)
     dbl, a = make_level(g, (0, 0, 0), (15, 7, 7), (4, 4, 4), 2, 1)
