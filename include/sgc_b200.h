@@ -65,6 +65,17 @@ typedef struct sgc_level_s* sgc_level_t;   /* device-resident LevelData<BaseFab<
 typedef struct sgc_plan_s*  sgc_plan_t;    /* device-resident Copier (exchange plan)      */
 typedef struct sgc_event_s* sgc_event_t;   /* cudaEvent on the compute stream             */
 typedef struct sgc_stream_s* sgc_stream_t; /* a transfer stream (cudaStream_t + its staging area) */
+typedef struct sgc_copyset_s* sgc_copyset_t; /* a recorded list of BaseFab::copy calls, replayed in one launch */
+
+/* One BaseFab::copy(dstBox, dstComp, src, srcBox, srcComp, numComp, flags) call (BaseFab.cpp:296-329)
+ * between fab dst_box of one level and fab src_box of another (or the same) level; boxes are LOCAL
+ * indices, the source region is [src_lo, src_lo + (dst_hi - dst_lo)].                         */
+typedef struct {
+  int dst_box, dst_lo[3], dst_hi[3], dst_comp;
+  int src_box, src_lo[3], src_comp;
+  int ncomp;
+  unsigned comp_flags;
+} sgc_copy_op;
 
 /* One Motion2Way (Copier.H:37-160) as a POD. */
 typedef struct {
@@ -223,6 +234,21 @@ int sgc_exchange_end(sgc_level_t level, sgc_plan_t plan);
 int sgc_plan_create_bc_zero_gradient(sgc_level_t level, const int dlo[3], const int dhi[3],
                                      sgc_plan_t* plan);
 
+/* ------------------------------------------------------------------ batched fab copies --- */
+
+/* The application-side copy loops of the reference — LBPatch::stream (LBPatch.H:49-64: one shifted
+ * BaseFab::copy per box and component, dst level != src level) and the bounce-back ghost fill of
+ * LBLevel::advance (LBLevel.cpp:65-112: shifted copies with component remap inside one fab) — are
+ * lists of BaseFab::copy calls.  A copy set records such a list once (geometry of `dst_like` /
+ * `src_like`) and sgc_copyset_run replays it in ONE launch on any two levels of those geometries.
+ * The calls must be independent (no op reads a cell another op writes), which makes the batched
+ * result identical to the reference's sequential loop.                                        */
+int sgc_copyset_create(sgc_level_t dst_like, sgc_level_t src_like, const sgc_copy_op* ops, int nop,
+                       sgc_copyset_t* set);
+int sgc_copyset_run(sgc_copyset_t set, sgc_level_t dst, sgc_level_t src);
+int sgc_copyset_destroy(sgc_copyset_t set);
+long long sgc_copyset_num_cells(sgc_copyset_t set);
+
 /* ------------------------------------------------------------------ stencil apply -------- */
 
 /* Heat / Jacobi 7-point sweep over every box of the level, one batched launch over the device
@@ -264,6 +290,30 @@ int sgc_wave_run(sgc_level_t levels[3], sgc_plan_t exchange_plan, sgc_plan_t bc_
  * last-written level is b.  With nproc > 1 each step overlaps the halo with interior boxes.   */
 int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags,
                  int nstep, int* result_in_b);
+
+/* ------------------------------------------------------------------ lattice Boltzmann ---- */
+
+/* The per-cell loops of the reference's multi-box application (application/latticeBoltzmann):
+ * a 19-component D3Q19 distribution level `fi` and a 4-component macroscopic level `macro`
+ * (density, velocity) on the same boxes, nghost = 1.  Arithmetic = the source expressions without
+ * contraction: bit-identical to the reference built with -ffp-contract=off, within rounding of
+ * its default build.
+ * sgc_lb_collide     : LBPatch::collision / LBPhysics::collision (LBPatch.H:27-46, LBPhysics.H:5-14)
+ * sgc_lb_macroscopic : LBPatch::macroscopic / LBPhysics::macroscopic (LBPatch.H:9-23, LBPhysics.H:17-35)
+ * sgc_lb_copy_ops    : the copy lists of which = 0 LBPatch::stream (LBPatch.H:49-64) and
+ *                      which = 1 the bounce-back ghost fill (LBLevel.cpp:65-112) for sgc_copyset_create;
+ *                      returns the number of ops (ops == NULL: count only).
+ * sgc_lb_run         : nstep x LBLevel::advance (LBLevel.cpp:7-127) device-resident: collision,
+ *                      sgc_exchange(exchange) [the caller's PeriodicX|PeriodicY, TrimCorner plan],
+ *                      bounce, stream into `prev` + swap, macroscopic.  fuse != 0 replaces
+ *                      stream + macroscopic + the NEXT step's collision by one kernel (same bits,
+ *                      ghost cells included; `stream` may then be NULL).  *result_in_prev tells
+ *                      which level is the reference's m_curr afterwards.                      */
+int sgc_lb_collide(sgc_level_t fi, sgc_level_t macro);
+int sgc_lb_macroscopic(sgc_level_t macro, sgc_level_t fi);
+int sgc_lb_copy_ops(sgc_level_t fi, const int dlo[3], const int dhi[3], int which, sgc_copy_op* ops, int cap);
+int sgc_lb_run(sgc_level_t fi, sgc_level_t prev, sgc_level_t macro, sgc_plan_t exchange, sgc_copyset_t bounce,
+               sgc_copyset_t stream, int nstep, int fuse, int* result_in_prev);
 
 /* ------------------------------------------------------------------ multi-GPU ------------ */
 

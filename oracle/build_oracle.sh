@@ -47,7 +47,14 @@ mkdir -p "$OUT/stub"
 : > "$OUT/stub/cgnslib.h"
 W="$REF_DIR/application/wave"
 $CXX $COMMON $REL -I"$OUT/stub" -I"$W" -shared -o "$OUT/libsgcref_wave.so" $LIBSRC "$W/WavePatch.cpp" "$HERE/ref_wave_shim.cpp"
-echo "[oracle] built _ref/libsgcref{,_nofma,_omp,_dbg,_wave}.so from $REF_DIR"
+# the shipped lattice-Boltzmann application (the only multi-box one) + the library's CGNS plot
+# writers, against the recording CGNS stand-in oracle/cgns_record/cgnslib.h (no -DNO_CGNS here)
+LB="$REF_DIR/application/latticeBoltzmann"
+LBFL="-std=c++14 -Wno-vla -Wno-unknown-pragmas -w -I$S -fPIC -I$HERE/cgns_record -I$LB"
+$CXX $LBFL $REL                   -shared -o "$OUT/libsgcref_lb.so"       $LIBSRC "$LB/LBLevel.cpp" "$HERE/ref_lb_shim.cpp"
+$CXX $LBFL $REL -ffp-contract=off -shared -o "$OUT/libsgcref_lb_nofma.so" $LIBSRC "$LB/LBLevel.cpp" "$HERE/ref_lb_shim.cpp"
+$CXX $LBFL $REL -fopenmp          -shared -o "$OUT/libsgcref_lb_omp.so"   $LIBSRC "$LB/LBLevel.cpp" "$HERE/ref_lb_shim.cpp"
+echo "[oracle] built _ref/libsgcref{,_nofma,_omp,_dbg,_wave,_lb,_lb_nofma,_lb_omp}.so from $REF_DIR"
 
 # the reference's own serial tests, asserts live (no -DRELEASE)
 T="$REF_DIR/lib/test/BoxFramework"

@@ -157,6 +157,44 @@ def main():
             arrays[name + "_un"], arrays[name + "_unm1"] = un, unm1
             meta["wavepatch"].append(dict(key=name, h=h, nstep=nstep, cfl=0.125, factor=factor, init=init))
 
+    # the lattice-Boltzmann application (LBLevel::advance), from the reference built with and without
+    # contraction; fi perturbed (ghosts included) so that every term of the collision is exercised
+    if po.have_reference("_lb") and po.have_reference("_lb_nofma"):
+        if not os.path.isdir("plot"):
+            os.makedirs("plot")                      # LBLevel::writePlotFile's path prefix (never written: CGNS stand-in)
+        LB = {"": po.ReferenceLB(""), "_nofma": po.ReferenceLB("_nofma")}
+        meta["lb"], meta["lb_hash"], meta["plot"] = [], [], []
+        for name, dlo, dhi, mb, nstep in (("lb_8x4x8_b4", (0, 0, 0), (7, 3, 7), (4, 4, 4), 5),
+                                          ("lb_off_1layer", (2, -1, 0), (9, 6, 3), (4, 4, 4), 4)):
+            boxes, owner, nb = O.layout(dlo, dhi, mb)
+            fi0, m0 = O.lb_initial(boxes)
+            fi0 = fi0 * (1 + rng.integers(-64, 64, fi0.size) / 4096.0)
+            O.lb_macroscopic(boxes, fi0, m0)
+            arrays[name + "_fi0"], arrays[name + "_macro0"] = fi0, m0
+            for variant in ("", "_nofma"):
+                fi, mac, mass = LB[variant].run(dlo, dhi, mb, nstep, fi0.size, m0.size, fi0, m0)
+                if variant == "_nofma":
+                    arrays[name + "_fi_nofma"] = fi
+                arrays[name + "_macro" + variant] = mac
+            meta["lb"].append(dict(key=name, dlo=dlo, dhi=dhi, maxbox=mb, nstep=nstep))
+        # the shipped configuration (latticeBoltzmann.cpp:16,36): 64x32x32 in 16^3 boxes from initialData
+        dlo, dhi, mb = (0, 0, 0), (63, 31, 31), (16, 16, 16)
+        boxes, owner, nb = O.layout(dlo, dhi, mb)
+        nfi, nm = O.level_size(boxes, 1, 19), O.level_size(boxes, 1, 4)
+        for nstep in (1, 40):
+            rec = dict(key="lb_shipped_%d" % nstep, dlo=dlo, dhi=dhi, maxbox=mb, nstep=nstep)
+            for variant in ("", "_nofma"):
+                fi, mac, mass = LB[variant].run(dlo, dhi, mb, nstep, nfi, nm)
+                rec["fnv_macro" + variant] = "%016x" % O.fnv1a64(O.level_valid_out(boxes, 1, 4, mac))
+                rec["fnv_fi" + variant] = "%016x" % O.fnv1a64(fi)
+                rec["mass" + variant] = mass
+            meta["lb_hash"].append(rec)
+        # what LBLevel::writePlotFile hands to CGNS after 3 steps of a small level
+        dlo, dhi, mb = (0, 0, 0), (7, 3, 7), (4, 4, 4)
+        data, pm, names = LB["_nofma"].plot(dlo, dhi, mb, 3)
+        arrays["plot_data"], arrays["plot_meta"] = data, pm
+        meta["plot"].append(dict(key="plot", dlo=dlo, dhi=dhi, maxbox=mb, nstep=3, names=names))
+
     with open(os.path.join(OUT, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1)
     np.savez_compressed(os.path.join(OUT, "golden.npz"), **arrays)

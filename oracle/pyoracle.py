@@ -58,6 +58,14 @@ class Oracle:
         L.sgco_bc_zero_gradient.argtypes = [_i3, _i3, C.c_int, _dp]
         L.sgco_level_fill_hash.argtypes = [_ip, C.c_int, C.c_int, C.c_double, _dp]
         L.sgco_level_gather.argtypes = [_i3, _i3, _ip, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp]
+        L.sgco_lb_constants.argtypes = [_dp, _ip, _ip, _dp]
+        L.sgco_lb_collision.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp]
+        L.sgco_lb_macroscopic.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp]
+        L.sgco_lb_stream.argtypes = [_ip, C.c_int, C.c_int, _dp, _dp]
+        L.sgco_lb_bounce.argtypes = [_i3, _i3, _ip, C.c_int, C.c_int, _dp]
+        L.sgco_lb_advance.argtypes = [_i3, _i3, _i3, C.c_int, _dp, _dp, _dp]
+        L.sgco_level_valid_out.argtypes = [_ip, C.c_int, C.c_int, C.c_int, _dp, _dp]
+        L.sgco_level_valid_out.restype = C.c_long
         L.sgco_fnv1a64.argtypes = [C.c_void_p, C.c_long]
         L.sgco_fnv1a64.restype = C.c_uint64
         L.sgco_adjbox.argtypes = [_i3, _i3, C.c_int, C.c_int, C.c_int, _ip]
@@ -160,6 +168,49 @@ class Oracle:
         self.lib.sgco_adjbox(i3(lo), i3(hi), ncell, d, side, out)
         return out
 
+    # ---- lattice Boltzmann application (LBPatch.H / LBPhysics.H / LBLevel.cpp restated)
+    def lb_collision(self, boxes, fi, macro):
+        boxes = np.ascontiguousarray(boxes, np.int32)
+        self.lib.sgco_lb_collision(boxes, len(boxes), 1, fi, macro)
+
+    def lb_macroscopic(self, boxes, fi, macro):
+        boxes = np.ascontiguousarray(boxes, np.int32)
+        self.lib.sgco_lb_macroscopic(boxes, len(boxes), 1, fi, macro)
+
+    def lb_stream(self, boxes, fi, prev):
+        boxes = np.ascontiguousarray(boxes, np.int32)
+        self.lib.sgco_lb_stream(boxes, len(boxes), 1, fi, prev)
+
+    def lb_bounce(self, dlo, dhi, boxes, fi):
+        boxes = np.ascontiguousarray(boxes, np.int32)
+        self.lib.sgco_lb_bounce(i3(dlo), i3(dhi), boxes, len(boxes), 1, fi)
+
+    def lb_advance(self, dlo, dhi, maxbox, nstep, fi, prev, macro):
+        n = self.lib.sgco_lb_advance(i3(dlo), i3(dhi), i3(maxbox), nstep, fi, prev, macro)
+        if n < 0:
+            raise ValueError("sgco_lb_advance failed: %d" % n)
+        return n
+
+    def lb_initial(self, boxes):
+        """LBLevel::initialData (LBLevel.H:82-94): f_q = w_q everywhere, macro = (1, 0, 0, 0)."""
+        boxes = np.ascontiguousarray(boxes, np.int32)
+        w = np.zeros(19); e = np.zeros(57, np.int32); opp = np.zeros(19, np.int32); c = np.zeros(3)
+        self.lib.sgco_lb_constants(w, e, opp, c)
+        fi, macro = [], []
+        for b in boxes:
+            S = int(np.prod(b[3:] - b[:3] + 3))
+            fi.append(np.repeat(w, S))
+            macro.append(np.repeat(np.array([1.0, 0, 0, 0]), S))
+        return np.concatenate(fi), np.concatenate(macro)
+
+    def level_valid_out(self, boxes, ng, ncomp, fabs):
+        boxes = np.ascontiguousarray(boxes, np.int32)
+        n = int(sum(np.prod(b[3:] - b[:3] + 1) for b in boxes)) * ncomp
+        out = np.zeros(n)
+        got = self.lib.sgco_level_valid_out(boxes, len(boxes), ng, ncomp, fabs, out)
+        assert got == n
+        return out
+
 
 def ref_path(variant=""):
     return os.path.join(HERE, "_ref", "libsgcref%s.so" % variant)
@@ -257,3 +308,48 @@ class ReferenceWave:
                                       None if u_init is None else u_init.ctypes.data,
                                       None if um1_init is None else um1_init.ctypes.data, un, unm1, C.byref(f))
         return un, unm1, f.value
+
+
+class ReferenceLB:
+    """The reference's lattice-Boltzmann application (oracle/_ref/libsgcref_lb{,_nofma}.so, built from
+    application/latticeBoltzmann + oracle/ref_lb_shim.cpp with the recording CGNS stand-in)."""
+    NVEL, NMACRO = 19, 4
+
+    def __init__(self, variant=""):
+        self.lib = L = C.CDLL(ref_path("_lb" + variant))
+        _i3p = _i3
+        L.sgcref_lb_run.restype = C.c_double
+        L.sgcref_lb_run.argtypes = [_i3p, _i3p, _i3p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sgcref_lb_phase.argtypes = [_i3p, _i3p, _i3p, C.c_int, _dp, _dp, _dp]
+        L.sgcref_lb_plot.argtypes = [_i3p, _i3p, _i3p, C.c_int, C.c_void_p, _P(np.int64, flags="C_CONTIGUOUS"),
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+
+    @staticmethod
+    def _p(a):
+        return None if a is None else a.ctypes.data
+
+    def run(self, dlo, dhi, maxbox, nstep, nfi, nmacro, fi_init=None, macro_init=None):
+        """nstep x LBLevel::advance(); returns (fi, macro, total mass)."""
+        fi, macro = np.zeros(nfi), np.zeros(nmacro)
+        mass = self.lib.sgcref_lb_run(i3(dlo), i3(dhi), i3(maxbox), nstep, self._p(fi_init), self._p(macro_init),
+                                      fi.ctypes.data, macro.ctypes.data)
+        return fi, macro, mass
+
+    def phase(self, dlo, dhi, maxbox, phase, fi, macro, prev):
+        """0 collision, 1 macroscopic, 2 stream — in place on copies, returns (fi, macro, prev)."""
+        fi, macro, prev = fi.copy(), macro.copy(), prev.copy()
+        if self.lib.sgcref_lb_phase(i3(dlo), i3(dhi), i3(maxbox), phase, fi, macro, prev):
+            raise ValueError("bad phase")
+        return fi, macro, prev
+
+    def plot(self, dlo, dhi, maxbox, nstep, macro_init=None):
+        """what LBLevel::writePlotFile hands to CGNS: (data, meta, names)"""
+        sizes = np.zeros(3, np.int64)
+        self.lib.sgcref_lb_plot(i3(dlo), i3(dhi), i3(maxbox), nstep, self._p(macro_init), sizes, None, None, None)
+        data, meta = np.zeros(sizes[0]), np.zeros(sizes[1], np.int32)
+        names = C.create_string_buffer(int(sizes[2]) + 1)
+        err = self.lib.sgcref_lb_plot(i3(dlo), i3(dhi), i3(maxbox), nstep, self._p(macro_init), sizes,
+                                      data.ctypes.data, meta.ctypes.data, names)
+        if err:
+            raise ValueError("writePlotFile failed: %d" % err)
+        return data, meta, names.value.decode().split("\n")[:-1]

@@ -637,3 +637,203 @@ uint64_t sgco_fnv1a64(const void* p, long nbytes)
   for (long n = 0; n < nbytes; ++n) { h ^= s[n]; h *= 1099511628211ull; }
   return h;
 }
+
+/* ------------------------------------------------- lattice Boltzmann application (D3Q19) */
+
+/* LBParameters.H:38-49,71-96,134-140: weights, lattice velocities, opposite directions.   */
+#define SGCO_LB_NVEL 19
+static const double lb_w[SGCO_LB_NVEL] = {
+  1./3.,
+  1./18., 1./18., 1./18., 1./18., 1./18., 1./18.,
+  1./36., 1./36., 1./36., 1./36., 1./36., 1./36.,
+  1./36., 1./36., 1./36., 1./36., 1./36., 1./36. };
+static const int lb_e[SGCO_LB_NVEL][3] = {
+  { 0, 0, 0 }, { -1, 0, 0 }, { 1, 0, 0 }, { 0, -1, 0 }, { 0, 1, 0 }, { 0, 0, -1 }, { 0, 0, 1 },
+  { -1, -1, 0 }, { 1, -1, 0 }, { -1, 1, 0 }, { 1, 1, 0 }, { -1, 0, -1 }, { 1, 0, -1 }, { -1, 0, 1 },
+  { 1, 0, 1 }, { 0, -1, -1 }, { 0, 1, -1 }, { 0, -1, 1 }, { 0, 1, 1 } };
+static const int lb_opp[SGCO_LB_NVEL] = { 0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17, 16, 15 };
+static const double lb_tau = 0.516, lb_cs2 = 1.0/3, lb_force = 0.000001042;   /* LBParameters.H:52-54 */
+
+void sgco_lb_constants(double* w19, int* e57, int* opp19, double* tau_cs2_force)
+{
+  memcpy(w19, lb_w, sizeof lb_w); memcpy(e57, lb_e, sizeof lb_e); memcpy(opp19, lb_opp, sizeof lb_opp);
+  tau_cs2_force[0] = lb_tau; tau_cs2_force[1] = lb_cs2; tau_cs2_force[2] = lb_force;
+}
+
+/* LBPatch::collision (LBPatch.H:27-46) with LBPhysics::collision (LBPhysics.H:5-14) on the valid
+ * cells of every box, no contraction (the -ffp-contract=off build of the reference):
+ *   eu   = (u0*e0 + u1*e1) + u2*e2
+ *   feq  = (w*rho)*( ((1 + eu/cs2) + (eu*eu)/((2*cs2)*cs2)) - ((u0*u0 + u1*u1) + u2*u2)/(2*cs2) )
+ *   f    = (f + (feq - f)/tau) + ((3*w)*e0)*force                                          */
+void sgco_lb_collision(const int* boxes6, int nbox, int ng, double* fi, const double* macro)
+{
+  long offf = 0, offm = 0;
+  for (int b = 0; b < nbox; ++b)
+    {
+      const int* lo = boxes6 + 6*b; const int* hi = lo + 3;
+      obox fb = mk(lo, hi);
+      box_grow(&fb, ng);
+      const long S = box_size(&fb);
+      for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+          for (int i = lo[0]; i <= hi[0]; ++i)
+            {
+              const long c = fab_index(&fb, i, j, k, 0);
+              const double rho = macro[offm + c];
+              const double u0 = macro[offm + S + c], u1 = macro[offm + 2*S + c], u2 = macro[offm + 3*S + c];
+              for (int q = 0; q < SGCO_LB_NVEL; ++q)
+                {
+                  const double eu = (u0*lb_e[q][0] + u1*lb_e[q][1]) + u2*lb_e[q][2];
+                  const double feq = (lb_w[q]*rho)*(((1 + eu/lb_cs2) + (eu*eu)/(2*lb_cs2*lb_cs2))
+                                                    - ((u0*u0 + u1*u1) + u2*u2)/(2*lb_cs2));
+                  double* f = fi + offf + q*S + c;
+                  *f = (*f + (feq - *f)/lb_tau) + 3*lb_w[q]*lb_e[q][0]*lb_force;
+                }
+            }
+      offf += S*SGCO_LB_NVEL; offm += S*4;
+    }
+}
+
+/* LBPatch::macroscopic (LBPatch.H:9-23) with LBPhysics::macroscopic (LBPhysics.H:17-35):
+ * rho = sum f_q, u_d = (sum f_q*e_q[d])/rho, sums in the order q = 0..18 starting from 0.   */
+void sgco_lb_macroscopic(const int* boxes6, int nbox, int ng, const double* fi, double* macro)
+{
+  long offf = 0, offm = 0;
+  for (int b = 0; b < nbox; ++b)
+    {
+      const int* lo = boxes6 + 6*b; const int* hi = lo + 3;
+      obox fb = mk(lo, hi);
+      box_grow(&fb, ng);
+      const long S = box_size(&fb);
+      for (int k = lo[2]; k <= hi[2]; ++k)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+          for (int i = lo[0]; i <= hi[0]; ++i)
+            {
+              const long c = fab_index(&fb, i, j, k, 0);
+              double m[4] = { 0, 0, 0, 0 };
+              for (int q = 0; q < SGCO_LB_NVEL; ++q)
+                {
+                  const double f = fi[offf + q*S + c];
+                  m[0] += f; m[1] += f*lb_e[q][0]; m[2] += f*lb_e[q][1]; m[3] += f*lb_e[q][2];
+                }
+              macro[offm + c] = m[0];
+              for (int d = 1; d < 4; ++d) macro[offm + d*S + c] = m[d]/m[0];
+            }
+      offf += S*SGCO_LB_NVEL; offm += S*4;
+    }
+}
+
+/* LBPatch::stream (LBPatch.H:49-64) without the swap: for every box and direction q,
+ * prev(box, q) = fi(box shifted by e[opp(q)], q) — each valid cell pulls from the cell at -e_q.
+ * Ghost cells of prev are not written.                                                      */
+void sgco_lb_stream(const int* boxes6, int nbox, int ng, const double* fi, double* prev)
+{
+  long off = 0;
+  for (int b = 0; b < nbox; ++b)
+    {
+      const int* lo = boxes6 + 6*b; const int* hi = lo + 3;
+      obox fb = mk(lo, hi);
+      box_grow(&fb, ng);
+      for (int q = 0; q < SGCO_LB_NVEL; ++q)
+        {
+          const int* sh = lb_e[lb_opp[q]];
+          const int slo[3] = { lo[0] + sh[0], lo[1] + sh[1], lo[2] + sh[2] };
+          const int shi[3] = { hi[0] + sh[0], hi[1] + sh[1], hi[2] + sh[2] };
+          sgco_fab_copy(fb.lo, fb.hi, SGCO_LB_NVEL, prev + off, fb.lo, fb.hi, SGCO_LB_NVEL, fi + off,
+                        lo, hi, q, slo, shi, q, 1, ~0u);
+        }
+      off += box_size(&fb)*SGCO_LB_NVEL;
+    }
+}
+
+/* The bounce-back ghost fill of LBLevel::advance (LBLevel.cpp:65-112): a box whose top face is the
+ * domain's top copies, for every cell c of its top valid layer, f_6(c) -> f_5(c+e6),
+ * f_13 -> f_12(c+e13), f_14 -> f_11(c+e14), f_17 -> f_16(c+e17), f_18 -> f_15(c+e18); ELSE a box on
+ * the domain's bottom does the mirror image (5->6, 12->13, 11->14, 16->17, 15->18 along e5, e12,
+ * e11, e16, e15).  A box touching both only gets the top treatment (the reference's else-if).     */
+void sgco_lb_bounce(const int* dlo, const int* dhi, const int* boxes6, int nbox, int ng, double* fi)
+{
+  static const int top[5][2] = { { 6, 5 }, { 13, 12 }, { 14, 11 }, { 17, 16 }, { 18, 15 } };   /* src, dst */
+  (void)dlo;
+  long off = 0;
+  for (int b = 0; b < nbox; ++b)
+    {
+      const int* lo = boxes6 + 6*b; const int* hi = lo + 3;
+      obox fb = mk(lo, hi);
+      box_grow(&fb, ng);
+      int side = 0;
+      if (hi[2] == dhi[2]) side = 1; else if (lo[2] == dlo[2]) side = -1;
+      if (side)
+        {
+          const int z = side > 0 ? hi[2] : lo[2];
+          const int slo[3] = { lo[0], lo[1], z }, shi[3] = { hi[0], hi[1], z };
+          for (int m = 0; m < 5; ++m)
+            {
+              const int sc = side > 0 ? top[m][0] : top[m][1], dc = side > 0 ? top[m][1] : top[m][0];
+              const int* e = lb_e[sc];
+              const int tlo[3] = { slo[0] + e[0], slo[1] + e[1], slo[2] + e[2] };
+              const int thi[3] = { shi[0] + e[0], shi[1] + e[1], shi[2] + e[2] };
+              double* fab = fi + off;
+              /* distinct components and disjoint cells: the in-place copy is order-independent */
+              sgco_fab_copy(fb.lo, fb.hi, SGCO_LB_NVEL, fab, fb.lo, fb.hi, SGCO_LB_NVEL, fab,
+                            tlo, thi, dc, slo, shi, sc, 1, ~0u);
+            }
+        }
+      off += box_size(&fb)*SGCO_LB_NVEL;
+    }
+}
+
+/* nstep x LBLevel::advance (LBLevel.cpp:7-127): collision; exchange(PeriodicX|PeriodicY,
+ * TrimCorner) of all 19 components; bounce-back; stream + swap; macroscopic.  fi/prev/macro are
+ * levels on the uniform layout (ng = 1); on return fi is the reference's m_curr.               */
+int sgco_lb_advance(const int* dlo, const int* dhi, const int* maxbox, int nstep,
+                    double* fi, double* prev, double* macro)
+{
+  int nb3[3];
+  const int ng = 1;
+  const int cap = ((dhi[0]-dlo[0]+1)/maxbox[0])*((dhi[1]-dlo[1]+1)/maxbox[1])*((dhi[2]-dlo[2]+1)/maxbox[2]);
+  int* boxes = (int*)malloc(sizeof(int)*6*(size_t)cap);
+  int* owner = (int*)malloc(sizeof(int)*(size_t)cap);
+  const int nbox = sgco_layout(dlo, dhi, maxbox, 1, boxes, owner, cap, nb3);
+  if (nbox < 0) { free(boxes); free(owner); return nbox; }
+  const unsigned periodic = 3u, trim = 8u;       /* PeriodicX|PeriodicY, TrimCorner (LayoutIterator.H:27-41) */
+  const int nitem = sgco_copier_items(dlo, dhi, maxbox, ng, periodic, trim, 1, 0, 0, 0);
+  int* items = (int*)malloc(sizeof(int)*SGCO_ITEM_INTS*(size_t)(nitem > 0 ? nitem : 1));
+  sgco_copier_items(dlo, dhi, maxbox, ng, periodic, trim, 1, 0, items, nitem);
+  const long tot = sgco_level_offsets(boxes, nbox, ng, SGCO_LB_NVEL, 0);
+  double* lev[2] = { fi, prev };
+  int cur = 0;
+  for (int s = 0; s < nstep; ++s)
+    {
+      sgco_lb_collision(boxes, nbox, ng, lev[cur], macro);
+      sgco_level_exchange(boxes, nbox, ng, SGCO_LB_NVEL, 0, SGCO_LB_NVEL, items, nitem, SGCO_ITEM_INTS, lev[cur]);
+      sgco_lb_bounce(dlo, dhi, boxes, nbox, ng, lev[cur]);
+      sgco_lb_stream(boxes, nbox, ng, lev[cur], lev[1 - cur]);
+      cur = 1 - cur;
+      sgco_lb_macroscopic(boxes, nbox, ng, lev[cur], macro);
+    }
+  if (cur == 1)
+    for (long n = 0; n < tot; ++n) { const double t = fi[n]; fi[n] = prev[n]; prev[n] = t; }
+  free(items); free(boxes); free(owner);
+  return nitem;
+}
+
+/* What the reference's plot writer hands to CGNS for a level (LevelData.cpp:150-193): for every
+ * box, for every component, the VALID cells (ghosts stripped), x fastest.                        */
+long sgco_level_valid_out(const int* boxes6, int nbox, int ng, int ncomp, const double* fabs, double* out)
+{
+  long off = 0, n = 0;
+  for (int b = 0; b < nbox; ++b)
+    {
+      const int* lo = boxes6 + 6*b; const int* hi = lo + 3;
+      obox fb = mk(lo, hi);
+      box_grow(&fb, ng);
+      for (int c = 0; c < ncomp; ++c)
+        for (int k = lo[2]; k <= hi[2]; ++k)
+          for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int i = lo[0]; i <= hi[0]; ++i)
+              out[n++] = fabs[off + fab_index(&fb, i, j, k, c)];
+      off += box_size(&fb)*ncomp;
+    }
+  return n;
+}

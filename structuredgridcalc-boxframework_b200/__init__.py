@@ -32,7 +32,8 @@ SYMBOLS = [
     "sgc_plan_create_bc_zero_gradient", "sgc_heat_sweep", "sgc_heat_sweep_range", "sgc_heat_sweep_ranges", "sgc_laplacian_apply",
     "sgc_wave_step", "sgc_wave_run", "sgc_heat_run", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
     "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
-    "sgc_level_upload_async", "sgc_level_download_async",
+    "sgc_level_upload_async", "sgc_level_download_async", "sgc_copyset_create", "sgc_copyset_run", "sgc_copyset_destroy",
+    "sgc_copyset_num_cells", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run",
 ]
 
 
@@ -49,6 +50,10 @@ class MotionItem(C.Structure):
                 ("tag_send", C.c_int), ("tag_recv", C.c_int), ("comp_flags", C.c_uint),
                 ("send_lo", C.c_int * 3), ("send_hi", C.c_int * 3)]
 
+
+COPY_OP_DTYPE = np.dtype([("dst_box", "i4"), ("dst_lo", "i4", 3), ("dst_hi", "i4", 3), ("dst_comp", "i4"),
+                          ("src_box", "i4"), ("src_lo", "i4", 3), ("src_comp", "i4"), ("ncomp", "i4"),
+                          ("comp_flags", "u4")])     # sgc_copy_op
 
 ITEM_DTYPE = np.dtype([("recv_box", "i4"), ("send_box", "i4"), ("recv_lo", "i4", 3), ("recv_hi", "i4", 3),
                        ("src_lo", "i4", 3), ("src_hi", "i4", 3), ("dir", "i4", 3), ("recv_proc", "i4"),
@@ -131,6 +136,16 @@ def lib():
     L.sgc_stream_sync.argtypes = [C.c_void_p]
     L.sgc_level_upload_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sgc_level_download_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sgc_copyset_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.sgc_copyset_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sgc_copyset_destroy.argtypes = [C.c_void_p]
+    L.sgc_copyset_num_cells.argtypes = [C.c_void_p]
+    L.sgc_copyset_num_cells.restype = C.c_longlong
+    L.sgc_lb_collide.argtypes = [C.c_void_p, C.c_void_p]
+    L.sgc_lb_macroscopic.argtypes = [C.c_void_p, C.c_void_p]
+    L.sgc_lb_copy_ops.argtypes = [C.c_void_p, _i3, _i3, C.c_int, C.c_void_p, C.c_int]
+    L.sgc_lb_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                             C.POINTER(C.c_int)]
     L.sgc_comm_unique_id.argtypes = [C.c_char_p]
     L.sgc_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
     _lib = L
@@ -510,6 +525,89 @@ def heat_run(a, b, copier, f, nstep, flags=SGC_FMA):
     r = C.c_int()
     check(lib().sgc_heat_run(a.h, b.h, copier.h, f, flags, nstep, C.byref(r)))
     return b if r.value else a
+
+
+class CopySet:
+    """A recorded list of BaseFab::copy calls (COPY_OP_DTYPE records, local box indices) replayed in
+    one launch: LBPatch::stream (LBPatch.H:49-64), the LB bounce-back fill (LBLevel.cpp:65-112)."""
+
+    def __init__(self, dst_like, src_like, ops):
+        ops = np.ascontiguousarray(ops, COPY_OP_DTYPE)
+        self.h = C.c_void_p()
+        check(lib().sgc_copyset_create(dst_like.h, src_like.h, ops.ctypes.data, len(ops), C.byref(self.h)))
+        self.nop = len(ops)
+
+    def run(self, dst, src):
+        check(lib().sgc_copyset_run(self.h, dst.h, src.h))
+
+    def numCells(self):
+        return int(lib().sgc_copyset_num_cells(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _lib is not None:
+            _lib.sgc_copyset_destroy(self.h)
+            self.h = None
+
+
+LB_NVEL, LB_NMACRO = 19, 4
+LB_PERIODIC, LB_TRIM = 3, 8         # PeriodicX|PeriodicY, TrimCorner (LBLevel.cpp:13)
+
+
+def lb_copy_ops(fi, which):
+    """which = 0: the stream copies, 1: the bounce-back copies, as COPY_OP_DTYPE records"""
+    dom = fi.dbl.domain
+    n = check(lib().sgc_lb_copy_ops(fi.h, _v3(dom.lo), _v3(dom.hi), which, None, 0))
+    ops = np.zeros(n, COPY_OP_DTYPE)
+    check(lib().sgc_lb_copy_ops(fi.h, _v3(dom.lo), _v3(dom.hi), which, ops.ctypes.data, n))
+    return ops
+
+
+def lb_collide(fi, macro):
+    check(lib().sgc_lb_collide(fi.h, macro.h))
+
+
+def lb_macroscopic(macro, fi):
+    check(lib().sgc_lb_macroscopic(macro.h, fi.h))
+
+
+class LBLevel:
+    """The reference's LBLevel (LBLevel.H:12-49): distribution levels m_curr / m_prev (19 comps),
+    m_macro_comps (4 comps), initialData, advance — device-resident."""
+
+    def __init__(self, dbl):
+        self.dbl = dbl
+        self.curr = LevelData(dbl, LB_NVEL, 1)
+        self.prev = LevelData(dbl, LB_NVEL, 1)
+        self.macro = LevelData(dbl, LB_NMACRO, 1)
+        self.copier = Copier().defineExchangeLD(self.curr, LB_PERIODIC, LB_TRIM)
+        self.bounce = CopySet(self.curr, self.curr, lb_copy_ops(self.curr, 1))
+        self.stream = CopySet(self.prev, self.curr, lb_copy_ops(self.curr, 0))
+        self.initialData()
+
+    def initialData(self):
+        w = [1. / 3.] + [1. / 18.] * 6 + [1. / 36.] * 12
+        for k in range(LB_NVEL):
+            self.curr.setVal(w[k], comp=k)
+            self.prev.setVal(w[k], comp=k)
+        self.macro.setVal(1.0, comp=0)
+        for k in range(1, 4):
+            self.macro.setVal(0.0, comp=k)
+
+    def advance(self, nstep=1, fuse=True):
+        r = C.c_int()
+        check(lib().sgc_lb_run(self.curr.h, self.prev.h, self.macro.h, self.copier.h, self.bounce.h, self.stream.h,
+                               nstep, 1 if fuse else 0, C.byref(r)))
+        if r.value:
+            self.curr, self.prev = self.prev, self.curr
+
+    def advance_phases(self):
+        """one step as the five separate calls of LBLevel::advance"""
+        lb_collide(self.curr, self.macro)
+        self.curr.exchange(self.copier)
+        self.bounce.run(self.curr, self.curr)
+        self.stream.run(self.prev, self.curr)
+        self.curr, self.prev = self.prev, self.curr
+        lb_macroscopic(self.macro, self.curr)
 
 
 def comm_unique_id():

@@ -609,6 +609,70 @@ int sgc_fab_copy(sgc_level_t dst, int dst_box, const int dlo[3], const int dhi[3
   return st;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Copy sets: recorded BaseFab::copy calls (LBPatch::stream, the LB bounce-back fill), one launch
+// ---------------------------------------------------------------------------------------------
+static bool set_matches(const sgc_copyset_s* c, int which, const sgc_level_s* l) {
+  return c->nbox[which] == l->nbox && c->ncomp[which] == l->ncomp && c->ng[which] == l->ng && c->esz == l->esz &&
+         memcmp(c->boxes[which].data(), l->boxes.data(), sizeof(IBox) * (size_t)l->nbox) == 0;
+}
+
+int sgc_copyset_create(sgc_level_t dst, sgc_level_t src, const sgc_copy_op* ops, int nop, sgc_copyset_t* set) {
+  SGC_REQUIRE_RT();
+  if (!dst || !src || (!ops && nop > 0) || nop < 0 || !set) return fail(SGC_ERR_ARG, "sgc_copyset_create: bad argument");
+  if (dst->esz != src->esz) return fail(SGC_ERR_ARG, "sgc_copyset_create: element types differ");
+  std::vector<CopyItem> v;
+  long long ncell = 0;
+  for (int n = 0; n < nop; ++n) {
+    const sgc_copy_op& o = ops[n];
+    if (o.dst_box < 0 || o.dst_box >= dst->nbox || o.src_box < 0 || o.src_box >= src->nbox)
+      return fail(SGC_ERR_ARG, "sgc_copyset_create: box index out of range");
+    IBox dr, sr;
+    for (int d = 0; d < 3; ++d) {
+      dr.lo[d] = o.dst_lo[d]; dr.hi[d] = o.dst_hi[d];
+      sr.lo[d] = o.src_lo[d]; sr.hi[d] = o.src_lo[d] + (o.dst_hi[d] - o.dst_lo[d]);
+    }
+    if (dr.empty()) return fail(SGC_ERR_ARG, "sgc_copyset_create: empty region");
+    if (!fab_contains(dst->geom[o.dst_box], dr) || !fab_contains(src->geom[o.src_box], sr))
+      return fail(SGC_ERR_ARG, "sgc_copyset_create: region outside fab");
+    if (o.dst_comp < 0 || o.src_comp < 0 || o.ncomp < 1 || o.dst_comp + o.ncomp > dst->ncomp ||
+        o.src_comp + o.ncomp > src->ncomp)
+      return fail(SGC_ERR_ARG, "sgc_copyset_create: component range");
+    make_items(v, dst->geom[o.dst_box], dr, o.dst_comp, src->geom[o.src_box], sr, o.src_comp, o.ncomp, o.comp_flags);
+    ncell += (long long)dr.ext(0) * dr.ext(1) * dr.ext(2) * o.ncomp;
+  }
+  sgc_copyset_s* c = new sgc_copyset_s;
+  const sgc_level_s* both[2] = {dst, src};
+  for (int w = 0; w < 2; ++w) {
+    c->nbox[w] = both[w]->nbox; c->ncomp[w] = both[w]->ncomp; c->ng[w] = both[w]->ng;
+    c->boxes[w] = both[w]->boxes;
+  }
+  c->esz = dst->esz;
+  c->ncell = ncell;
+  const int st = c->table.upload(v);
+  if (st) { delete c; return st; }
+  *set = c;
+  return 0;
+}
+
+int sgc_copyset_run(sgc_copyset_t c, sgc_level_t dst, sgc_level_t src) {
+  SGC_REQUIRE_RT();
+  if (!c || !dst || !src) return fail(SGC_ERR_ARG, "sgc_copyset_run: null argument");
+  if (!set_matches(c, 0, dst) || !set_matches(c, 1, src))
+    return fail(SGC_ERR_GEOMETRY, "sgc_copyset_run: levels differ from the ones the set was recorded on");
+  return launch_copy(c->table, dst->d_arena, src->d_arena, c->esz, rt().compute);
+}
+
+int sgc_copyset_destroy(sgc_copyset_t c) {
+  if (!c) return 0;
+  if (rt().ready) cudaStreamSynchronize(rt().compute);
+  c->table.release();
+  delete c;
+  return 0;
+}
+
+long long sgc_copyset_num_cells(sgc_copyset_t c) { return c ? c->ncell : -1; }
+
 static int linear_io(sgc_level_t l, int box, const int rlo[3], const int rhi[3], int c0, int c1, unsigned flags,
                      void* buffer, bool out) {
   SGC_REQUIRE_RT();

@@ -221,6 +221,14 @@ struct sgc_event_s {
   cudaEvent_t ev = nullptr;
 };
 
+struct sgc_copyset_s {
+  // geometry signatures of the two levels the set was recorded on
+  int nbox[2] = {0, 0}, ncomp[2] = {0, 0}, ng[2] = {0, 0}, esz = 0;
+  std::vector<sgc::IBox> boxes[2];
+  sgc::CopyTable table;
+  long long ncell = 0;
+};
+
 struct sgc_stream_s {
   cudaStream_t s = nullptr;
   void* d_stage = nullptr;      // reference-order staging area of this stream's transfers

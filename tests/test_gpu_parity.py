@@ -584,3 +584,129 @@ def test_full_size_C2_properties(g, oracle):
     mask[1:65, 1:65, 1:65] = True
     m = np.tile(mask.ravel(), a.size())
     assert abs(su[m].sum() - u[m].sum()) <= 1e-9 * abs(u[m].sum())
+
+
+# ------------------------------------------------------------------ copy sets + lattice Boltzmann application
+def test_copyset_replays_fab_copies_in_one_launch(g, oracle):
+    """A list of BaseFab::copy calls (BaseFab.cpp:296-329) between two multi-box levels with different
+    component counts, shifts into ghost cells and flags == the oracle's sequential loop."""
+    import pyoracle as po
+    L = oracle.lib
+    rng = np.random.default_rng(21)
+    dlo, dhi, mb = (0, -2, 1), (11, 5, 8), (4, 4, 4)
+    dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
+    dst, src = g.LevelData(dbl, 3, 1), g.LevelData(dbl, 5, 1)
+    d0, s0 = rng.standard_normal(dst.elems), rng.standard_normal(src.elems)
+    dst.upload(d0); src.upload(s0)
+    ops = np.zeros(dbl.size() * 2, g.COPY_OP_DTYPE)
+    want = d0.copy()
+    doff, soff = oracle.level_offsets(dbl.boxes, 1, 3), oracle.level_offsets(dbl.boxes, 1, 5)
+    for n, o in enumerate(ops):
+        b = n // 2                               # two ops per destination box, on different components
+        sb = int(rng.integers(0, dbl.size()))
+        box = dbl.boxes[b]
+        sbox = dbl.boxes[sb]
+        ext = rng.integers(1, 5, 3)
+        o["dst_box"], o["src_box"] = b, sb
+        o["dst_lo"] = box[:3] - 1 + np.array([rng.integers(0, 7 - ext[d]) for d in range(3)])
+        o["dst_hi"] = o["dst_lo"] + ext - 1
+        o["src_lo"] = sbox[:3] - 1 + np.array([rng.integers(0, 7 - ext[d]) for d in range(3)])
+        o["dst_comp"], o["src_comp"], o["ncomp"] = n % 2, int(rng.integers(0, 4)), 1
+        o["comp_flags"] = 0xFFFFFFFF if n % 3 else 0x1
+        dfl, dfh = box[:3] - 1, box[3:] + 1
+        sfl, sfh = sbox[:3] - 1, sbox[3:] + 1
+        L.sgco_fab_copy(po.i3(dfl), po.i3(dfh), 3, want[doff[b]:], po.i3(sfl), po.i3(sfh), 5, s0[soff[sb]:],
+                        po.i3(o["dst_lo"]), po.i3(o["dst_hi"]), int(o["dst_comp"]), po.i3(o["src_lo"]),
+                        po.i3(o["src_lo"] + ext - 1), int(o["src_comp"]), 1, int(o["comp_flags"]))
+    cs = g.CopySet(dst, src, ops)
+    n0 = g.launch_count()
+    cs.run(dst, src)
+    assert g.launch_count() - n0 == 1
+    assert np.array_equal(dst.download(), want) and np.array_equal(src.download(), s0)
+    other = g.LevelData(dbl, 4, 1)
+    with pytest.raises(g.SgcError):
+        cs.run(other, src)
+    ops[0]["dst_lo"][0] -= 5
+    with pytest.raises(g.SgcError):
+        g.CopySet(dst, src, ops)
+
+
+def _lb_setup(g, oracle, dlo, dhi, mb, seed):
+    rng = np.random.default_rng(seed)
+    dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
+    lb = g.LBLevel(dbl)
+    fi, mac = oracle.lb_initial(dbl.boxes)
+    fi = fi * (1 + 0.05 * rng.standard_normal(fi.size))
+    prev = fi * (1 + 0.05 * rng.standard_normal(fi.size))
+    oracle.lb_macroscopic(dbl.boxes, fi, mac)
+    lb.curr.upload(fi); lb.prev.upload(prev); lb.macro.upload(mac)
+    return dbl, lb, fi, prev, mac
+
+
+def test_lb_phases_vs_oracle(g, oracle):
+    """LBPatch::collision, macroscopic, stream and the bounce-back fill of LBLevel::advance, one at a time"""
+    for seed, (dlo, dhi, mb) in enumerate([((0, 0, 0), (15, 7, 7), (4, 4, 4)), ((2, -1, 0), (13, 6, 4), (6, 4, 5)),
+                                           ((0, 0, 0), (31, 15, 15), (16, 16, 16))]):
+        dbl, lb, fi, prev, mac = _lb_setup(g, oracle, dlo, dhi, mb, seed)
+        boxes = dbl.boxes
+        g.lb_collide(lb.curr, lb.macro)
+        oracle.lb_collision(boxes, fi, mac)
+        assert np.array_equal(lb.curr.download(), fi)
+        lb.curr.exchange(lb.copier)
+        items = oracle.copier_items(dlo, dhi, mb, 1, g.LB_PERIODIC, g.LB_TRIM)
+        oracle.level_exchange(boxes, 1, 19, items, fi)
+        assert np.array_equal(lb.curr.download(), fi)
+        lb.bounce.run(lb.curr, lb.curr)
+        oracle.lb_bounce(dlo, dhi, boxes, fi)
+        assert np.array_equal(lb.curr.download(), fi)
+        lb.stream.run(lb.prev, lb.curr)
+        oracle.lb_stream(boxes, fi, prev)
+        assert np.array_equal(lb.prev.download(), prev) and np.array_equal(lb.curr.download(), fi)
+        g.lb_macroscopic(lb.macro, lb.prev)
+        oracle.lb_macroscopic(boxes, prev, mac)
+        assert np.array_equal(lb.macro.download(), mac)
+
+
+def test_lb_advance_fused_and_unfused_vs_oracle(g, oracle):
+    for seed, (dlo, dhi, mb, nstep) in enumerate([((0, 0, 0), (15, 7, 7), (4, 4, 4), 5), ((2, -1, 0), (13, 6, 4), (6, 4, 5), 4),
+                                                  ((0, 0, 0), (31, 15, 15), (16, 16, 16), 3), ((0, 0, 0), (7, 7, 7), (8, 8, 8), 1)]):
+        results = []
+        for mode in ("phases", "unfused", "fused"):
+            dbl, lb, fi, prev, mac = _lb_setup(g, oracle, dlo, dhi, mb, 100 + seed)
+            n0 = g.launch_count()
+            if mode == "phases":
+                for _ in range(nstep):
+                    lb.advance_phases()
+            else:
+                lb.advance(nstep, fuse=(mode == "fused"))
+            launches = g.launch_count() - n0
+            assert launches == (5 * nstep if mode != "fused" else 3 * nstep + 1), (mode, launches)
+            results.append((lb.curr.download(), lb.prev.download(), lb.macro.download()))
+        oracle.lb_advance(dlo, dhi, mb, nstep, fi, prev, mac)
+        for mode, (c, p, m) in zip(("phases", "unfused", "fused"), results):
+            assert np.array_equal(c, fi), mode          # ghost cells included
+            assert np.array_equal(m, mac), mode
+            if mode != "fused":
+                assert np.array_equal(p, prev), mode    # fused: m_prev's valid cells hold post-collision values
+
+
+def test_lb_matches_reference_golden(g, golden, oracle):
+    meta, arr = golden
+    for c in meta["lb"]:
+        k = c["key"]
+        dbl = g.DisjointBoxLayout(g.Box(c["dlo"], c["dhi"]), c["maxbox"])
+        for fuse in (False, True):
+            lb = g.LBLevel(dbl)
+            lb.curr.upload(arr[k + "_fi0"]); lb.macro.upload(arr[k + "_macro0"])
+            lb.advance(c["nstep"], fuse=fuse)
+            assert np.array_equal(lb.curr.download(), arr[k + "_fi_nofma"]), k    # reference, -ffp-contract=off
+            mac = lb.macro.download()
+            assert np.array_equal(mac, arr[k + "_macro_nofma"]), k
+            ref = arr[k + "_macro"]                                               # reference, default build
+            assert np.abs(mac - ref).max() <= 1e-12 * np.abs(ref).max(), k
+    for c in meta["lb_hash"]:                    # the shipped configuration from LBLevel::initialData
+        dbl = g.DisjointBoxLayout(g.Box(c["dlo"], c["dhi"]), c["maxbox"])
+        lb = g.LBLevel(dbl)
+        lb.advance(c["nstep"])
+        assert "%016x" % oracle.fnv1a64(lb.curr.download()) == c["fnv_fi_nofma"], c["key"]
+        assert "%016x" % oracle.fnv1a64(oracle.level_valid_out(dbl.boxes, 1, 4, lb.macro.download())) == c["fnv_macro_nofma"]

@@ -140,3 +140,59 @@ def test_shipped_wavepatch_matches_reference_golden(oracle, golden):
         oracle.wave_dirsum((0, 0, 0), (h - 1,) * 3, c["factor"], c["nstep"], u0, u1, 1)
         assert np.array_equal(_valid(u0, h), _valid(arr[c["key"] + "_un"], h)), c["key"]
         assert np.array_equal(_valid(u1, h), _valid(arr[c["key"] + "_unm1"], h)), c["key"]
+
+
+# ------------------------------------------------------------------ lattice Boltzmann application
+def test_lb_advance_matches_reference_golden(oracle, golden):
+    """LBLevel::advance (LBLevel.cpp:7-127): bit-exact (ghost cells included) against the reference built
+    with -ffp-contract=off, <= 1e-12 relative against its default (contracting) build."""
+    meta, arr = golden
+    assert len(meta["lb"]) >= 2
+    for c in meta["lb"]:
+        k = c["key"]
+        boxes, owner, nb = oracle.layout(c["dlo"], c["dhi"], c["maxbox"])
+        fi, mac = arr[k + "_fi0"].copy(), arr[k + "_macro0"].copy()
+        prev = oracle.lb_initial(boxes)[0]
+        oracle.lb_advance(c["dlo"], c["dhi"], c["maxbox"], c["nstep"], fi, prev, mac)
+        assert np.array_equal(fi, arr[k + "_fi_nofma"]), k
+        assert np.array_equal(mac, arr[k + "_macro_nofma"]), k
+        ref = arr[k + "_macro"]
+        assert np.abs(mac - ref).max() <= 1e-12 * np.abs(ref).max(), k
+
+
+def test_lb_shipped_configuration_hashes(oracle, golden):
+    """latticeBoltzmann.cpp:16,36: 64x32x32 in 16^3 boxes from LBLevel::initialData"""
+    meta, arr = golden
+    for c in meta["lb_hash"]:
+        boxes, owner, nb = oracle.layout(c["dlo"], c["dhi"], c["maxbox"])
+        fi, mac = oracle.lb_initial(boxes)
+        prev = fi.copy()
+        oracle.lb_advance(c["dlo"], c["dhi"], c["maxbox"], c["nstep"], fi, prev, mac)
+        assert "%016x" % oracle.fnv1a64(fi) == c["fnv_fi_nofma"], c["key"]
+        assert "%016x" % oracle.fnv1a64(oracle.level_valid_out(boxes, 1, 4, mac)) == c["fnv_macro_nofma"], c["key"]
+
+
+def test_plot_record_matches_reference_golden(oracle, golden):
+    """What LBLevel::writePlotFile hands to CGNS (DisjointBoxLayout.cpp:224-383, LevelData.cpp:65-196):
+    per zone the vertex coordinates, then per zone and variable the valid cells, ghosts stripped."""
+    meta, arr = golden
+    c = meta["plot"][0]
+    boxes, owner, nb = oracle.layout(c["dlo"], c["dhi"], c["maxbox"])
+    fi, mac = oracle.lb_initial(boxes)
+    prev = fi.copy()
+    oracle.lb_advance(c["dlo"], c["dhi"], c["maxbox"], c["nstep"], fi, prev, mac)
+    data, pm, names = arr["plot_data"], arr["plot_meta"], c["names"]
+    nbox = len(boxes)
+    assert names[:nbox] == ["Zone_%06d" % (b + 1) for b in range(nbox)]
+    assert names[nbox:nbox + 3] == ["COMPONENT_X", "COMPONENT_Y", "COMPONENT_Z"]
+    assert names[4 * nbox:4 * nbox + 4] == ["density", "x-velocity", "y-velocity", "z-velocity"]
+    # coordinates: (n+1)^3 vertices of every box, value = the index along the direction
+    pos = 0
+    for b in boxes:
+        nv = b[3:] - b[:3] + 2
+        for d in range(3):
+            idx = np.indices((nv[2], nv[1], nv[0]))[2 - d] + b[d]
+            assert np.array_equal(data[pos:pos + idx.size], idx.ravel().astype(float))
+            pos += idx.size
+    # solution: the valid cells of every box and component
+    assert np.array_equal(data[pos:], oracle.level_valid_out(boxes, 1, 4, mac))

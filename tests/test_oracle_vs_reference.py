@@ -166,3 +166,42 @@ def test_laplacian_and_wave_random(oracle, reference):
     oracle.wave(dlo, dhi, 0.08, 5, u0, u1, 1)
     reference.wave(dlo, dhi, 0.08, 5, v0, v1)
     assert np.array_equal(u0, v0) and np.array_equal(u1, v1)
+
+
+def test_lb_phases_and_steps_random(oracle, tmp_path, monkeypatch):
+    """LBPatch::collision / macroscopic / stream one at a time, then whole LBLevel::advance steps, on
+    random layouts (one and several box layers in z) against the reference LB application."""
+    if not (po.have_reference("_lb") and po.have_reference("_lb_nofma")):
+        pytest.skip("oracle/_ref LB build not available")
+    monkeypatch.chdir(tmp_path)
+    RN, RF = po.ReferenceLB("_nofma"), po.ReferenceLB("")
+    rng = np.random.default_rng(11)
+    for case in range(6):
+        mb = rng.integers(2, 6, 3)
+        nb = rng.integers(1, 4, 3)
+        dlo = rng.integers(-3, 4, 3)
+        dhi = dlo + mb * nb - 1
+        boxes, owner, nbx = oracle.layout(dlo, dhi, mb)
+        fi, mac = oracle.lb_initial(boxes)
+        fi = fi * (1 + 0.05 * rng.standard_normal(fi.size))
+        prev = fi * (1 + 0.05 * rng.standard_normal(fi.size))
+        oracle.lb_macroscopic(boxes, fi, mac)
+        # phases
+        a = fi.copy(); oracle.lb_collision(boxes, a, mac)
+        assert np.array_equal(a, RN.phase(dlo, dhi, mb, 0, fi, mac, prev)[0]), case
+        m = np.zeros_like(mac); oracle.lb_macroscopic(boxes, fi, m)
+        want = RN.phase(dlo, dhi, mb, 1, fi, np.zeros_like(mac), prev)[1]
+        mask = want != 0                           # the reference never touches ghost cells of macro
+        assert np.array_equal(m[mask], want[mask]) and np.array_equal(m, RF.phase(dlo, dhi, mb, 1, fi, np.zeros_like(mac), prev)[1])
+        p = prev.copy(); oracle.lb_stream(boxes, fi, p)
+        rfi, _, rprev = RN.phase(dlo, dhi, mb, 2, fi, mac, prev)      # the reference swaps: its m_curr is our p
+        assert np.array_equal(p, rfi) and np.array_equal(fi, rprev), case
+        # whole steps
+        nstep = int(rng.integers(1, 6))
+        f2, m2 = fi.copy(), mac.copy()
+        p2 = oracle.lb_initial(boxes)[0]
+        oracle.lb_advance(dlo, dhi, mb, nstep, f2, p2, m2)
+        rfi, rmac, mass = RN.run(dlo, dhi, mb, nstep, fi.size, mac.size, fi, mac)
+        assert np.array_equal(f2, rfi) and np.array_equal(m2, rmac), case
+        ffi, fmac, _ = RF.run(dlo, dhi, mb, nstep, fi.size, mac.size, fi, mac)
+        assert np.abs(f2 - ffi).max() <= 1e-12 * np.abs(ffi).max(), case
