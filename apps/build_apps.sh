@@ -14,7 +14,7 @@ OUT="$HERE/_build"
 mkdir -p "$OUT"
 FL="-std=c++17 -O2 -Wall -Wno-vla -Wno-unknown-pragmas -I$ROOT/include -I$ROOT/include/BoxFramework"
 LD="-L$PKG -lsgc_b200 -Wl,-rpath,\$ORIGIN/../../structuredgridcalc-boxframework_b200"
-for app in laplacian levelheat wave; do
+for app in laplacian levelheat wave latticeBoltzmann; do
   [ -f "$HERE/$app.cpp" ] && $CXX $FL -o "$OUT/$app" "$HERE/$app.cpp" $LD
 done
 if [ -d "$REF_DIR/lib/test/BoxFramework" ]; then

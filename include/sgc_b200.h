@@ -168,6 +168,9 @@ int sgc_level_download(sgc_level_t level, int box, void* host);
  * run beside the compute stream (kernels of all other entry points) and beside each other:
  * batch i+1 uploads and batch i-1 downloads while batch i sweeps.  Both calls return after
  * enqueueing; `host` must be pinned (sgc_host_alloc) and stay valid until the stream passed it.
+ * A download first gathers the level into the stream's staging area and then copies that to the
+ * host: `gathered` (may be NULL) is recorded between the two, so a compute stream that waits for it
+ * may overwrite the level while the D2H copy is still in flight.
  * Ordering between streams is explicit, through events: sgc_event_record_stream marks a point
  * of a stream, sgc_stream_wait_event makes work submitted LATER to `stream` start after that
  * point.  A NULL stream argument names the library's compute stream.                         */
@@ -177,7 +180,16 @@ int sgc_stream_sync(sgc_stream_t stream);
 int sgc_event_record_stream(sgc_event_t ev, sgc_stream_t stream);
 int sgc_stream_wait_event(sgc_stream_t stream, sgc_event_t ev);
 int sgc_level_upload_async(sgc_level_t level, const void* host, sgc_stream_t stream);
-int sgc_level_download_async(sgc_level_t level, void* host, sgc_stream_t stream);
+int sgc_level_download_async(sgc_level_t level, void* host, sgc_stream_t stream, sgc_event_t gathered);
+
+/* Plot output from device data: what LevelData::writeCGNSSolData hands to CGNS
+ * (LevelData.cpp:150-193: per box, per component, the core grid only — ghosts stripped through
+ * memrmin/memrmax) gathered on the device into one dense buffer [box][comp][k][j][i] and copied
+ * to the host; the async form runs on a transfer stream beside the compute stream, the overlap of
+ * wave.cpp:230-275.  sgc_level_valid_elems = elements of that buffer.                          */
+long long sgc_level_valid_elems(sgc_level_t level);
+int sgc_level_download_valid(sgc_level_t level, void* host);
+int sgc_level_download_valid_async(sgc_level_t level, void* host, sgc_stream_t stream, sgc_event_t gathered);
 /* LevelData::setVal / BaseFab::setVal (LevelData.H:352-383, BaseFab.cpp:219-246);
  * comp = -1: all components.  `value` points at one element of elem_bytes bytes.           */
 int sgc_level_setval(sgc_level_t level, int box, int comp, const void* value);

@@ -33,7 +33,7 @@ SYMBOLS = [
     "sgc_wave_step", "sgc_wave_run", "sgc_heat_run", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
     "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
     "sgc_level_upload_async", "sgc_level_download_async", "sgc_copyset_create", "sgc_copyset_run", "sgc_copyset_destroy",
-    "sgc_copyset_num_cells", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run",
+    "sgc_copyset_num_cells", "sgc_level_valid_elems", "sgc_level_download_valid", "sgc_level_download_valid_async", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run",
 ]
 
 
@@ -135,7 +135,11 @@ def lib():
     L.sgc_stream_wait_event.argtypes = [C.c_void_p, C.c_void_p]
     L.sgc_stream_sync.argtypes = [C.c_void_p]
     L.sgc_level_upload_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    L.sgc_level_download_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sgc_level_download_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sgc_level_valid_elems.argtypes = [C.c_void_p]
+    L.sgc_level_valid_elems.restype = C.c_longlong
+    L.sgc_level_download_valid.argtypes = [C.c_void_p, C.c_void_p]
+    L.sgc_level_download_valid_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sgc_copyset_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.sgc_copyset_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sgc_copyset_destroy.argtypes = [C.c_void_p]
@@ -398,10 +402,27 @@ class LevelData:
         check(lib().sgc_level_upload_async(self.h, pinned.ptr, stream.h))
         return self
 
-    def downloadAsync(self, pinned, stream):
+    def downloadAsync(self, pinned, stream, gathered=None):
+        """`gathered` (an Event) is recorded once the level has been read: waiting for it is enough
+        before the level is overwritten, the D2H copy may still be in flight"""
         assert pinned.array.size == self.elems and pinned.array.dtype == self.dtype
-        check(lib().sgc_level_download_async(self.h, pinned.ptr, stream.h))
+        check(lib().sgc_level_download_async(self.h, pinned.ptr, stream.h, gathered.h if gathered else None))
         return self
+
+    def validElems(self):
+        return int(lib().sgc_level_valid_elems(self.h))
+
+    def downloadValid(self, out=None, stream=None, gathered=None):
+        """plot gather: [box][comp] valid cells, ghosts stripped (LevelData.cpp:150-193).  With `stream`
+        (and `out` a PinnedBuffer) the gather + D2H run on that transfer stream and the call returns."""
+        if stream is not None:
+            assert out.array.size == self.validElems()
+            check(lib().sgc_level_download_valid_async(self.h, out.ptr, stream.h, gathered.h if gathered else None))
+            return out
+        if out is None:
+            out = np.empty(self.validElems(), self.dtype)
+        check(lib().sgc_level_download_valid(self.h, out.ctypes.data))
+        return out
 
     def setVal(self, value, comp=-1, box=-1):
         v = np.array([value], self.dtype)

@@ -407,6 +407,7 @@ int sgc_level_destroy(sgc_level_t l) {
   if (rt().ready) cudaStreamSynchronize(rt().compute);
   l->conv_in.release();
   l->conv_out.release();
+  l->conv_valid.release();
   if (l->d_base) cudaFree(l->d_base);
   if (l->d_geom) cudaFree(l->d_geom);
   if (l->d_work) cudaFree(l->d_work);
@@ -540,13 +541,62 @@ int sgc_level_upload_async(sgc_level_t l, const void* host, sgc_stream_t x) {
   return launch_copy(l->conv_in, l->d_arena, x->d_stage, l->esz, x->s);
 }
 
-int sgc_level_download_async(sgc_level_t l, void* host, sgc_stream_t x) {
+int sgc_level_download_async(sgc_level_t l, void* host, sgc_stream_t x, sgc_event_t gathered) {
   SGC_REQUIRE_RT();
   if (!l || !host || !x) return fail(SGC_ERR_ARG, "sgc_level_download_async: bad argument");
   const size_t bytes = (size_t)l->elems * l->esz;
   int st = stream_stage(x, bytes);
   if (!st) st = launch_copy(l->conv_out, x->d_stage, l->d_arena, l->esz, x->s);
   if (st) return st;
+  if (gathered) SGC_CUDA(cudaEventRecord(gathered->ev, x->s));
+  SGC_CUDA(cudaMemcpyAsync(host, x->d_stage, bytes, cudaMemcpyDeviceToHost, x->s));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Plot gather: valid cells only (LevelData::writeCGNSSolData, LevelData.cpp:150-193)
+// ---------------------------------------------------------------------------------------------
+long long sgc_level_valid_elems(sgc_level_t l) {
+  if (!l) return -1;
+  long long n = 0;
+  for (const IBox& b : l->boxes) n += b.size() * l->ncomp;
+  return n;
+}
+
+static int ensure_valid_table(sgc_level_s* l) {
+  if (l->conv_valid.d_items || l->nbox == 0) return 0;
+  std::vector<CopyItem> v;
+  long long off = 0;
+  for (int b = 0; b < l->nbox; ++b) {
+    const IBox& vb = l->boxes[b];
+    make_items(v, dense_geom(vb, off), vb, 0, l->geom[b], vb, 0, l->ncomp, ~0u);
+    off += vb.size() * l->ncomp;
+  }
+  l->valid_elems = off;
+  return l->conv_valid.upload(v);
+}
+
+int sgc_level_download_valid(sgc_level_t l, void* host) {
+  SGC_REQUIRE_RT();
+  if (!l || !host) return fail(SGC_ERR_ARG, "sgc_level_download_valid: bad argument");
+  int st = ensure_valid_table(l);
+  if (!st) st = ensure_stage((size_t)sgc_level_valid_elems(l) * l->esz);
+  if (!st) st = launch_copy(l->conv_valid, rt().d_stage, l->d_arena, l->esz, rt().compute);
+  if (st) return st;
+  SGC_CUDA(cudaMemcpyAsync(host, rt().d_stage, (size_t)sgc_level_valid_elems(l) * l->esz, cudaMemcpyDeviceToHost, rt().compute));
+  SGC_CUDA(cudaStreamSynchronize(rt().compute));
+  return 0;
+}
+
+int sgc_level_download_valid_async(sgc_level_t l, void* host, sgc_stream_t x, sgc_event_t gathered) {
+  SGC_REQUIRE_RT();
+  if (!l || !host || !x) return fail(SGC_ERR_ARG, "sgc_level_download_valid_async: bad argument");
+  const size_t bytes = (size_t)sgc_level_valid_elems(l) * l->esz;
+  int st = ensure_valid_table(l);
+  if (!st) st = stream_stage(x, bytes);
+  if (!st) st = launch_copy(l->conv_valid, x->d_stage, l->d_arena, l->esz, x->s);
+  if (st) return st;
+  if (gathered) SGC_CUDA(cudaEventRecord(gathered->ev, x->s));
   SGC_CUDA(cudaMemcpyAsync(host, x->d_stage, bytes, cudaMemcpyDeviceToHost, x->s));
   return 0;
 }

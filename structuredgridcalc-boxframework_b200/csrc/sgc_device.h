@@ -162,6 +162,8 @@ struct sgc_level_s {
   long long xg_base = 0;                // element offset of the xg region in the arena
   long long arena_elems = 0;            // main + xg (+ padding)
   sgc::CopyTable conv_in, conv_out;     // reference-order staging <-> split-x arena, whole level
+  sgc::CopyTable conv_valid;            // arena -> [box][comp] valid cells only (plot output), built on first use
+  long long valid_elems = 0;
   sgc::FabGeom* d_geom = nullptr;
   std::vector<sgc::FabGeom> geom;
   bool uniform = true;                  // all fabs have the same extents

@@ -85,3 +85,33 @@ def test_wave_driver_facade_matches_shipped_wavepatch(oracle, golden):
     m = c["h"] + 2
     want = arr["wp16_pulse_un"].reshape(m, m, m)[1:-1, 1:-1, 1:-1].copy()
     assert line["un_valid_fnv1a64"] == "%016x" % oracle.fnv1a64(want)
+
+
+@pytest.mark.gpu
+def test_lattice_boltzmann_driver_facade_known_answer(golden, tmp_path):
+    # apps/latticeBoltzmann (C++ facade, LBLevel interface of the reference) on the shipped
+    # configuration: hash of the plot data (valid cells of the macroscopic level) after 1 and 40
+    # steps == the reference application's (-ffp-contract=off build), in one call and step by step
+    import numpy as np
+    meta, arr = golden
+    for c in meta["lb_hash"]:
+        for per_call in ("0", "1", "7"):
+            path = os.path.join(BUILD, "latticeBoltzmann")
+            if not os.path.exists(path):
+                pytest.skip("latticeBoltzmann not built")
+            r = subprocess.run([path, "64", "32", "32", "16", str(c["nstep"]), "0", per_call], capture_output=True,
+                               text=True, timeout=300, cwd=tmp_path)
+            assert r.returncode == 0, r.stdout + r.stderr
+            line = json.loads(r.stdout.strip().splitlines()[-1])
+            assert line["macro_fnv1a64"] == c["fnv_macro_nofma"], (c["key"], per_call)
+            assert abs(line["mass"] - c["mass_nofma"]) <= 1e-9 * c["mass_nofma"]
+    # plot file: header + the gathered valid cells
+    r = subprocess.run([os.path.join(BUILD, "latticeBoltzmann"), "8", "4", "8", "4", "3", "3"], capture_output=True,
+                       text=True, timeout=300, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(os.path.join(tmp_path, "plot", "solution0000.sgcplot"), "rb").read()
+    head, _, rest = raw.partition(b"data ")
+    n = int(rest.split(b"\n", 1)[0])
+    data = np.frombuffer(rest.split(b"\n", 1)[1], np.float64)
+    assert n == data.size == 4 * 8 * 4 * 8 and head.startswith(b"SGCPLOT 1\nzones 4\n")
+    assert (data[:64] == 1.0).all() and (data[64:256] == 0.0).all()     # initialData: rho = 1, u = 0 (zone 1)

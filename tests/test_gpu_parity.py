@@ -710,3 +710,37 @@ def test_lb_matches_reference_golden(g, golden, oracle):
         lb.advance(c["nstep"])
         assert "%016x" % oracle.fnv1a64(lb.curr.download()) == c["fnv_fi_nofma"], c["key"]
         assert "%016x" % oracle.fnv1a64(oracle.level_valid_out(dbl.boxes, 1, 4, lb.macro.download())) == c["fnv_macro_nofma"]
+
+
+def test_plot_gather_matches_reference_writer(g, golden, oracle):
+    """LBLevel::writePlotFile -> LevelData::writeCGNSSolData (LevelData.cpp:150-193): the solution values the
+    reference hands to CGNS (recorded through the CGNS stand-in) == the device gather of the valid cells."""
+    meta, arr = golden
+    c = meta["plot"][0]
+    dbl = g.DisjointBoxLayout(g.Box(c["dlo"], c["dhi"]), c["maxbox"])
+    lb = g.LBLevel(dbl)
+    lb.advance(c["nstep"])
+    nsol = lb.macro.validElems()
+    assert nsol == 4 * 8 * 4 * 8
+    want = arr["plot_data"][-nsol:]
+    assert np.array_equal(lb.macro.downloadValid(), want)
+    # asynchronous form on a transfer stream, ordered after the compute stream by an event
+    pin = g.PinnedBuffer(nsol)
+    pin.array[:] = -1
+    xs, ev, gathered = g.Stream(), g.Event(), g.Event()
+    lb.advance(2)
+    ev.record()
+    xs.wait(ev)
+    lb.macro.downloadValid(out=pin, stream=xs, gathered=gathered)
+    g.compute_wait(gathered)                     # macro may be rewritten once it has been gathered ...
+    lb.advance(1)                                # ... while the D2H copy is still in flight
+    xs.sync()
+    ref = g.LBLevel(dbl)
+    ref.advance(c["nstep"] + 2)
+    assert np.array_equal(pin.array, ref.macro.downloadValid())
+    # multi-component level with 2 ghost layers and an offset domain
+    rng = np.random.default_rng(9)
+    dbl2, lev = make_level(g, (1, -1, 1), (12, 10, 12), (4, 4, 4), 3, 2)
+    u = rng.standard_normal(lev.elems)
+    lev.upload(u)
+    assert np.array_equal(lev.downloadValid(), oracle.level_valid_out(dbl2.boxes, 2, 3, u))
