@@ -326,6 +326,10 @@ int sgc_lb_macroscopic(sgc_level_t macro, sgc_level_t fi);
 int sgc_lb_copy_ops(sgc_level_t fi, const int dlo[3], const int dhi[3], int which, sgc_copy_op* ops, int cap);
 int sgc_lb_run(sgc_level_t fi, sgc_level_t prev, sgc_level_t macro, sgc_plan_t exchange, sgc_copyset_t bounce,
                sgc_copyset_t stream, int nstep, int fuse, int* result_in_prev);
+/* Device self-test of the collision's three-instruction division by the constants
+ * which = 0 cs2, 1 2*cs2, 2 2*cs2*cs2, 3 tau (sgc_lb.cu, tests/test_divconst_proof.py): for n
+ * HOST values x writes the fast quotient and the IEEE x / c computed on the device.            */
+int sgc_lb_selftest_divconst(int which, const double* x, double* fast, double* exact, long long n, double* constant);
 
 /* ------------------------------------------------------------------ multi-GPU ------------ */
 

@@ -33,7 +33,7 @@ SYMBOLS = [
     "sgc_wave_step", "sgc_wave_run", "sgc_heat_run", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
     "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
     "sgc_level_upload_async", "sgc_level_download_async", "sgc_copyset_create", "sgc_copyset_run", "sgc_copyset_destroy",
-    "sgc_copyset_num_cells", "sgc_level_valid_elems", "sgc_level_download_valid", "sgc_level_download_valid_async", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run",
+    "sgc_copyset_num_cells", "sgc_level_valid_elems", "sgc_level_download_valid", "sgc_level_download_valid_async", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run", "sgc_lb_selftest_divconst",
 ]
 
 
@@ -148,6 +148,7 @@ def lib():
     L.sgc_lb_collide.argtypes = [C.c_void_p, C.c_void_p]
     L.sgc_lb_macroscopic.argtypes = [C.c_void_p, C.c_void_p]
     L.sgc_lb_copy_ops.argtypes = [C.c_void_p, _i3, _i3, C.c_int, C.c_void_p, C.c_int]
+    L.sgc_lb_selftest_divconst.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_double)]
     L.sgc_lb_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                              C.POINTER(C.c_int)]
     L.sgc_comm_unique_id.argtypes = [C.c_char_p]
@@ -581,6 +582,14 @@ def lb_copy_ops(fi, which):
     ops = np.zeros(n, COPY_OP_DTYPE)
     check(lib().sgc_lb_copy_ops(fi.h, _v3(dom.lo), _v3(dom.hi), which, ops.ctypes.data, n))
     return ops
+
+
+def lb_selftest_divconst(which, x):
+    """(fast, exact, constant): the collision's 3-instruction x / c against the device's IEEE division"""
+    x = np.ascontiguousarray(x, np.float64)
+    fast, exact, c = np.empty_like(x), np.empty_like(x), C.c_double()
+    check(lib().sgc_lb_selftest_divconst(which, x.ctypes.data, fast.ctypes.data, exact.ctypes.data, x.size, C.byref(c)))
+    return fast, exact, c.value
 
 
 def lb_collide(fi, macro):

@@ -612,6 +612,12 @@ int sgc_level_setval(sgc_level_t l, int box, int comp, const void* value) {
       st = launch_fill((char*)l->d_arena + l->xg_base * l->esz, l->arena_elems - l->xg_base, l->esz, value, rt().compute);
     return st;
   }
+  if (box < 0) {
+    // one component of every fab: one launch over the device box table
+    long long mx = 0;
+    for (const FabGeom& g : l->geom) mx = std::max(mx, g.cs + g.xcs);
+    return launch_fill_fabs(l->d_arena, l->d_geom, l->nbox, mx, comp, 1, l->esz, value, rt().compute);
+  }
   for (int b = b0; b < b1; ++b) {
     const FabGeom& g = l->geom[b];
     const int c0 = comp < 0 ? 0 : comp, nc = comp < 0 ? l->ncomp : 1;

@@ -146,6 +146,8 @@ struct PushArgs {
 // launchers implemented in sgc_kernels.cu
 int launch_copy(const CopyTable& t, void* dst_arena, const void* src_arena, int esz, cudaStream_t s);
 int launch_fill(void* p, long long n, int esz, const void* value, cudaStream_t s);
+int launch_fill_fabs(void* arena, const FabGeom* d_geom, int nbox, long long max_elems, int c0, int nc, int esz,
+                     const void* value, cudaStream_t s);
 
 }  // namespace sgc
 

@@ -97,6 +97,37 @@ __global__ void k_fill(T* __restrict__ p, long long n, T v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
 
+// LevelData::setVal(comp, val) over every fab of a level in one launch: blockIdx.y = fab, the main
+// and xg blocks of components [c0, c0+nc) are contiguous ranges of the arena
+template <typename T>
+__global__ void k_fill_fabs(T* __restrict__ arena, const FabGeom* __restrict__ geom, int c0, int nc, T v) {
+  const FabGeom g = geom[blockIdx.y];
+  const long long nmain = g.cs * nc, nx = g.xcs * nc;
+  T* pm = arena + g.off + c0 * g.cs;
+  T* px = arena + g.xoff + c0 * g.xcs;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nmain + nx; i += stride) {
+    if (i < nmain) pm[i] = v; else px[i - nmain] = v;
+  }
+}
+
+int launch_fill_fabs(void* arena, const FabGeom* d_geom, int nbox, long long max_elems, int c0, int nc, int esz,
+                     const void* value, cudaStream_t s) {
+  if (nbox <= 0) return 0;
+  const int threads = 256;
+  long long want = (max_elems + threads - 1) / threads;
+  const dim3 grid((unsigned)(want < 64 ? (want < 1 ? 1 : want) : 64), (unsigned)nbox, 1);
+  switch (esz) {
+    case 8: k_fill_fabs<uint64_t><<<grid, threads, 0, s>>>((uint64_t*)arena, d_geom, c0, nc, *(const uint64_t*)value); break;
+    case 4: k_fill_fabs<uint32_t><<<grid, threads, 0, s>>>((uint32_t*)arena, d_geom, c0, nc, *(const uint32_t*)value); break;
+    case 1: k_fill_fabs<uint8_t><<<grid, threads, 0, s>>>((uint8_t*)arena, d_geom, c0, nc, *(const uint8_t*)value); break;
+    default: return fail(SGC_ERR_UNSUPPORTED, "element size must be 1, 4 or 8 bytes");
+  }
+  rt().launches++;
+  SGC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_fill(void* p, long long n, int esz, const void* value, cudaStream_t s) {
   if (n <= 0) return 0;
   const int threads = 256;

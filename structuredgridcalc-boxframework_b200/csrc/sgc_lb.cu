@@ -51,28 +51,98 @@ __device__ __forceinline__ long long valid_cell(const FabGeom& g, int t) {
   return fab_index(g, i + g.vlo[0] - g.lo[0], j + g.vlo[1] - g.lo[1], k + g.vlo[2] - g.lo[2], 0);
 }
 
-// LBPhysics::collision for the 19 directions of one cell, in place
-__device__ __forceinline__ void collide_cell(double* f /* [kQ] */, double rho, double u0, double u1, double u2) {
-  const double usq = ((u0 * u0 + u1 * u1) + u2 * u2) / (2 * kCs2);
-#pragma unroll
-  for (int q = 0; q < kQ; ++q) {
-    const double eu = (u0 * c_e[q][0] + u1 * c_e[q][1]) + u2 * c_e[q][2];
-    const double feq = (c_w[q] * rho) * (((1 + eu / kCs2) + (eu * eu) / (2 * kCs2 * kCs2)) - usq);
-    f[q] = (f[q] + (feq - f[q]) / kTau) + 3 * c_w[q] * c_e[q][0] * kForce;
-  }
+// ---------------------------------------------------------------------------------------------
+// Correctly rounded division by a compile-time constant in three FP64 instructions.
+//
+// The collision divides 58 times per cell by the four constants cs2, 2*cs2, 2*cs2*cs2 and tau; an
+// IEEE double division costs ~12 instructions on the FP64 pipe, which (not HBM) is what bounds this
+// kernel on B200.  With rc = RN(1/c):   q = RN(x*rc);  r = x - q*c (exact, one fma);
+// x/c == RN(q + r*rc).  This is correctly rounded for every normal x unless x/c lies within ~2^-53
+// ulp of a rounding boundary; for a given c those x are the solutions of a linear congruence, a
+// handful of mantissas, and tests/test_divconst_proof.py enumerates and checks them with exact
+// rational arithmetic for each of the four constants (none fails) — so the result equals the
+// reference's `/` bit for bit.  Zeros, subnormals, huge values, inf and nan take the real division.
+// ---------------------------------------------------------------------------------------------
+template <int K> struct DivConst;
+template <> struct DivConst<0> { static constexpr double c = kCs2; };
+template <> struct DivConst<1> { static constexpr double c = 2 * kCs2; };
+template <> struct DivConst<2> { static constexpr double c = 2 * kCs2 * kCs2; };
+template <> struct DivConst<3> { static constexpr double c = kTau; };
+
+template <int K>
+__device__ __forceinline__ double divc(double x) {
+  constexpr double c = DivConst<K>::c;
+  constexpr double rc = 1.0 / c;
+  const unsigned e = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+  if (e - 64u >= 1920u) return x / c;            // |x| < 2^-959 (incl. 0) or >= 2^961, inf, nan
+  const double q = __dmul_rn(x, rc);
+  const double r = __fma_rn(-q, c, x);
+  return __fma_rn(r, rc, q);
 }
 
-// LBPhysics::macroscopic of one cell
-__device__ __forceinline__ void moments_cell(const double* f, double* m /* [4] */) {
-  double r = 0, a = 0, b = 0, c = 0;
-#pragma unroll
-  for (int q = 0; q < kQ; ++q) {
-    r += f[q];
-    a += f[q] * c_e[q][0];
-    b += f[q] * c_e[q][1];
-    c += f[q] * c_e[q][2];
+// LBPhysics::collision for the 19 directions of one cell, in place (LBPhysics.H:5-14):
+//   eu  = (u0*e0 + u1*e1) + u2*e2
+//   feq = (w*rho)*( ((1 + eu/cs2) + (eu*eu)/(2*cs2*cs2)) - ((u0*u0 + u1*u1) + u2*u2)/(2*cs2) )
+//   f   = (f + (feq - f)/tau) + ((3*w)*e0)*force
+// evaluated with the same operations on the same values, minus the ones whose result is known:
+// products with the lattice components 0 and +-1 are exact, so eu is one of +-u_a, +-(u_a + u_b),
+// +-(u_a - u_b) (negation commutes with rounding; the sign of a zero eu cannot reach f), and
+// eu/cs2, eu*eu/(2 cs2^2) are shared by the two directions of a pair.
+__device__ __forceinline__ void collide_cell(double* f /* [kQ] */, double rho, double u0, double u1, double u2) {
+  const double usq = divc<1>((u0 * u0 + u1 * u1) + u2 * u2);
+  const double wr0 = (1. / 3.) * rho, wr1 = (1. / 18.) * rho, wr2 = (1. / 36.) * rho;
+  constexpr double F1 = 3 * (1. / 18.) * kForce, F2 = 3 * (1. / 36.) * kForce;   // ((3*w)*(+-1))*force
+  // one direction: t = ((1 +- a) + b) - usq, then relax towards (w*rho)*t and add the body force
+#define SGC_LB_RELAX(q, t, wr, force) \
+  f[q] = (f[q] + divc<3>((wr) * (t) - f[q])) + (force)
+  {
+    const double t = (1.0 - usq);                       // eu == 0: (1 + 0) + 0
+    SGC_LB_RELAX(0, t, wr0, 0.0);
   }
+#define SGC_LB_PAIR(qpos, qneg, eu, wr, fpos, fneg)                      \
+  {                                                                     \
+    const double eu_ = (eu);                                            \
+    const double a = divc<0>(eu_), b = divc<2>(eu_ * eu_);              \
+    const double tp = ((1.0 + a) + b) - usq, tn = ((1.0 - a) + b) - usq; \
+    SGC_LB_RELAX(qpos, tp, wr, fpos);                                   \
+    SGC_LB_RELAX(qneg, tn, wr, fneg);                                   \
+  }
+  SGC_LB_PAIR(2, 1, u0, wr1, F1, -F1)
+  SGC_LB_PAIR(4, 3, u1, wr1, 0.0, 0.0)
+  SGC_LB_PAIR(6, 5, u2, wr1, 0.0, 0.0)
+  SGC_LB_PAIR(10, 7, u0 + u1, wr2, F2, -F2)
+  SGC_LB_PAIR(8, 9, u0 - u1, wr2, F2, -F2)
+  SGC_LB_PAIR(14, 11, u0 + u2, wr2, F2, -F2)
+  SGC_LB_PAIR(12, 13, u0 - u2, wr2, F2, -F2)
+  SGC_LB_PAIR(18, 15, u1 + u2, wr2, 0.0, 0.0)
+  SGC_LB_PAIR(16, 17, u1 - u2, wr2, 0.0, 0.0)
+#undef SGC_LB_PAIR
+#undef SGC_LB_RELAX
+}
+
+// LBPhysics::macroscopic of one cell (LBPhysics.H:17-35): the four sums run over q = 0..18 in order,
+// starting from 0; terms multiplied by a zero lattice component add +-0 to a sum that is never -0
+// and are skipped, f*(+-1) is +-f.
+__device__ __forceinline__ void moments_cell(const double* f, double* m /* [4] */) {
+  double r = 0.0 + f[0];
+#pragma unroll
+  for (int q = 1; q < kQ; ++q) r += f[q];
+  double a = 0.0 - f[1];
+  a += f[2]; a -= f[7]; a += f[8]; a -= f[9]; a += f[10]; a -= f[11]; a += f[12]; a -= f[13]; a += f[14];
+  double b = 0.0 - f[3];
+  b += f[4]; b -= f[7]; b -= f[8]; b += f[9]; b += f[10]; b -= f[15]; b += f[16]; b -= f[17]; b += f[18];
+  double c = 0.0 - f[5];
+  c += f[6]; c -= f[11]; c -= f[12]; c += f[13]; c += f[14]; c -= f[15]; c -= f[16]; c += f[17]; c += f[18];
   m[0] = r; m[1] = a / r; m[2] = b / r; m[3] = c / r;
+}
+
+// device check of divc against the real division (tests)
+template <int K>
+__global__ void k_divc_check(const double* __restrict__ x, double* __restrict__ fast, double* __restrict__ exact, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fast[i] = divc<K>(x[i]);
+  exact[i] = x[i] / DivConst<K>::c;
 }
 
 __global__ void __launch_bounds__(kLbThreads)
@@ -181,6 +251,29 @@ int sgc_lb_macroscopic(sgc_level_t macro, sgc_level_t fi) {
                                                                 (double*)macro->d_arena);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sgc_lb_selftest_divconst(int which, const double* x, double* fast, double* exact, long long n, double* constant) {
+  SGC_REQUIRE_RT();
+  if (which < 0 || which > 3 || !x || !fast || !exact || n < 1) return fail(SGC_ERR_ARG, "sgc_lb_selftest_divconst: bad argument");
+  double *dx = nullptr, *df = nullptr, *de = nullptr;
+  SGC_CUDA(cudaMalloc(&dx, sizeof(double) * n));
+  SGC_CUDA(cudaMalloc(&df, sizeof(double) * n));
+  SGC_CUDA(cudaMalloc(&de, sizeof(double) * n));
+  SGC_CUDA(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  switch (which) {
+    case 0: k_divc_check<0><<<blocks, 256, 0, rt().compute>>>(dx, df, de, n); if (constant) *constant = DivConst<0>::c; break;
+    case 1: k_divc_check<1><<<blocks, 256, 0, rt().compute>>>(dx, df, de, n); if (constant) *constant = DivConst<1>::c; break;
+    case 2: k_divc_check<2><<<blocks, 256, 0, rt().compute>>>(dx, df, de, n); if (constant) *constant = DivConst<2>::c; break;
+    default: k_divc_check<3><<<blocks, 256, 0, rt().compute>>>(dx, df, de, n); if (constant) *constant = DivConst<3>::c; break;
+  }
+  cudaError_t e = cudaStreamSynchronize(rt().compute);
+  if (e == cudaSuccess) e = cudaMemcpy(fast, df, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(exact, de, sizeof(double) * n, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(df); cudaFree(de);
+  if (e != cudaSuccess) return fail(SGC_ERR_CUDA, cudaGetErrorString(e));
   return 0;
 }
 
