@@ -107,7 +107,8 @@ int sgc_sync(void);
 long long sgc_launch_count(void);
 
 /* Per-kernel device timing for the roofline report: while enabled, every sweep launch (class 0)
- * and every batched copy launch of an exchange (class 1) is bracketed by a cudaEvent pair on its
+ * every batched copy launch of an exchange (class 1) and every two-step sweep launch (class 2,
+ * sgc_heat_run's temporal-blocking passes) is bracketed by a cudaEvent pair on its
  * own stream.  sgc_profile_read synchronises and returns the launch count and the summed
  * duration per class, then clears the log.  At most 8192 launches are logged per class.      */
 int sgc_profile_enable(int on);

@@ -180,7 +180,7 @@ def profile_enable(on=True):
 
 
 def profile_read(klass):
-    """(launches, total_ms) of class 0 = sweep kernels, 1 = exchange copy kernels; clears the log."""
+    """(launches, total_ms) of class 0 = sweep kernels, 1 = exchange copy kernels, 2 = two-step sweep passes; clears the log."""
     n, ms = C.c_int(), C.c_double()
     check(lib().sgc_profile_read(klass, C.byref(n), C.byref(ms)))
     return n.value, ms.value

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgc_b200.so")
-SOURCES = ["sgc_plan.cpp", "sgc_device.cu", "sgc_kernels.cu", "sgc_stream.cu", "sgc_comm.cu", "sgc_lb.cu"]
+SOURCES = ["sgc_plan.cpp", "sgc_device.cu", "sgc_kernels.cu", "sgc_stream.cu", "sgc_stream2.cu", "sgc_comm.cu", "sgc_lb.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",              # never contract behind our back: FMAs are explicit __fma_rn calls

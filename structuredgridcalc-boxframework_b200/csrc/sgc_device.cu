@@ -35,6 +35,10 @@ void comm_p2p_release(sgc_plan_s* plan);
 int comm_p2p_signal(sgc_plan_s* plan, unsigned long long value, cudaStream_t s);
 int comm_p2p_check(sgc_plan_s* plan);
 bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u);
+bool heat_t2_covers(const sgc_level_s* unew, const sgc_level_s* u);
+int launch_build_xe(sgc_level_s* l, cudaStream_t s);
+int launch_heat_t2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, const int* d_nbr, const T2Args* remote,
+                   cudaStream_t s);
 int launch_wave_stream(sgc_level_s* unp1, sgc_level_s* un, sgc_level_s* unm1, double f, int fma, cudaStream_t s);
 // multi-rank transport (sgc_comm.cu)
 int comm_plan_setup(sgc_plan_s* plan, sgc_level_s* level, const Grid& g, unsigned periodic, unsigned trim);
@@ -267,7 +271,7 @@ int sgc_profile_enable(int on) {
 
 int sgc_profile_read(int klass, int* launches, double* total_ms) {
   SGC_REQUIRE_RT();
-  if (klass < 0 || klass > 1) return fail(SGC_ERR_ARG, "sgc_profile_read: class must be 0 or 1");
+  if (klass < 0 || klass > 2) return fail(SGC_ERR_ARG, "sgc_profile_read: class must be 0, 1 or 2");
   ProfLog& L = rt().prof[klass];
   double sum = 0;
   for (int i = 0; i < L.used; ++i) {
@@ -361,7 +365,14 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
   l->xg_base = (moff + 63) / 64 * 64;
   l->arena_elems = l->xg_base + xoff;
   for (int b = 0; b < nbox; ++b) l->geom[b].xoff += l->xg_base;
-  const size_t bytes = (size_t)(l->lead + l->arena_elems + 64) * elem_bytes;
+  // edge strips for the two-step sweep (sgc_stream2.cu), behind the arena proper
+  l->xe_base = (l->arena_elems + 63) / 64 * 64;
+  {
+    const FabGeom& g0 = l->geom[0];
+    if (l->uniform && ncomp == 1 && nghost == 1 && elem_bytes == 8 && g0.vn[0] == 64 && g0.vn[1] == 64 && g0.vn[2] >= 4)
+      l->xe_elems = (long long)nbox * g0.vn[2] * 4 * g0.vn[1];
+  }
+  const size_t bytes = (size_t)(l->lead + l->xe_base + l->xe_elems + 64) * elem_bytes;
   cudaError_t e = cudaMalloc(&l->d_base, bytes);
   if (e != cudaSuccess) { delete l; return fail(SGC_ERR_CUDA, std::string("cudaMalloc level arena: ") + cudaGetErrorString(e)); }
   cudaMemsetAsync(l->d_base, 0, bytes, rt().compute);
@@ -845,6 +856,16 @@ int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], 
     if (e == cudaSuccess) e = cudaMemcpy(p->d_push, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess && !st) st = fail(SGC_ERR_CUDA, std::string("push table: ") + cudaGetErrorString(e));
     p->fusable = (st == 0);
+    // two-step sweep: the 8 in-plane neighbours must be local boxes; z neighbours local, or remote
+    // on a z-slab partition (then the plan has remote items and the peer-memory session decides)
+    p->t2_local = p->t2_slab = p->fusable;
+    for (int b = 0; b < l->nbox && p->t2_slab; ++b) {
+      const int* nb = nbr.data() + (size_t)b * 27;
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx)
+          if ((dx || dy) && nb[13 + dx + 3 * dy] < 0) p->t2_local = p->t2_slab = false;
+      if (nb[4] < 0 || nb[22] < 0) p->t2_local = false;
+    }
   }
   if (st) { sgc_plan_destroy(p); return st; }
   *plan = p;
@@ -1106,6 +1127,43 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
     // ONE launch per step.  SGC_P2P=0 keeps the NCCL schedule below.
     const char* pe = getenv("SGC_P2P");
     const bool p2p = plan->nremote > 0 && !(pe && pe[0] == '0') && comm_p2p_setup(plan, a, b) == 0 && plan->p2p.ready;
+
+    // ---- two steps per pass (sgc_stream2.cu): level t is read once and level t+2 written once, the
+    // intermediate level stays on the SM.  It reads VALID cells only (the neighbours' rows, planes and
+    // edge strips), so no ghost cell is touched until the phase ends; an even number of passes keeps
+    // the result in the level the step-by-step schedule would leave it in.
+    const int npass = ((nstep - 2) / 2) & ~1;
+    if (npass >= 2 && heat_t2_covers(b, a) && (plan->t2_local || (plan->t2_slab && p2p))) {
+      sgc_plan_s::P2P& S = plan->p2p;
+      st = launch_build_xe(cur, rt().compute);
+      if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);     // our strips are readable
+      for (int k = 0; k < npass && !st; ++k) {
+        T2Args ra;
+        memset(&ra, 0, sizeof ra);
+        if (p2p) {
+          const int li = (cur == S.lev[0]) ? 0 : 1;
+          ra.rz = S.d_rz;
+          for (int q = 0; q < S.npeer; ++q) {
+            ra.peer_in[q] = (const double*)((char*)S.peer_base[q][li] + cur->lead * cur->esz);
+            ra.peer_flag[q] = (const unsigned long long*)S.peer_flag_base[q];
+          }
+          ra.wait_value = S.counter;
+          ra.err = S.d_err;
+        }
+        {
+          ProfScope prof(2, rt().compute);
+          st = launch_heat_t2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, plan->d_push, p2p ? &ra : nullptr, rt().compute);
+        }
+        if (st > 0) st = fail(SGC_ERR_UNSUPPORTED, "two-step sweep: geometry not covered");
+        if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);
+        std::swap(cur, nxt);
+        s0 += 2;
+      }
+      if (!st && p2p) st = comm_p2p_check(plan);
+      if (st) return st;
+    }
+    // the exchange below also orders the phases on a multi-GPU run: its receives complete only after
+    // the neighbours have left their last pass, so their reads of our levels are over
     st = sgc_exchange(cur, plan);
     if (p2p && !st) {
       sgc_plan_s::P2P& S = plan->p2p;

@@ -85,7 +85,7 @@ void make_items(std::vector<CopyItem>& out, const FabGeom& gd, const IBox& dreg,
 constexpr int kCopyChunk = 2048;       // cells per CTA of the batched copy kernel
 constexpr int kCopyThreads = 256;
 
-// Event-pair log for sgc_profile_* (class 0 = sweep, 1 = exchange copy).
+// Event-pair log for sgc_profile_* (class 0 = sweep, 1 = exchange copy, 2 = two-step sweep).
 struct ProfLog {
   std::vector<cudaEvent_t> a, b;
   int used = 0;
@@ -100,7 +100,7 @@ struct Runtime {
   void* d_stage = nullptr;              // reference-order staging area for upload / download
   size_t stage_bytes = 0;
   bool profiling = false;
-  ProfLog prof[2];
+  ProfLog prof[3];
   bool ready = false;
   int device = -1;
   int sm_count = 0;
@@ -143,6 +143,23 @@ struct PushArgs {
   unsigned int* err;                         // set to 1 when a wait timed out
 };
 
+// Arguments of the two-steps-per-pass sweep (sgc_stream2.cu).
+struct T2Args {
+  const double* in_level;     // arena base of the level at time t
+  double* out_level;          // arena base of the level that receives time t+2
+  long long xe_in, xe_out;    // element offsets of the edge-strip blocks in the two arenas
+  const int* nbr;             // [nbox][27], as PushArgs::nbr
+  int nplanes;                // nbox * (vz + 4) virtual planes
+  int vz;                     // valid planes per box
+  double f;
+  // z neighbours in the neighbouring GPU's memory (z-slab partitions), as PushArgs
+  const int* rz;
+  const double* peer_in[2];
+  const unsigned long long* peer_flag[2];
+  unsigned long long wait_value;
+  unsigned int* err;
+};
+
 // launchers implemented in sgc_kernels.cu
 int launch_copy(const CopyTable& t, void* dst_arena, const void* src_arena, int esz, cudaStream_t s);
 int launch_fill(void* p, long long n, int esz, const void* value, cudaStream_t s);
@@ -163,6 +180,9 @@ struct sgc_level_s {
   long long main_elems = 0;             // elements in the main region (xg region starts here, padded)
   long long xg_base = 0;                // element offset of the xg region in the arena
   long long arena_elems = 0;            // main + xg (+ padding)
+  // edge strips [box][kz][4][vny] (copies of the valid columns 0, 1, vnx-2, vnx-1) read by the two-step
+  // sweep (sgc_stream2.cu); allocated behind the arena for levels that kernel covers, else xe_elems = 0
+  long long xe_base = 0, xe_elems = 0;
   sgc::CopyTable conv_in, conv_out;     // reference-order staging <-> split-x arena, whole level
   sgc::CopyTable conv_valid;            // arena -> [box][comp] valid cells only (plot output), built on first use
   long long valid_elems = 0;
@@ -205,6 +225,9 @@ struct sgc_plan_s {
   // box per (box, direction code), -1 where there is no local motion item
   int* d_push = nullptr;
   bool fusable = false;
+  // two-steps-per-pass sweep (sgc_stream2.cu): every box has its 8 in-plane neighbours locally, and its
+  // two z neighbours locally (t2_local) or at least in the plan (t2_slab: the missing ones are remote)
+  bool t2_local = false, t2_slab = false;
   // peer-memory halo session (sgc_comm.cu): the two ping-pong levels of a step loop, their arenas on
   // the z neighbours mapped through cudaIpc, and progress counters
   struct P2P {

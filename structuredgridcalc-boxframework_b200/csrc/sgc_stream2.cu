@@ -1,0 +1,345 @@
+// sgc_stream2.cu — TWO heat / Jacobi steps per pass over the level (temporal blocking of the
+// streaming sweep of sgc_stream.cu), used inside sgc_heat_run.
+//
+// The one-step sweep is HBM-bound at ~86 % of the measured copy bandwidth, so the only way to go
+// faster is to move fewer bytes per cell-update.  This kernel reads level t once and writes level
+// t+2 once: the intermediate level t+1 never leaves the SM.  It is bit-identical to two
+// { exchange ; sweep } steps of the reference (LevelData.H:455-566 + the application's sweep loop)
+// on the valid cells, because every t+1 value it needs — including the ones that belong to the
+// neighbouring boxes — is recomputed with the same operations in the same order from the same
+// inputs.
+//
+// Per box the CTA marches along z through VZ+4 "virtual planes" z = -2 .. VZ+1.  For every virtual
+// plane the producer assembles a TILE of level t in a ring slot — entirely from VALID cells (ghost
+// cells are never read, so no exchange is needed between the two steps or between passes):
+//     rows y = -2..V+1 of the V valid columns      (own valid rows + 2 rows of each y neighbour)
+//     x strips x = -2,-1,V,V+1 for y = 0..V-1      (the x neighbours' EDGE STRIPS, see below)
+//     the 4 corner cells (-1|V, -1|V)              (the xy-diagonal neighbours; plain loads)
+//   planes z < 0 / z >= VZ are the same tile of the z neighbour (a local fab or, on a z-slab
+//   partition, a fab in the neighbouring GPU's memory over NVLink, gated by its progress counter).
+// Consumers (NCW warps, thread = one x and CPT consecutive rows, all state in registers):
+//   stage 1: t+1 on plane z-1 for the V x V cells; the extra "halo warp" computes t+1 on the four
+//            1-cell-wide flanks (x = -1, V and y = -1, V) — the values the x / y neighbours would
+//            have exchanged.  Results go to registers (z neighbours of stage 2) and to one of two
+//            t+1 plane buffers in shared memory (x / y neighbours of stage 2).
+//   stage 2: t+2 on plane z-2 from the t+1 planes z-3, z-2, z-1; stored as dense rows.
+//   One named barrier per plane orders the t+1 buffer hand-over between the warps.
+// EDGE STRIPS (xe): a per-level side array [box][kz][4][V] holding copies of the box's own columns
+// x = 0, 1, V-2, V-1, written by stage 2 straight from the result registers (and built once per
+// sgc_heat_run by k_build_xe).  Reading a neighbour's edge column out of its main block would
+// fetch one 32-byte sector per 8-byte value; the strips make the x halo dense.
+//
+// HBM traffic per plane pass (V = 64): 36.9 KB tile + 32 KB rows + 2 KB strips for TWO cell-updates
+// of 4096 cells = 8.7 B per cell-update (x (VZ+4)/VZ for the z overlap) against 16.8 B for the
+// one-step sweep; the algorithmic figure stays 16 B per cell-update.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+#include "sgc_device.h"
+#include "sgc_pipe.cuh"
+
+namespace sgc {
+
+template <bool FMA>
+__device__ __forceinline__ double heat_update(double c, double xm, double xp, double ym, double yp, double zm, double zp,
+                                              double f) {
+  // association of the reference loop: ((u[+e] - 2u) + u[-e]) per direction, x -> y -> z, then u + f*S
+  const double twoc = __dmul_rn(2.0, c);
+  const double tx = sd2(xp, twoc, xm);
+  const double ty = sd2(yp, twoc, ym);
+  const double tz = sd2(zp, twoc, zm);
+  const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
+  return FMA ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+}
+
+template <int V, int NS, int NCW, bool FMA>
+__global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
+  constexpr int NT = NCW * 32;                  // threads: every warp is a consumer
+  constexpr int N1 = V + 2;                     // fab rows (one ghost layer)
+  constexpr int FABP = V * N1;                  // elements of one fab plane in the main block
+  constexpr int NR = (V + 4) * V;               // tile rows y = -2..V+1
+  constexpr int ESTR = V + 4;                   // allocation of one x strip in the tile
+  constexpr int SLOT = NR + 4 * ESTR;           // ring slot, elements
+  // t+1 plane buffer: the tile layout shifted down by one row (rows y = -1..V, the x = -1 strip at
+  // E(1) - V, the x = V strip at E(2) - V), so that "buffer - V" is addressed with TILE offsets
+  constexpr int T1SZ = (NR + 2 * ESTR + 2 + V + 15) / 16 * 16;
+  constexpr int G = NT / V;                     // thread groups along y
+  constexpr int CPT = V / G;                    // consecutive rows per thread
+  constexpr uint32_t TILE_BYTES = (uint32_t)(V * V + 4 * V + 4 * V) * 8u;   // rows + 2x2 y rows + 4 strips
+  static_assert(NT % V == 0 && V % G == 0, "thread mapping");
+  static_assert(4 * V == NT / 2, "the upper half of the warps owns one flank cell per thread");
+  constexpr int NROLE = 6;                      // warps that bring in a piece of each tile (one arrival each)
+  static_assert((NS & (NS - 1)) == 0 && NS >= 4, "ring: two tiles being read, two in flight");
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  double* t1 = ring + (size_t)NS * SLOT;
+  uint64_t* full = reinterpret_cast<uint64_t*>(t1 + 2 * T1SZ);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int vz = a.vz, VP = vz + 4;
+  const long long fabm = (long long)FABP * (vz + 2);
+  const int s_begin = (int)((long long)blockIdx.x * a.nplanes / gridDim.x);
+  const int s_end = (int)((long long)(blockIdx.x + 1) * a.nplanes / gridDim.x);
+  if (s_begin >= s_end) return;
+  const int l_begin = s_begin >= 4 ? s_begin - 4 : 0;     // 4 tiles prime the two stages
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) mbar_init(full + i, NROLE);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto E = [](int s) { return NR + s * ESTR + 2; };       // tile offset of strip s at y = 0
+
+  // ---------------- producer roles (warps 0-5, one piece of the tile each) ----------------
+  // Tile t goes to ring slot (t - l_begin) % NS.  The address arithmetic of a tile is spread over six
+  // warps so that no warp lags at the per-plane barrier: lane 0 of warp r issues
+  //   r = 0: the V own rows (+ announces the tile's bytes)   r = 1 / 2: the two rows of the -y / +y neighbour
+  //   r = 3 / 4: the two edge strips of the -x / +x neighbour
+  // and lanes 0-3 of warp 5 fetch the four corner cells with plain loads.  issue() starts the copies /
+  // loads of the tile two iterations ahead; finish(), an iteration's worth of computing later, stores
+  // the corner values and makes warp 5's arrival (the slot completes on six arrivals + the bytes).
+  int S = -1, N = 0;                  // source box of the current tiles; this role's neighbour of S
+  const double* base = a.in_level;
+  unsigned waited = 0;                // bit per peer slot
+  double cv = 0.0;
+  auto issue = [&](int slot, int tbox, int tl) {          // tile = virtual plane tl of box tbox
+    const int z = tl - 2;
+    const int cls = z < 0 ? 0 : (z >= vz ? 2 : 1);
+    if (S < 0 || tl == 0 || tl == 2 || tl == vz + 2) {    // first tile, or the source box changes here
+      base = a.in_level;
+      if (cls == 1) S = tbox;
+      else {
+        S = __ldg(a.nbr + (size_t)tbox * 27 + (cls == 0 ? 4 : 22));
+        if (S < 0) {                           // z neighbour lives on another GPU (checked on the host)
+          const int rr = __ldg(a.rz + 2 * tbox + (cls == 0 ? 0 : 1));
+          const int ps = rr >> 28;
+          S = rr & 0x0fffffff;
+          base = ps ? a.peer_in[1] : a.peer_in[0];
+          if (!(waited >> ps & 1u)) {          // the peer must have finished writing the level we read
+            if (lane == 0) {
+              const volatile unsigned long long* fl = ps ? a.peer_flag[1] : a.peer_flag[0];
+              long long spins = 0;
+              while (*fl < a.wait_value) {
+                if (++spins > (1LL << 20)) { *a.err = 1u; break; }    // ~3 s: report, never hang
+                __nanosleep(64);
+              }
+            }
+            __syncwarp();
+            __threadfence_system();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            waited |= 1u << ps;
+          }
+        }
+      }
+      // this role's in-plane neighbour of S (on a z-slab partition the peer's local indices equal ours)
+      int code = 13;
+      if (warp == 1) code = 10; else if (warp == 2) code = 16; else if (warp == 3) code = 12; else if (warp == 4) code = 14;
+      else if (warp == 5) code = 13 + ((lane & 1) ? 1 : -1) + ((lane & 2) ? 3 : -3);   // corner (dx,dy) by lane bits
+      N = warp == 0 ? S : __ldg(a.nbr + (size_t)S * 27 + code);
+    }
+    const int kz = cls == 0 ? z + vz : (cls == 2 ? z - vz : z);
+    const long long prow = ((long long)(kz + 1) * N1 + 1) * V;      // first valid row of fab plane kz
+    double* dst = ring + (size_t)slot * SLOT;
+    if (warp == 5) {
+      if (lane < 4) cv = *(base + N * fabm + prow + (long long)((lane & 2) ? 0 : V - 1) * V + ((lane & 1) ? 0 : V - 1));
+    } else if (lane == 0) {
+      if (warp == 0) {
+        mbar_expect_tx(full + slot, TILE_BYTES);                  // this warp's arrival + the tile's byte count
+        bulk_g2s(dst + 2 * V, base + N * fabm + prow, V * V * 8u, full + slot);                           // rows 0..V-1
+      } else if (warp == 1) {
+        bulk_g2s(dst, base + N * fabm + prow + (long long)(V - 2) * V, 2 * V * 8u, full + slot);           // rows -2,-1
+      } else if (warp == 2) {
+        bulk_g2s(dst + (V + 2) * V, base + N * fabm + prow, 2 * V * 8u, full + slot);                      // rows V,V+1
+      } else {
+        const double* e = base + a.xe_in + ((long long)N * vz + kz) * (4 * V);
+        if (warp == 3) {
+          bulk_g2s(dst + E(0), e + 2 * V, V * 8u, full + slot);     // x = -2  <- x neighbour's column V-2
+          bulk_g2s(dst + E(1), e + 3 * V, V * 8u, full + slot);     // x = -1  <- column V-1
+        } else {
+          bulk_g2s(dst + E(2), e, V * 8u, full + slot);             // x = V   <- column 0
+          bulk_g2s(dst + E(3), e + V, V * 8u, full + slot);         // x = V+1 <- column 1
+        }
+      }
+      if (warp != 0) mbar_arrive(full + slot);
+    }
+  };
+  auto finish = [&](int slot) {                           // warp 5 only
+    if (lane < 4) ring[(size_t)slot * SLOT + E((lane & 1) ? 2 : 1) + ((lane & 2) ? V : -1)] = cv;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full + slot);
+  };
+  if (warp < NROLE) {
+    const int b0 = l_begin / VP, l0 = l_begin - b0 * VP;
+    issue(0, b0, l0);
+    if (warp == 5) finish(0);
+    if (l_begin + 1 < s_end) {
+      issue(1, l0 + 1 == VP ? b0 + 1 : b0, l0 + 1 == VP ? 0 : l0 + 1);
+      if (warp == 5) finish(1);
+    }
+  }
+
+  // ---------------- flank role (upper half of the warps): one cell of the x / y flanks per thread ----------------
+  // warp-uniform m = 0..3: x flanks (side m>>1, y = (m&1)*32 + lane); m = 4..7: y flanks (side, x likewise)
+  const bool flank = warp >= NCW / 2;
+  double hcc = 0.0, hzm = 0.0;
+
+  // ---------------- regular role (every thread): x = xi, rows y0 .. y0+CPT-1 ----------------
+  const int xi = tid % V, y0 = (tid / V) * CPT;
+  const bool at_lo = (xi == 0), at_hi = (xi == V - 1);
+  const int oC0 = (y0 + 2) * V + xi;                              // tile offset of (xi, y0)
+  // x neighbours: the plane, or the x = -1 / x = V strip for the first / last column (strips advance
+  // by 1 per row, planes by V); one integer multiply-add per access, no divergent branch
+  const int oxm0 = at_lo ? E(1) + y0 : oC0 - 1, sxm = at_lo ? 1 : V;
+  const int oxp0 = at_hi ? E(2) + y0 : oC0 + 1, sxp = at_hi ? 1 : V;
+  double cc[CPT], zm[CPT], c1[CPT], zm1[CPT];
+#pragma unroll
+  for (int m = 0; m < CPT; ++m) cc[m] = zm[m] = c1[m] = zm1[m] = 0.0;
+  const double f = a.f;
+  int box = l_begin / VP, l = l_begin - box * VP;
+
+  const int n_iter = s_end - l_begin, lead = s_begin - l_begin, par0 = l_begin & 1;
+  for (int i = 0; i < n_iter; ++i) {
+    const int slot = i & (NS - 1);
+    mbar_wait(full + slot, (i / NS) & 1u);
+    __syncthreads();                 // t+1 buffer hand-over; every warp has left tile i-2 and t+1 plane i-3
+    const bool more = i + 2 < n_iter;
+    if (warp < NROLE && more) issue((i + 2) & (NS - 1), l + 2 >= VP ? box + 1 : box, l + 2 >= VP ? l + 2 - VP : l + 2);
+    const double* __restrict__ C = ring + (size_t)slot * SLOT;
+    const double* __restrict__ P = ring + (size_t)((i + NS - 1) & (NS - 1)) * SLOT;
+    const bool do1 = (l >= 2) && (i >= 2);
+    const bool do2 = (l >= 4) && (i >= lead);
+    // t+1 plane buffers, addressed with tile offsets
+    const int par = (i + par0) & 1;                               // parity of the virtual plane v = l_begin + i
+    double* __restrict__ Tw = t1 + (par ^ 1) * T1SZ - V;          // virtual plane v-1 (written now)
+    const double* __restrict__ Tr = t1 + par * T1SZ - V;          // virtual plane v-2 (written last iteration)
+    if (flank) {
+      // tile offsets of the flank cell and its four in-plane neighbours (a handful of integer
+      // instructions per plane; keeping them in registers would cost more than recomputing)
+      const int m = warp - NCW / 2, p = (m & 1) * 32 + lane;
+      int hc, hxm, hxp, hym, hyp;
+      if (m < 2)      { hc = E(1) + p; hxm = E(0) + p; hxp = (p + 2) * V; hym = hc - 1; hyp = hc + 1; }             // x = -1
+      else if (m < 4) { hc = E(2) + p; hxm = (p + 2) * V + V - 1; hxp = E(3) + p; hym = hc - 1; hyp = hc + 1; }     // x = V
+      else if (m < 6) { hc = V + p; hym = p; hyp = 2 * V + p;                                                       // y = -1
+                        hxm = p > 0 ? hc - 1 : E(1) - 1; hxp = p < V - 1 ? hc + 1 : E(2) - 1; }
+      else            { hc = (V + 2) * V + p; hym = (V + 1) * V + p; hyp = (V + 3) * V + p;                         // y = V
+                        hxm = p > 0 ? hc - 1 : E(1) + V; hxp = p < V - 1 ? hc + 1 : E(2) + V; }
+      const double zp = C[hc];
+      if (do1) Tw[hc] = heat_update<FMA>(hcc, P[hxm], P[hxp], P[hym], P[hyp], hzm, zp, f);
+      hzm = hcc; hcc = zp;
+    }
+    if (!do1) {
+#pragma unroll
+      for (int m = 0; m < CPT; ++m) { zm[m] = cc[m]; cc[m] = C[oC0 + m * V]; }
+    } else {
+      const int kz = l - 4;                                       // output plane inside the fab's valid region
+      // (xi, y0) of fab plane kz: fab-relative offset = tile offset + (N1 - 1) * V
+      double* __restrict__ po = a.out_level + box * fabm + (long long)kz * FABP + (oC0 + (N1 - 1) * V);
+      const int xq = oC0 & (V - 1);                               // = xi; edge-strip index of this column, if any
+      const int xs = xq == 0 ? 0 : (xq == 1 ? 1 : (xq == V - 2 ? 2 : (xq == V - 1 ? 3 : -1)));
+      double* __restrict__ pe = a.out_level + a.xe_out + (((long long)box * vz + kz) * 4 + (xs < 0 ? 0 : xs)) * V + (oC0 / V - 2);
+      double ym = P[oC0 - V];
+      const double ylast = P[oC0 + CPT * V];
+      double ym1 = Tr[oC0 - V];
+      const double ylast1 = Tr[oC0 + CPT * V];
+#pragma unroll
+      for (int m = 0; m < CPT; ++m) {
+        const double zp = C[oC0 + m * V];
+        const double c = cc[m];
+        const double yp = (m < CPT - 1) ? cc[m + 1] : ylast;
+        const double r1 = heat_update<FMA>(c, P[oxm0 + m * sxm], P[oxp0 + m * sxp], ym, yp, zm[m], zp, f);
+        ym = c; zm[m] = c; cc[m] = zp;
+        Tw[oC0 + m * V] = r1;
+        // stage 2 (its result is stored only when the plane is owned and complete: do2)
+        const double d = c1[m];
+        const double yp1 = (m < CPT - 1) ? c1[m + 1] : ylast1;
+        const double o = heat_update<FMA>(d, Tr[oxm0 + m * sxm], Tr[oxp0 + m * sxp], ym1, yp1, zm1[m], r1, f);
+        ym1 = d; zm1[m] = d; c1[m] = r1;
+        if (do2) {
+          po[m * V] = o;
+          if (xs >= 0) pe[m] = o;
+        }
+      }
+    }
+    if (warp == 5 && more) finish((i + 2) & (NS - 1));
+    if (++l == VP) { l = 0; ++box; }
+  }
+}
+
+// edge strips of a level from its main blocks: xe[box][kz][s][y], s = columns 0, 1, V-2, V-1
+__global__ void k_build_xe(const double* __restrict__ level, double* __restrict__ xe, int nbox, int vx, int vy, int vz) {
+  const long long n = (long long)nbox * vz * 4 * vy;
+  const int n1 = vy + 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i % vy);
+    const int s = (int)((i / vy) % 4);
+    const int kz = (int)((i / (4 * vy)) % vz);
+    const long long b = i / ((long long)4 * vy * vz);
+    const int x = s == 0 ? 0 : (s == 1 ? 1 : (s == 2 ? vx - 2 : vx - 1));
+    xe[i] = level[b * ((long long)vx * n1 * (vz + 2)) + ((long long)(kz + 1) * n1 + (y + 1)) * vx + x];
+  }
+}
+
+template <int V, int NS, int NCW>
+static int launch_t2_cfg(const T2Args& a, int fma, cudaStream_t s) {
+  constexpr size_t smem = ((size_t)NS * ((V + 4) * V + 4 * (V + 4)) + 2 * (((V + 4) * V + 2 * (V + 4) + 2 + V + 15) / 16 * 16)) * 8 + NS * 8;
+  static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
+  static bool configured = false;
+  if (!configured) {
+    SGC_CUDA(cudaFuncSetAttribute(k_heat_t2<V, NS, NCW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGC_CUDA(cudaFuncSetAttribute(k_heat_t2<V, NS, NCW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int grid = rt().sm_count;
+  if (grid > a.nplanes / 8) grid = a.nplanes / 8 > 0 ? a.nplanes / 8 : 1;
+  if (fma) k_heat_t2<V, NS, NCW, true><<<grid, NCW * 32, smem, s>>>(a);
+  else k_heat_t2<V, NS, NCW, false><<<grid, NCW * 32, smem, s>>>(a);
+  rt().launches++;
+  SGC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// does the two-step kernel have an instance for this pair of levels?
+bool heat_t2_covers(const sgc_level_s* unew, const sgc_level_s* u) {
+  if (!u->uniform || !unew->uniform || u->ncomp != 1 || unew->ncomp != 1 || u->ng != 1 || unew->ng != 1) return false;
+  if (u->esz != 8 || unew->esz != 8 || !u->xe_elems || !unew->xe_elems || getenv("SGC_NO_T2")) return false;
+  const FabGeom& g = u->geom[0];
+  if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0 || u->nbox != unew->nbox) return false;
+  return g.vn[0] == 64 && g.vn[1] == 64 && g.vn[2] >= 4;
+}
+
+int launch_build_xe(sgc_level_s* l, cudaStream_t s) {
+  const FabGeom& g = l->geom[0];
+  const long long n = (long long)l->nbox * g.vn[2] * 4 * g.vn[1];
+  const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  k_build_xe<<<grid, 256, 0, s>>>((const double*)l->d_arena, (double*)l->d_arena + l->xe_base, l->nbox, g.vn[0], g.vn[1],
+                                  g.vn[2]);
+  rt().launches++;
+  SGC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// unew(t+2) <- u(t): two steps over all boxes in one launch.  `remote` carries the peer-memory fields.
+int launch_heat_t2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, const int* d_nbr, const T2Args* remote,
+                   cudaStream_t s) {
+  const FabGeom& g = u->geom[0];
+  T2Args a;
+  memset(&a, 0, sizeof a);
+  if (remote) a = *remote;
+  a.in_level = (const double*)u->d_arena;
+  a.out_level = (double*)unew->d_arena;
+  a.xe_in = u->xe_base;
+  a.xe_out = unew->xe_base;
+  a.nbr = d_nbr;
+  a.vz = g.vn[2];
+  const long long np = (long long)u->nbox * (g.vn[2] + 4);
+  if (np > 0x7fffffffLL) return 1;
+  a.nplanes = (int)np;
+  a.f = f;
+  return launch_t2_cfg<64, 4, 16>(a, fma, s);
+}
+
+}  // namespace sgc
