@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   // ---------------- flank role (upper half of the warps): one cell of the x / y flanks per thread ----------------
   // warp-uniform m = 0..3: x flanks (side m>>1, y = (m&1)*32 + lane); m = 4..7: y flanks (side, x likewise)
   const bool flank = warp >= NCW / 2;
-  double hcc = 0.0, hzm = 0.0;
+  double hA = 0.0, hB = 0.0;          // the flank cell at the two latest planes of level t (roles alternate)
 
   // ---------------- regular role (every thread): x = xi, rows y0 .. y0+CPT-1 ----------------
   const int xi = tid % V, y0 = (tid / V) * CPT;
@@ -195,14 +195,20 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   // by 1 per row, planes by V); one integer multiply-add per access, no divergent branch
   const int oxm0 = at_lo ? E(1) + y0 : oC0 - 1, sxm = at_lo ? 1 : V;
   const int oxp0 = at_hi ? E(2) + y0 : oC0 + 1, sxp = at_hi ? 1 : V;
-  double cc[CPT], zm[CPT], c1[CPT], zm1[CPT];
+  // Column state, all in registers: level t at the two latest planes (tA / tB) and level t+1 at the two
+  // latest planes (uA / uB).  The roles "newest / previous" alternate from plane to plane — the loop
+  // below is unrolled by two so that no value is ever moved between registers.
+  double tA[CPT], tB[CPT], uA[CPT], uB[CPT];
 #pragma unroll
-  for (int m = 0; m < CPT; ++m) cc[m] = zm[m] = c1[m] = zm1[m] = 0.0;
+  for (int m = 0; m < CPT; ++m) tA[m] = tB[m] = uA[m] = uB[m] = 0.0;
   const double f = a.f;
   int box = l_begin / VP, l = l_begin - box * VP;
-
   const int n_iter = s_end - l_begin, lead = s_begin - l_begin, par0 = l_begin & 1;
-  for (int i = 0; i < n_iter; ++i) {
+
+  // One plane: tile i arrives as the z+1 plane of stage 1.  X = level t at the previous plane (centre of
+  // stage 1), Y = the plane before (overwritten with the arriving plane); U = level t+1 at the previous
+  // plane (centre of stage 2), W = the plane before (overwritten with the stage-1 result).
+  auto plane = [&](int i, double (&X)[CPT], double (&Y)[CPT], double (&U)[CPT], double (&W)[CPT], double& hX, double& hY) {
     const int slot = i & (NS - 1);
     mbar_wait(full + slot, (i / NS) & 1u);
     __syncthreads();                 // t+1 buffer hand-over; every warp has left tile i-2 and t+1 plane i-3
@@ -228,12 +234,12 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       else            { hc = (V + 2) * V + p; hym = (V + 1) * V + p; hyp = (V + 3) * V + p;                         // y = V
                         hxm = p > 0 ? hc - 1 : E(1) + V; hxp = p < V - 1 ? hc + 1 : E(2) + V; }
       const double zp = C[hc];
-      if (do1) Tw[hc] = heat_update<FMA>(hcc, P[hxm], P[hxp], P[hym], P[hyp], hzm, zp, f);
-      hzm = hcc; hcc = zp;
+      if (do1) Tw[hc] = heat_update<FMA>(hX, P[hxm], P[hxp], P[hym], P[hyp], hY, zp, f);
+      hY = zp;
     }
     if (!do1) {
 #pragma unroll
-      for (int m = 0; m < CPT; ++m) { zm[m] = cc[m]; cc[m] = C[oC0 + m * V]; }
+      for (int m = 0; m < CPT; ++m) Y[m] = C[oC0 + m * V];
     } else {
       const int kz = l - 4;                                       // output plane inside the fab's valid region
       // (xi, y0) of fab plane kz: fab-relative offset = tile offset + (N1 - 1) * V
@@ -241,23 +247,19 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       const int xq = oC0 & (V - 1);                               // = xi; edge-strip index of this column, if any
       const int xs = xq == 0 ? 0 : (xq == 1 ? 1 : (xq == V - 2 ? 2 : (xq == V - 1 ? 3 : -1)));
       double* __restrict__ pe = a.out_level + a.xe_out + (((long long)box * vz + kz) * 4 + (xs < 0 ? 0 : xs)) * V + (oC0 / V - 2);
-      double ym = P[oC0 - V];
-      const double ylast = P[oC0 + CPT * V];
-      double ym1 = Tr[oC0 - V];
-      const double ylast1 = Tr[oC0 + CPT * V];
+      const double yfirst = P[oC0 - V], ylast = P[oC0 + CPT * V];
+      const double yfirst1 = Tr[oC0 - V], ylast1 = Tr[oC0 + CPT * V];
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
         const double zp = C[oC0 + m * V];
-        const double c = cc[m];
-        const double yp = (m < CPT - 1) ? cc[m + 1] : ylast;
-        const double r1 = heat_update<FMA>(c, P[oxm0 + m * sxm], P[oxp0 + m * sxp], ym, yp, zm[m], zp, f);
-        ym = c; zm[m] = c; cc[m] = zp;
+        const double r1 = heat_update<FMA>(X[m], P[oxm0 + m * sxm], P[oxp0 + m * sxp], m > 0 ? X[m - 1] : yfirst,
+                                           m < CPT - 1 ? X[m + 1] : ylast, Y[m], zp, f);
+        Y[m] = zp;
         Tw[oC0 + m * V] = r1;
         // stage 2 (its result is stored only when the plane is owned and complete: do2)
-        const double d = c1[m];
-        const double yp1 = (m < CPT - 1) ? c1[m + 1] : ylast1;
-        const double o = heat_update<FMA>(d, Tr[oxm0 + m * sxm], Tr[oxp0 + m * sxp], ym1, yp1, zm1[m], r1, f);
-        ym1 = d; zm1[m] = d; c1[m] = r1;
+        const double o = heat_update<FMA>(U[m], Tr[oxm0 + m * sxm], Tr[oxp0 + m * sxp], m > 0 ? U[m - 1] : yfirst1,
+                                          m < CPT - 1 ? U[m + 1] : ylast1, W[m], r1, f);
+        W[m] = r1;
         if (do2) {
           po[m * V] = o;
           if (xs >= 0) pe[m] = o;
@@ -266,6 +268,10 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
     }
     if (warp == 5 && more) finish((i + 2) & (NS - 1));
     if (++l == VP) { l = 0; ++box; }
+  };
+  for (int i = 0; i < n_iter; i += 2) {
+    plane(i, tA, tB, uA, uB, hA, hB);
+    if (i + 1 < n_iter) plane(i + 1, tB, tA, uB, uA, hB, hA);
   }
 }
 
