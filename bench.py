@@ -291,7 +291,7 @@ def main():
         sampler.start()
         time.sleep(0.25)
     sgc.profile_enable(True)
-    sgc.profile_read(0), sgc.profile_read(1)
+    sgc.profile_read(0), sgc.profile_read(1), sgc.profile_read(2)
     launches0 = sgc.launch_count()
     e0, e1 = sgc.Event(), sgc.Event()
     barrier()
@@ -306,6 +306,7 @@ def main():
     launches = sgc.launch_count() - launches0
     sweep_n, sweep_ms = sgc.profile_read(0)
     exch_n, exch_ms = sgc.profile_read(1)
+    t2_n, t2_ms = sgc.profile_read(2)
     sgc.profile_enable(False)
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
 
@@ -337,18 +338,40 @@ def main():
         mask_sum, ref_sum = float(t[0]), float(t[1])
     conserved = abs(mask_sum - ref_sum) <= 1e-9 * abs(ref_sum)
 
-    # roofline of the dominant kernel (the sweep): algorithmic bytes per launch / mean launch time
+    # roofline of the dominant kernel: algorithmic bytes per launch / mean launch time.  Inside
+    # sgc_heat_run the dominant kernel is the two-step sweep (k_heat_t2, profile class 2: ONE launch =
+    # TWO cell-updates per cell = 2 x 16 algorithmic bytes per cell) whenever the level is covered by it;
+    # the remaining steps, and levels it does not cover, use the one-step sweep (class 0).  A fraction
+    # above 1 means the kernel moves fewer DRAM bytes than the algorithmic figure (`traffic` shows it).
     peak, peak_src = measured_hbm_peak()
-    # with N > 1 a step issues 2-3 sweep launches (interior + boundary ranges): use bytes per sweep
     sweeps_done = a.steps * a.sweeps
-    sweep_ms_per_sweep = sweep_ms / max(sweeps_done, 1)
-    achieved = cells_local * ALGO_BYTES_PER_CELL / (sweep_ms_per_sweep * 1e-3) / 1e9 if sweep_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "heat sweep (class 0)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": load_traffic(),
-                "algorithmic_bytes_per_launch": cells_local * ALGO_BYTES_PER_CELL,
-                "avg_launch_ms": sweep_ms / max(sweep_n, 1), "launches_timed": sweep_n,
+    sweep_ms_per_sweep = (sweep_ms + t2_ms) / max(sweeps_done, 1)
+    one_step = {"launches_timed": sweep_n, "avg_launch_ms": sweep_ms / max(sweep_n, 1),
+                "achieved_GBs": (cells_local * ALGO_BYTES_PER_CELL * (sweeps_done - 2 * t2_n) / (sweep_ms * 1e-3) / 1e9
+                                 if sweep_ms > 0 else 0.0),
+                "traffic": load_traffic("sweep_dram_bytes_per_launch")}
+    if t2_n > 0:
+        kernel, n_l, ms_l, upd = "two-step heat sweep k_heat_t2 (class 2)", t2_n, t2_ms, 2
+        traffic = load_traffic("t2_dram_bytes_per_launch")
+    else:
+        kernel, n_l, ms_l, upd = "heat sweep k_heat_stream (class 0)", sweep_n, sweep_ms, 1
+        traffic = one_step["traffic"]
+    # with N > 1 and the NCCL schedule a step issues 2-3 one-step launches (interior + boundary ranges):
+    # there use bytes per sweep rather than per launch
+    if t2_n == 0 and sweep_n != sweeps_done:
+        avg_ms = sweep_ms / max(sweeps_done, 1)
+    else:
+        avg_ms = ms_l / max(n_l, 1)
+    bytes_per_launch = cells_local * ALGO_BYTES_PER_CELL * upd
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "cell_updates_per_cell_per_launch": upd,
+                "avg_launch_ms": avg_ms, "launches_timed": n_l,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
-                "sweep_only_gcells": cells_local / (sweep_ms_per_sweep * 1e-3) / 1e9 if sweep_ms > 0 else 0.0,
+                "dram_frac_of_peak": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic and avg_ms > 0 else None,
+                "one_step_kernel": one_step,
+                "sweep_only_gcells": cells_local / (sweep_ms_per_sweep * 1e-3) / 1e9 if sweep_ms_per_sweep > 0 else 0.0,
                 "exchange_ms_per_sweep": exch_ms / max(sweeps_done, 1), "sweep_ms_per_sweep": sweep_ms_per_sweep,
                 "exchange_bytes_per_sweep": 16.0 * cp.numCells()}
 
@@ -471,12 +494,12 @@ def main():
         dist.destroy_process_group()
 
 
-def load_traffic():
-    """dram bytes per sweep launch from the last committed ncu --set full capture (profiles/)."""
+def load_traffic(key="sweep_dram_bytes_per_launch"):
+    """dram bytes per launch of a kernel from the last committed ncu --set full capture (profiles/)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get("sweep_dram_bytes_per_launch")
+            return json.load(f).get(key)
     except Exception:
         return None
 

@@ -859,12 +859,17 @@ int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], 
     // two-step sweep: the 8 in-plane neighbours must be local boxes; z neighbours local, or remote
     // on a z-slab partition (then the plan has remote items and the peer-memory session decides)
     p->t2_local = p->t2_slab = p->fusable;
+    std::vector<char> zcover((size_t)l->nbox * 2, 0);   // box has a -z / +z face item, local or remote
+    for (const sgc_motion_item& it : p->items)
+      if (it.dir[0] == 0 && it.dir[1] == 0 && it.dir[2] != 0)
+        zcover[(size_t)(it.recv_box - l->gidx0) * 2 + (it.dir[2] < 0 ? 0 : 1)] = 1;
     for (int b = 0; b < l->nbox && p->t2_slab; ++b) {
       const int* nb = nbr.data() + (size_t)b * 27;
       for (int dy = -1; dy <= 1; ++dy)
         for (int dx = -1; dx <= 1; ++dx)
           if ((dx || dy) && nb[13 + dx + 3 * dy] < 0) p->t2_local = p->t2_slab = false;
       if (nb[4] < 0 || nb[22] < 0) p->t2_local = false;
+      if (!zcover[(size_t)b * 2] || !zcover[(size_t)b * 2 + 1]) p->t2_slab = false;
     }
   }
   if (st) { sgc_plan_destroy(p); return st; }

@@ -89,6 +89,7 @@ def run_gpu(rank, world, local_rank):
     sgc.comm_init(world, rank, ids[0])
     for dlo, dhi, mb, per, f, nstep in (((0, 0, 0), (31, 31, 32 * world - 1), (16, 16, 16), 7, 0.125, 12),
                                         ((0, 0, 0), (63, 63, 64 * world - 1), (64, 64, 64), 7, 1.0 / 6.0, 6),
+                                        ((0, 0, 0), (127, 63, 128 * world - 1), (64, 64, 64), 7, 0.2, 11),
                                         ((0, 0, 0), (63, 31, 64 * world - 1), (32, 32, 32), 3, 0.125, 9),
                                         ((0, 0, 0), (15, 15, 8 * world - 1), (8, 8, 8), 0, 0.125, 5),
                                         ((0, 0, 0), (11, 7, 10 * world - 1), (6, 4, 5), 3, 0.2, 4)):
@@ -111,9 +112,16 @@ def run_gpu(rank, world, local_rank):
         O.level_exchange(allboxes, 1, 1, O.copier_items(dlo, dhi, mb, 1, per, 0), w1)
         assert np.array_equal(a.download(), w1[goff[b0]:end]), ("exchange", rank, mb)
         a.upload(mine)
+        sgc.profile_enable(True)
+        sgc.profile_read(2)
         res = sgc.heat_run(a, b, cp, f, nstep)
+        n2, _ = sgc.profile_read(2)
+        sgc.profile_enable(False)
         got = res.download()
         assert np.array_equal(got, want[goff[b0]:end]), ("heat_run", rank, mb)
+        if mb == (64, 64, 64) and per == 7 and os.environ.get("SGC_P2P", "1") != "0" and not os.environ.get("SGC_NO_T2"):
+            # the two-step passes pull their z tiles out of the neighbouring GPU's memory
+            assert n2 == ((nstep - 2) // 2) & ~1, ("two-step passes", n2, nstep)
         if world > 1:
             assert cp.numRemoteItem() > 0
     sgc.sync()

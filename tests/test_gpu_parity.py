@@ -337,6 +337,73 @@ def test_heat_random_vs_oracle_both_fma_modes(g, oracle):
                 assert np.array_equal(res.download(), want), (dlo, dhi, mb, f, contract)
 
 
+def test_two_step_sweep_matches_oracle_and_step_by_step(g, oracle, monkeypatch):
+    """sgc_heat_run's two-steps-per-pass kernel (sgc_stream2.cu, 64x64 boxes with all in-plane and z
+    neighbours): level t is read once and level t+2 written once.  Valid AND ghost cells of BOTH levels
+    must equal the oracle's nstep x {exchange; sweep} (LevelData.H:455-566 + the sweep loop) and the
+    library's own step-by-step schedule, bit for bit, in both FMA modes; odd and even step counts,
+    several boxes per direction, flat boxes (vz = 8)."""
+    rng = np.random.default_rng(21)
+    cases = [((0, 0, 0), (63, 63, 63), (64, 64, 64), 0.125, 10, 1),       # one box, periodic onto itself
+             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 0.31, 7, 1),
+             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 1.0 / 6.0, 12, 0),
+             ((0, 0, 0), (191, 63, 127), (64, 64, 64), 0.2, 9, 1),
+             ((-64, 0, 8), (-1, 127, 23), (64, 64, 8), 0.2, 11, 0)]
+    for (dlo, dhi, mb, f, nstep, contract) in cases:
+        dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
+        b = g.LevelData(dbl, 1, 1)
+        u0 = rng.standard_normal(a.elems)
+        v0 = rng.standard_normal(a.elems)          # the second level starts with different ghosts
+        cp = g.Copier().defineExchangeLD(a, 7, 0)
+        flags = g.SGC_FMA if contract else 0
+        outs = []
+        for no_t2 in (False, True):
+            if no_t2:
+                monkeypatch.setenv("SGC_NO_T2", "1")
+            else:
+                monkeypatch.delenv("SGC_NO_T2", raising=False)
+            a.upload(u0); b.upload(v0)
+            g.profile_enable(True)
+            g.profile_read(2)
+            res = g.heat_run(a, b, cp, f, nstep, flags)
+            n2, _ = g.profile_read(2)
+            g.profile_enable(False)
+            assert (n2 == 0) == no_t2, "two-step passes launched: %d (SGC_NO_T2 %s)" % (n2, no_t2)
+            assert n2 in (0, ((nstep - 2) // 2) & ~1)
+            assert (res is b) == bool(nstep & 1)
+            outs.append((a.download(), b.download()))
+        monkeypatch.delenv("SGC_NO_T2", raising=False)
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (dhi, mb, "vs step-by-step")
+        want = u0.copy()
+        oracle.level_heat(dlo, dhi, mb, 1, 7, 0, f, nstep, want, contract)
+        got = outs[0][1] if nstep & 1 else outs[0][0]
+        # the oracle ping-pongs against a copy of the input level; ghost cells of the result level were
+        # last written by the exchange two steps earlier, which both schedules reproduce — compare the
+        # valid cells against the oracle and everything (above) against the step-by-step schedule
+        assert np.array_equal(oracle.gather(dlo, dhi, dbl.boxes, 1, 1, 0, got),
+                              oracle.gather(dlo, dhi, dbl.boxes, 1, 1, 0, want)), (dhi, mb, "vs oracle")
+
+
+def test_two_step_sweep_not_used_without_all_neighbours(g, oracle):
+    """Non-periodic z: boxes at the domain boundary have no z neighbour, so sgc_heat_run must stay on
+    the one-step kernels (ghost cells carry the boundary values) and still match the oracle."""
+    dlo, dhi, mb = (0, 0, 0), (127, 127, 127), (64, 64, 64)
+    dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
+    b = g.LevelData(dbl, 1, 1)
+    u0 = np.random.default_rng(22).standard_normal(a.elems)
+    a.upload(u0); b.upload(u0)
+    cp = g.Copier().defineExchangeLD(a, 3, 0)
+    g.profile_enable(True)
+    g.profile_read(2)
+    res = g.heat_run(a, b, cp, 0.125, 8)
+    n2, _ = g.profile_read(2)
+    g.profile_enable(False)
+    assert n2 == 0
+    want = u0.copy()
+    oracle.level_heat(dlo, dhi, mb, 1, 3, 0, 0.125, 8, want, 1)
+    assert np.array_equal(res.download(), want)
+
+
 def test_heat_tolerance_across_fma_modes(g, oracle):
     # the north_star's floating-point bar: <= 1e-12 relative per cell after N steps (observed CPU
     # fast-vs-off gap after 100 steps: 1.6e-15)
