@@ -148,6 +148,7 @@ struct T2Args {
   const double* in_level;     // arena base of the level at time t
   double* out_level;          // arena base of the level that receives time t+2
   long long xe_in, xe_out;    // element offsets of the edge-strip blocks in the two arenas
+  long long xe_spare_plane;   // strip plane index behind the last box: scratch for stores that must go nowhere
   const int* nbr;             // [nbox][27], as PushArgs::nbr
   int nplanes;                // nbox * (vz + 4) virtual planes
   int vz;                     // valid planes per box

@@ -53,6 +53,14 @@ __device__ __forceinline__ double heat_update(double c, double xm, double xp, do
   return FMA ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
 }
 
+// shared-memory load from a 32-bit shared address (lets the x-neighbour addresses be formed with ONE
+// integer multiply-add: base + column * per-lane byte stride)
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
 template <int V, int NS, int NCW, bool FMA>
 __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   constexpr int NT = NCW * 32;                  // threads: every warp is a consumer
@@ -189,12 +197,14 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
 
   // ---------------- regular role (every thread): x = xi, rows y0 .. y0+CPT-1 ----------------
   const int xi = tid % V, y0 = (tid / V) * CPT;
-  const bool at_lo = (xi == 0), at_hi = (xi == V - 1);
   const int oC0 = (y0 + 2) * V + xi;                              // tile offset of (xi, y0)
-  // x neighbours: the plane, or the x = -1 / x = V strip for the first / last column (strips advance
-  // by 1 per row, planes by V); one integer multiply-add per access, no divergent branch
-  const int oxm0 = at_lo ? E(1) + y0 : oC0 - 1, sxm = at_lo ? 1 : V;
-  const int oxp0 = at_hi ? E(2) + y0 : oC0 + 1, sxp = at_hi ? 1 : V;
+  // x neighbours: the plane (offset -1 / +1), or the x = -1 / x = V strip for the first / last column of
+  // a row.  Per lane that is a base offset and a byte stride per row (V*8 in the plane, 8 in a strip);
+  // the strides are made opaque to the compiler so that an access costs one multiply-add + one load
+  // (it would otherwise select between per-column constants: three integer instructions per access).
+  int oxm0 = xi == 0 ? E(1) + y0 : oC0 - 1, sxm = xi == 0 ? 8 : V * 8;
+  int oxp0 = xi == V - 1 ? E(2) + y0 : oC0 + 1, sxp = xi == V - 1 ? 8 : V * 8;
+  asm volatile("" : "+r"(sxm), "+r"(sxp));
   // Column state, all in registers: level t at the two latest planes (tA / tB) and level t+1 at the two
   // latest planes (uA / uB).  The roles "newest / previous" alternate from plane to plane — the loop
   // below is unrolled by two so that no value is ever moved between registers.
@@ -241,29 +251,36 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
 #pragma unroll
       for (int m = 0; m < CPT; ++m) Y[m] = C[oC0 + m * V];
     } else {
-      const int kz = l - 4;                                       // output plane inside the fab's valid region
+      // output plane inside the fab's valid region.  While the stages are being primed (do2 false) the
+      // stage-2 values are meaningless: they go to the fab's lower ghost plane (kz = -1; ghost cells are
+      // not read by this kernel and are rewritten by the exchange that follows the two-step phase) and
+      // to the spare strip plane behind the edge strips, which keeps the stores free of branches.
+      const int kz = do2 ? l - 4 : -1;
       // (xi, y0) of fab plane kz: fab-relative offset = tile offset + (N1 - 1) * V
       double* __restrict__ po = a.out_level + box * fabm + (long long)kz * FABP + (oC0 + (N1 - 1) * V);
       const int xq = oC0 & (V - 1);                               // = xi; edge-strip index of this column, if any
       const int xs = xq == 0 ? 0 : (xq == 1 ? 1 : (xq == V - 2 ? 2 : (xq == V - 1 ? 3 : -1)));
-      double* __restrict__ pe = a.out_level + a.xe_out + (((long long)box * vz + kz) * 4 + (xs < 0 ? 0 : xs)) * V + (oC0 / V - 2);
+      const long long eplane = do2 ? (long long)box * vz + kz : a.xe_spare_plane;
+      double* __restrict__ pe = a.out_level + a.xe_out + (eplane * 4 + (xs < 0 ? 0 : xs)) * V + (oC0 / V - 2);
       const double yfirst = P[oC0 - V], ylast = P[oC0 + CPT * V];
       const double yfirst1 = Tr[oC0 - V], ylast1 = Tr[oC0 + CPT * V];
+      const uint32_t pxm = smem_u32(P + oxm0), pxp = smem_u32(P + oxp0);      // x neighbours of row y0, level t
+      const uint32_t qxm = smem_u32(Tr + oxm0), qxp = smem_u32(Tr + oxp0);    // and level t+1
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
         const double zp = C[oC0 + m * V];
-        const double r1 = heat_update<FMA>(X[m], P[oxm0 + m * sxm], P[oxp0 + m * sxp], m > 0 ? X[m - 1] : yfirst,
-                                           m < CPT - 1 ? X[m + 1] : ylast, Y[m], zp, f);
+        const double xm = lds64(pxm + m * sxm), xp = lds64(pxp + m * sxp);
+        const double r1 = heat_update<FMA>(X[m], xm, xp, m > 0 ? X[m - 1] : yfirst, m < CPT - 1 ? X[m + 1] : ylast,
+                                           Y[m], zp, f);
         Y[m] = zp;
         Tw[oC0 + m * V] = r1;
-        // stage 2 (its result is stored only when the plane is owned and complete: do2)
-        const double o = heat_update<FMA>(U[m], Tr[oxm0 + m * sxm], Tr[oxp0 + m * sxp], m > 0 ? U[m - 1] : yfirst1,
-                                          m < CPT - 1 ? U[m + 1] : ylast1, W[m], r1, f);
+        // stage 2
+        const double xm1 = lds64(qxm + m * sxm), xp1 = lds64(qxp + m * sxp);
+        const double o = heat_update<FMA>(U[m], xm1, xp1, m > 0 ? U[m - 1] : yfirst1, m < CPT - 1 ? U[m + 1] : ylast1,
+                                          W[m], r1, f);
         W[m] = r1;
-        if (do2) {
-          po[m * V] = o;
-          if (xs >= 0) pe[m] = o;
-        }
+        po[m * V] = o;
+        if (xs >= 0) pe[m] = o;
       }
     }
     if (warp == 5 && more) finish((i + 2) & (NS - 1));
@@ -344,6 +361,7 @@ int launch_heat_t2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, const i
   const long long np = (long long)u->nbox * (g.vn[2] + 4);
   if (np > 0x7fffffffLL) return 1;
   a.nplanes = (int)np;
+  a.xe_spare_plane = (long long)u->nbox * g.vn[2];
   a.f = f;
   return launch_t2_cfg<64, 4, 16>(a, fma, s);
 }
