@@ -651,6 +651,37 @@ def test_full_size_C2_properties(g, oracle):
     mask[1:65, 1:65, 1:65] = True
     m = np.tile(mask.ravel(), a.size())
     assert abs(su[m].sum() - u[m].sum()) <= 1e-9 * abs(u[m].sum())
+    # (v) the same two properties through the step loop, whose passes advance TWO steps at a time on this
+    # level (sgc_stream2.cu): 8 steps of dyadic data with f = 1/8 stay exact in double, so the run is linear
+    # bit for bit, valid cells and ghost cells
+
+    def run8(x):
+        a.upload(x); b.upload(x)
+        g.profile_enable(True); g.profile_read(2)
+        r = g.heat_run(a, b, cp, 0.125, 8)
+        n2, _ = g.profile_read(2); g.profile_enable(False)
+        assert n2 == 2 and r is a
+        return r.download()
+    ru, rv, ruv = run8(u), run8(v), run8(4.0 * u + v)
+    assert np.array_equal(ruv, 4.0 * ru + rv)
+    assert abs(ru[m].sum() - u[m].sum()) <= 1e-9 * abs(u[m].sum())
+
+
+def test_two_step_sweep_256cubed_vs_oracle(g, oracle):
+    """A quarter-size C2 level (256^3 in 64^3 boxes, 64 boxes, every box with 26 distinct neighbours or
+    periodic images) through 10 steps = 4 two-step passes + fused + plain steps, against the oracle's
+    step-by-step run: every cell of the result level, ghost cells included."""
+    n, mb = 256, 64
+    dlo, dhi = (0, 0, 0), (n - 1,) * 3
+    dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
+    b = g.LevelData(dbl, 1, 1)
+    cp = g.Copier().defineExchangeLD(a, 7, 0)
+    u0 = np.random.default_rng(23).standard_normal(a.elems)
+    a.upload(u0); b.upload(u0)
+    res = g.heat_run(a, b, cp, 1.0 / 6.0, 10, g.SGC_FMA)
+    want = u0.copy()
+    oracle.level_heat(dlo, dhi, (mb,) * 3, 1, 7, 0, 1.0 / 6.0, 10, want, 1)
+    assert np.array_equal(res.download(), want)
 
 
 # ------------------------------------------------------------------ copy sets + lattice Boltzmann application
