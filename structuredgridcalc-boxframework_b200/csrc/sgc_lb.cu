@@ -42,6 +42,9 @@ const int h_opp[kQ] = {0, 2, 1, 4, 3, 6, 5, 10, 9, 8, 7, 14, 13, 12, 11, 18, 17,
 constexpr double kTau = 0.516, kCs2 = 1.0 / 3, kForce = 0.000001042;   // LBParameters.H:52-54
 
 constexpr int kLbThreads = 256;
+#ifndef SGC_LB_MINB
+#define SGC_LB_MINB 3            // CTAs per SM the per-cell kernels are compiled for (80 registers: measured best of 1..4)
+#endif
 
 // element offset (component 0) of valid cell number t of a fab, cells numbered x fastest
 __device__ __forceinline__ long long valid_cell(const FabGeom& g, int t) {
@@ -61,7 +64,7 @@ __device__ __forceinline__ long long valid_cell(const FabGeom& g, int t) {
 // ulp of a rounding boundary; for a given c those x are the solutions of a linear congruence, a
 // handful of mantissas, and tests/test_divconst_proof.py enumerates and checks them with exact
 // rational arithmetic for each of the four constants (none fails) — so the result equals the
-// reference's `/` bit for bit.  Zeros, subnormals, huge values, inf and nan take the real division.
+// reference's `/` bit for bit.  -0, subnormals, huge values, inf and nan take the real division.
 // ---------------------------------------------------------------------------------------------
 template <int K> struct DivConst;
 template <> struct DivConst<0> { static constexpr double c = kCs2; };
@@ -69,12 +72,18 @@ template <> struct DivConst<1> { static constexpr double c = 2 * kCs2; };
 template <> struct DivConst<2> { static constexpr double c = 2 * kCs2 * kCs2; };
 template <> struct DivConst<3> { static constexpr double c = kTau; };
 
-template <int K>
-__device__ __forceinline__ double divc(double x) {
+// `bad` collects, without a branch, whether any operand fell outside the range the three-instruction
+// form is proven for (|x| < 2^-959 or >= 2^961, inf, nan, -0; +0 is exact: q = r = +0): the caller then
+// redoes the whole cell with real divisions (EXACT).  Keeping the 58 divisions of a cell free of
+// branches lets the compiler interleave their dependency chains — the kernel is bound by FP64 latency,
+// not by the operation count.
+template <int K, bool EXACT>
+__device__ __forceinline__ double divc(double x, unsigned& bad) {
   constexpr double c = DivConst<K>::c;
+  if (EXACT) return x / c;
   constexpr double rc = 1.0 / c;
-  const unsigned e = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
-  if (e - 64u >= 1920u) return x / c;            // |x| < 2^-959 (incl. 0) or >= 2^961, inf, nan
+  const unsigned h = (unsigned)__double2hiint(x), l = (unsigned)__double2loint(x);
+  bad |= (unsigned)((((h >> 20) & 0x7ffu) - 64u >= 1920u) & ((h | l) != 0u));
   const double q = __dmul_rn(x, rc);
   const double r = __fma_rn(-q, c, x);
   return __fma_rn(r, rc, q);
@@ -88,13 +97,14 @@ __device__ __forceinline__ double divc(double x) {
 // products with the lattice components 0 and +-1 are exact, so eu is one of +-u_a, +-(u_a + u_b),
 // +-(u_a - u_b) (negation commutes with rounding; the sign of a zero eu cannot reach f), and
 // eu/cs2, eu*eu/(2 cs2^2) are shared by the two directions of a pair.
-__device__ __forceinline__ void collide_cell(double* f /* [kQ] */, double rho, double u0, double u1, double u2) {
-  const double usq = divc<1>((u0 * u0 + u1 * u1) + u2 * u2);
+template <bool EXACT>
+__device__ __forceinline__ void collide_cell(double* f /* [kQ] */, double rho, double u0, double u1, double u2, unsigned& bad) {
+  const double usq = divc<1, EXACT>((u0 * u0 + u1 * u1) + u2 * u2, bad);
   const double wr0 = (1. / 3.) * rho, wr1 = (1. / 18.) * rho, wr2 = (1. / 36.) * rho;
   constexpr double F1 = 3 * (1. / 18.) * kForce, F2 = 3 * (1. / 36.) * kForce;   // ((3*w)*(+-1))*force
   // one direction: t = ((1 +- a) + b) - usq, then relax towards (w*rho)*t and add the body force
 #define SGC_LB_RELAX(q, t, wr, force) \
-  f[q] = (f[q] + divc<3>((wr) * (t) - f[q])) + (force)
+  f[q] = (f[q] + divc<3, EXACT>((wr) * (t) - f[q], bad)) + (force)
   {
     const double t = (1.0 - usq);                       // eu == 0: (1 + 0) + 0
     SGC_LB_RELAX(0, t, wr0, 0.0);
@@ -102,7 +112,7 @@ __device__ __forceinline__ void collide_cell(double* f /* [kQ] */, double rho, d
 #define SGC_LB_PAIR(qpos, qneg, eu, wr, fpos, fneg)                      \
   {                                                                     \
     const double eu_ = (eu);                                            \
-    const double a = divc<0>(eu_), b = divc<2>(eu_ * eu_);              \
+    const double a = divc<0, EXACT>(eu_, bad), b = divc<2, EXACT>(eu_ * eu_, bad); \
     const double tp = ((1.0 + a) + b) - usq, tn = ((1.0 - a) + b) - usq; \
     SGC_LB_RELAX(qpos, tp, wr, fpos);                                   \
     SGC_LB_RELAX(qneg, tn, wr, fneg);                                   \
@@ -141,11 +151,13 @@ template <int K>
 __global__ void k_divc_check(const double* __restrict__ x, double* __restrict__ fast, double* __restrict__ exact, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  fast[i] = divc<K>(x[i]);
+  unsigned bad = 0;
+  const double v = divc<K, false>(x[i], bad);
+  fast[i] = bad ? divc<K, true>(x[i], bad) : v;     // what a cell with this operand ends up with
   exact[i] = x[i] / DivConst<K>::c;
 }
 
-__global__ void __launch_bounds__(kLbThreads)
+__global__ void __launch_bounds__(kLbThreads, SGC_LB_MINB)
 k_lb_collide(const FabGeom* __restrict__ gf, const FabGeom* __restrict__ gm, double* __restrict__ fi,
              const double* __restrict__ macro) {
   const FabGeom F = gf[blockIdx.y], M = gm[blockIdx.y];
@@ -156,13 +168,19 @@ k_lb_collide(const FabGeom* __restrict__ gf, const FabGeom* __restrict__ gm, dou
     double f[kQ];
 #pragma unroll
     for (int q = 0; q < kQ; ++q) f[q] = fi[cf + q * F.cs];
-    collide_cell(f, rho, u0, u1, u2);
+    unsigned bad = 0;
+    collide_cell<false>(f, rho, u0, u1, u2, bad);
+    if (bad) {                                   // an operand outside the proven range: real divisions
+#pragma unroll
+      for (int q = 0; q < kQ; ++q) f[q] = fi[cf + q * F.cs];
+      collide_cell<true>(f, rho, u0, u1, u2, bad);
+    }
 #pragma unroll
     for (int q = 0; q < kQ; ++q) fi[cf + q * F.cs] = f[q];
   }
 }
 
-__global__ void __launch_bounds__(kLbThreads)
+__global__ void __launch_bounds__(kLbThreads, SGC_LB_MINB)
 k_lb_macroscopic(const FabGeom* __restrict__ gf, const FabGeom* __restrict__ gm, const double* __restrict__ fi,
                  double* __restrict__ macro) {
   const FabGeom F = gf[blockIdx.y], M = gm[blockIdx.y];
@@ -184,7 +202,7 @@ k_lb_macroscopic(const FabGeom* __restrict__ gf, const FabGeom* __restrict__ gm,
 // with COLLIDE the collision of the following step is applied before the store, so that the value
 // crosses HBM once per step instead of three times.
 template <bool COLLIDE>
-__global__ void __launch_bounds__(kLbThreads)
+__global__ void __launch_bounds__(kLbThreads, SGC_LB_MINB)
 k_lb_stream_moments(const FabGeom* __restrict__ gf, const FabGeom* __restrict__ gm, const double* __restrict__ cur,
                     double* __restrict__ nxt, double* __restrict__ macro) {
   const FabGeom F = gf[blockIdx.y], M = gm[blockIdx.y];
@@ -202,7 +220,16 @@ k_lb_stream_moments(const FabGeom* __restrict__ gf, const FabGeom* __restrict__ 
     const long long cm = fab_index(M, i + ox, j + oy, k + oz, 0);
 #pragma unroll
     for (int d = 0; d < kMacro; ++d) macro[cm + d * M.cs] = m[d];
-    if (COLLIDE) collide_cell(f, m[0], m[1], m[2], m[3]);
+    if (COLLIDE) {
+      unsigned bad = 0;
+      collide_cell<false>(f, m[0], m[1], m[2], m[3], bad);
+      if (bad) {                                 // an operand outside the proven range: real divisions
+#pragma unroll
+        for (int q = 0; q < kQ; ++q)
+          f[q] = cur[fab_index(F, i + ox - c_e[q][0], j + oy - c_e[q][1], k + oz - c_e[q][2], q)];
+        collide_cell<true>(f, m[0], m[1], m[2], m[3], bad);
+      }
+    }
     const long long cf = fab_index(F, i + ox, j + oy, k + oz, 0);
 #pragma unroll
     for (int q = 0; q < kQ; ++q) nxt[cf + q * F.cs] = f[q];
