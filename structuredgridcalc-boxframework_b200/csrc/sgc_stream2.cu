@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   constexpr uint32_t TILE_BYTES = (uint32_t)(V * V + 4 * V + 4 * V) * 8u;   // rows + 2x2 y rows + 4 strips
   static_assert(NT % V == 0 && V % G == 0, "thread mapping");
   static_assert(4 * V == NT / 2, "the upper half of the warps owns one flank cell per thread");
-  constexpr int NROLE = 6;                      // warps that bring in a piece of each tile (one arrival each)
+  constexpr int NROLE = 6;                      // warps that bring in a piece of each tile
+  constexpr int NARRIVE = 5 + 4;                // arrivals per tile: warps 0-4 + the four corner copies of warp 5
   static_assert((NS & (NS - 1)) == 0 && NS >= 4, "ring: two tiles being read, two in flight");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
 
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) mbar_init(full + i, NROLE);
+    for (int i = 0; i < NS; ++i) mbar_init(full + i, NARRIVE);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -107,13 +108,12 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   // warps so that no warp lags at the per-plane barrier: lane 0 of warp r issues
   //   r = 0: the V own rows (+ announces the tile's bytes)   r = 1 / 2: the two rows of the -y / +y neighbour
   //   r = 3 / 4: the two edge strips of the -x / +x neighbour
-  // and lanes 0-3 of warp 5 fetch the four corner cells with plain loads.  issue() starts the copies /
-  // loads of the tile two iterations ahead; finish(), an iteration's worth of computing later, stores
-  // the corner values and makes warp 5's arrival (the slot completes on six arrivals + the bytes).
+  // and lanes 0-3 of warp 5 fetch the four corner cells with 8-byte cp.async copies, each arriving on
+  // the slot's mbarrier when it lands (cp.async.mbarrier.arrive.noinc).  issue() starts all of that for
+  // the tile two iterations ahead; the slot completes on nine arrivals + the bulk copies' bytes.
   int S = -1, N = 0;                  // source box of the current tiles; this role's neighbour of S
   const double* base = a.in_level;
   unsigned waited = 0;                // bit per peer slot
-  double cv = 0.0;
   auto issue = [&](int slot, int tbox, int tl) {          // tile = virtual plane tl of box tbox
     const int z = tl - 2;
     const int cls = z < 0 ? 0 : (z >= vz ? 2 : 1);
@@ -153,7 +153,11 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
     const long long prow = ((long long)(kz + 1) * N1 + 1) * V;      // first valid row of fab plane kz
     double* dst = ring + (size_t)slot * SLOT;
     if (warp == 5) {
-      if (lane < 4) cv = *(base + N * fabm + prow + (long long)((lane & 2) ? 0 : V - 1) * V + ((lane & 1) ? 0 : V - 1));
+      if (lane < 4) {
+        const double* src = base + N * fabm + prow + (long long)((lane & 2) ? 0 : V - 1) * V + ((lane & 1) ? 0 : V - 1);
+        cp_async8(dst + E((lane & 1) ? 2 : 1) + ((lane & 2) ? V : -1), src);
+        cp_async_arrive(full + slot);
+      }
     } else if (lane == 0) {
       if (warp == 0) {
         mbar_expect_tx(full + slot, TILE_BYTES);                  // this warp's arrival + the tile's byte count
@@ -175,18 +179,11 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       if (warp != 0) mbar_arrive(full + slot);
     }
   };
-  auto finish = [&](int slot) {                           // warp 5 only
-    if (lane < 4) ring[(size_t)slot * SLOT + E((lane & 1) ? 2 : 1) + ((lane & 2) ? V : -1)] = cv;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(full + slot);
-  };
   if (warp < NROLE) {
     const int b0 = l_begin / VP, l0 = l_begin - b0 * VP;
     issue(0, b0, l0);
-    if (warp == 5) finish(0);
     if (l_begin + 1 < s_end) {
       issue(1, l0 + 1 == VP ? b0 + 1 : b0, l0 + 1 == VP ? 0 : l0 + 1);
-      if (warp == 5) finish(1);
     }
   }
 
@@ -283,7 +280,6 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
         if (xs >= 0) pe[m] = o;
       }
     }
-    if (warp == 5 && more) finish((i + 2) & (NS - 1));
     if (++l == VP) { l = 0; ++box; }
   };
   for (int i = 0; i < n_iter; i += 2) {
