@@ -1,0 +1,13 @@
+#!/bin/bash
+# A/B timing of library variants on the same GPU: variants/*.so are copied over the product library in turn
+# (profiles/micro/t2_probe.py perf), twice each, interleaved.   usage: bash profiles/micro/ab.sh
+L=structuredgridcalc-boxframework_b200/libsgc_b200.so
+cp $L /tmp/orig.so
+for rep in 1 2; do
+  for f in variants/*.so; do
+    cp $f $L; touch $L
+    echo -n "$f: "
+    timeout 120 python profiles/micro/t2_probe.py perf 2>&1 | tail -1 | python -c "import sys,json; j=json.loads(sys.stdin.read()); print('%.4f ms two-step, %.1f Gcell/s overall' % (j['two_step_ms'], j['gcell_per_s']))"
+  done
+done
+cp /tmp/orig.so $L

@@ -112,21 +112,18 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   // the slot's mbarrier when it lands (cp.async.mbarrier.arrive.noinc).  issue() starts all of that for
   // the tile two iterations ahead; the slot completes on nine arrivals + the bulk copies' bytes.
   int S = -1, N = 0;                  // source box of the current tiles; this role's neighbour of S
-  const double* base = a.in_level;
   unsigned waited = 0;                // bit per peer slot
   auto issue = [&](int slot, int tbox, int tl) {          // tile = virtual plane tl of box tbox
     const int z = tl - 2;
     const int cls = z < 0 ? 0 : (z >= vz ? 2 : 1);
     if (S < 0 || tl == 0 || tl == 2 || tl == vz + 2) {    // first tile, or the source box changes here
-      base = a.in_level;
       if (cls == 1) S = tbox;
       else {
         S = __ldg(a.nbr + (size_t)tbox * 27 + (cls == 0 ? 4 : 22));
         if (S < 0) {                           // z neighbour lives on another GPU (checked on the host)
           const int rr = __ldg(a.rz + 2 * tbox + (cls == 0 ? 0 : 1));
           const int ps = rr >> 28;
-          S = rr & 0x0fffffff;
-          base = ps ? a.peer_in[1] : a.peer_in[0];
+          S = (rr & 0x0fffffff) | (ps ? 0x60000000 : 0x40000000);     // bit 30: remote, bit 29: peer slot
           if (!(waited >> ps & 1u)) {          // the peer must have finished writing the level we read
             if (lane == 0) {
               const volatile unsigned long long* fl = ps ? a.peer_flag[1] : a.peer_flag[0];
@@ -147,11 +144,12 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       int code = 13;
       if (warp == 1) code = 10; else if (warp == 2) code = 16; else if (warp == 3) code = 12; else if (warp == 4) code = 14;
       else if (warp == 5) code = 13 + ((lane & 1) ? 1 : -1) + ((lane & 2) ? 3 : -3);   // corner (dx,dy) by lane bits
-      N = warp == 0 ? S : __ldg(a.nbr + (size_t)S * 27 + code);
+      N = warp == 0 ? (S & 0x0fffffff) : __ldg(a.nbr + (size_t)(S & 0x0fffffff) * 27 + code);
     }
     const int kz = cls == 0 ? z + vz : (cls == 2 ? z - vz : z);
     const long long prow = ((long long)(kz + 1) * N1 + 1) * V;      // first valid row of fab plane kz
     double* dst = ring + (size_t)slot * SLOT;
+    const double* base = !(S & 0x40000000) ? a.in_level : ((S & 0x20000000) ? a.peer_in[1] : a.peer_in[0]);
     if (warp == 5) {
       if (lane < 4) {
         const double* src = base + N * fabm + prow + (long long)((lane & 2) ? 0 : V - 1) * V + ((lane & 1) ? 0 : V - 1);
