@@ -89,8 +89,10 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int vz = a.vz, VP = vz + 4;
   const long long fabm = (long long)FABP * (vz + 2);
-  const int s_begin = (int)((long long)blockIdx.x * a.nplanes / gridDim.x);
-  const int s_end = (int)((long long)(blockIdx.x + 1) * a.nplanes / gridDim.x);
+  // ranges start on even virtual planes (vz is even: heat_t2_covers), which makes the parity of a plane's
+  // t+1 buffer the parity of the loop counter
+  const int s_begin = 2 * (int)((long long)blockIdx.x * (a.nplanes / 2) / gridDim.x);
+  const int s_end = 2 * (int)((long long)(blockIdx.x + 1) * (a.nplanes / 2) / gridDim.x);
   if (s_begin >= s_end) return;
   const int l_begin = s_begin >= 4 ? s_begin - 4 : 0;     // 4 tiles prime the two stages
 
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   for (int m = 0; m < CPT; ++m) tA[m] = tB[m] = uA[m] = uB[m] = 0.0;
   const double f = a.f;
   int box = l_begin / VP, l = l_begin - box * VP;
-  const int n_iter = s_end - l_begin, lead = s_begin - l_begin, par0 = l_begin & 1;
+  const int n_iter = s_end - l_begin, lead = s_begin - l_begin;
 
   // One plane: tile i arrives as the z+1 plane of stage 1.  X = level t at the previous plane (centre of
   // stage 1), Y = the plane before (overwritten with the arriving plane); U = level t+1 at the previous
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
     const bool do1 = (l >= 2) && (i >= 2);
     const bool do2 = (l >= 4) && (i >= lead);
     // t+1 plane buffers, addressed with tile offsets
-    const int par = (i + par0) & 1;                               // parity of the virtual plane v = l_begin + i
+    const int par = i & 1;                                        // parity of the virtual plane v = l_begin + i
     double* __restrict__ Tw = t1 + (par ^ 1) * T1SZ - V;          // virtual plane v-1 (written now)
     const double* __restrict__ Tr = t1 + par * T1SZ - V;          // virtual plane v-2 (written last iteration)
     if (flank) {
@@ -261,10 +263,12 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       const double yfirst1 = Tr[oC0 - V], ylast1 = Tr[oC0 + CPT * V];
       const uint32_t pxm = smem_u32(P + oxm0), pxp = smem_u32(P + oxp0);      // x neighbours of row y0, level t
       const uint32_t qxm = smem_u32(Tr + oxm0), qxp = smem_u32(Tr + oxp0);    // and level t+1
+      // the loads of the next column are issued before the arithmetic of this one (software prefetch)
+      double zpN = C[oC0], xmN = lds64(pxm), xpN = lds64(pxp);
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
-        const double zp = C[oC0 + m * V];
-        const double xm = lds64(pxm + m * sxm), xp = lds64(pxp + m * sxp);
+        const double zp = zpN, xm = xmN, xp = xpN;
+        if (m < CPT - 1) { zpN = C[oC0 + (m + 1) * V]; xmN = lds64(pxm + (m + 1) * sxm); xpN = lds64(pxp + (m + 1) * sxp); }
         const double r1 = heat_update<FMA>(X[m], xm, xp, m > 0 ? X[m - 1] : yfirst, m < CPT - 1 ? X[m + 1] : ylast,
                                            Y[m], zp, f);
         Y[m] = zp;
@@ -325,7 +329,7 @@ bool heat_t2_covers(const sgc_level_s* unew, const sgc_level_s* u) {
   if (u->esz != 8 || unew->esz != 8 || !u->xe_elems || !unew->xe_elems || getenv("SGC_NO_T2")) return false;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0 || u->nbox != unew->nbox) return false;
-  return g.vn[0] == 64 && g.vn[1] == 64 && g.vn[2] >= 4;
+  return g.vn[0] == 64 && g.vn[1] == 64 && g.vn[2] >= 4 && g.vn[2] % 2 == 0;
 }
 
 int launch_build_xe(sgc_level_s* l, cudaStream_t s) {
