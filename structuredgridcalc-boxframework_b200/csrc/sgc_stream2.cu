@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       const uint32_t qxm = smem_u32(Tr + oxm0), qxp = smem_u32(Tr + oxp0);    // and level t+1
       // the loads of the next column are issued before the arithmetic of this one (software prefetch)
       double zpN = C[oC0], xmN = lds64(pxm), xpN = lds64(pxp);
+      double oprev = 0.0;
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
         const double zp = zpN, xm = xmN, xp = xpN;
@@ -279,7 +280,8 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
                                           W[m], r1, f);
         W[m] = r1;
         po[m * V] = o;
-        if (xs >= 0) pe[m] = o;
+        // edge strips: two rows per 16-byte store (only the four edge columns of 64 store at all)
+        if (m & 1) { if (xs >= 0) *reinterpret_cast<double2*>(pe + m - 1) = make_double2(oprev, o); } else oprev = o;
       }
     }
     if (++l == VP) { l = 0; ++box; }
