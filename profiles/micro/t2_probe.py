@@ -1,5 +1,5 @@
 """Two-steps-per-pass sweep (sgc_stream2.cu): parity against the oracle, then timing on the C2 level.
-    python profiles/micro/t2_probe.py [parity|perf|all]
+    python profiles/micro/t2_probe.py [parity|perf|all] [periodic flags for perf, default 7]
 Test infrastructure: imports oracle/ as the checker only.
 """
 import json
@@ -41,7 +41,11 @@ if what in ("parity", "all"):
              ((0, 0, 0), (127, 127, 127), (64, 64, 64), 7, 1.0 / 6.0, 12, 0),
              ((0, 0, 0), (191, 63, 127), (64, 64, 64), 7, 0.2, 9, 1),
              ((0, 0, 0), (63, 127, 15), (64, 64, 8), 7, 0.2, 11, 1),
-             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 3, 0.125, 8, 1)]     # not periodic in z: falls back
+             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 3, 0.125, 8, 1),     # physical boundaries
+             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 0, 0.2, 9, 1),
+             ((0, 0, 0), (191, 127, 63), (64, 64, 64), 4, 1.0 / 6.0, 8, 0),
+             ((0, 0, 0), (63, 191, 127), (64, 64, 64), 1, 0.3, 10, 1),
+             ((0, 0, 0), (127, 127, 15), (64, 64, 8), 2, 0.3, 7, 1)]
     for (dlo, dhi, mb, per, f, nstep, contract) in cases:
         dbl = sgc.DisjointBoxLayout(sgc.Box(dlo, dhi), mb)
         rng = np.random.default_rng(3)
@@ -79,7 +83,8 @@ if what in ("perf", "all"):
     rng = np.random.default_rng(0)
     a.upload(rng.random(a.elems))
     b.copyFrom(a)
-    cp = sgc.Copier().defineExchangeLD(a, 7, 0)
+    per = int(sys.argv[2]) if len(sys.argv) > 2 else 7      # periodic flags (7 = xyz; 0 = physical boundaries all round)
+    cp = sgc.Copier().defineExchangeLD(a, per, 0)
     for _ in range(2):
         sgc.heat_run(a, b, cp, 0.125, sweeps)
     sgc.sync()
@@ -97,7 +102,7 @@ if what in ("perf", "all"):
     n0, t0 = sgc.profile_read(0)
     n2, t2 = sgc.profile_read(2)
     cells = float(n) ** 3
-    print(json.dumps({"ms_per_100_sweeps": ms, "gcell_per_s": cells * sweeps / (ms * 1e-3) / 1e9,
+    print(json.dumps({"periodic": per, "ms_per_100_sweeps": ms, "gcell_per_s": cells * sweeps / (ms * 1e-3) / 1e9,
                       "one_step_launches": n0, "one_step_ms": t0 / max(n0, 1),
                       "two_step_launches": n2, "two_step_ms": t2 / max(n2, 1),
                       "two_step_gcell_per_s": 2 * cells / (t2 / max(n2, 1) * 1e-3) / 1e9 if n2 else None}), flush=True)

@@ -370,7 +370,7 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
   {
     const FabGeom& g0 = l->geom[0];
     if (l->uniform && ncomp == 1 && nghost == 1 && elem_bytes == 8 && g0.vn[0] == 64 && g0.vn[1] == 64 && g0.vn[2] >= 4)
-      l->xe_elems = ((long long)nbox * g0.vn[2] + 1) * 4 * g0.vn[1];     // + one spare strip plane
+      l->xe_elems = ((long long)nbox * g0.vn[2] + 1) * 4 * g0.vn[1] + (long long)g0.vn[0] * g0.vn[1];   // + a spare strip plane + a scratch plane
   }
   const size_t bytes = (size_t)(l->lead + l->xe_base + l->xe_elems + 64) * elem_bytes;
   cudaError_t e = cudaMalloc(&l->d_base, bytes);
@@ -858,19 +858,37 @@ int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], 
     p->fusable = (st == 0);
     // two-step sweep: the 8 in-plane neighbours must be local boxes; z neighbours local, or remote
     // on a z-slab partition (then the plan has remote items and the peer-memory session decides)
-    p->t2_local = p->t2_slab = p->fusable;
-    std::vector<char> zcover((size_t)l->nbox * 2, 0);   // box has a -z / +z face item, local or remote
+    // Two-step sweep (sgc_stream2.cu).  t2_local: every box has its 8 in-plane neighbours and both z
+    // neighbours locally; t2_slab: the z neighbours may live on another rank (peer memory).  t2_bnd: some
+    // FACES have no motion item at all — a physical boundary or a trimmed direction, whose ghost cells the
+    // exchange never writes — which the kernel's boundary instance handles; what it cannot handle is an
+    // in-plane neighbour on another rank, or a diagonal box missing although both faces towards it exist.
+    std::vector<char> cover((size_t)l->nbox * 27, 0);   // (box, direction) has a face item, local or remote
     for (const sgc_motion_item& it : p->items)
-      if (it.dir[0] == 0 && it.dir[1] == 0 && it.dir[2] != 0)
-        zcover[(size_t)(it.recv_box - l->gidx0) * 2 + (it.dir[2] < 0 ? 0 : 1)] = 1;
-    for (int b = 0; b < l->nbox && p->t2_slab; ++b) {
+      if (abs(it.dir[0]) + abs(it.dir[1]) + abs(it.dir[2]) == 1)
+        cover[(size_t)(it.recv_box - l->gidx0) * 27 + 13 + it.dir[0] + 3 * it.dir[1] + 9 * it.dir[2]] = 1;
+    bool ok = p->fusable, all_inplane = true, all_z_local = true, all_z = true;
+    for (int b = 0; b < l->nbox && ok; ++b) {
       const int* nb = nbr.data() + (size_t)b * 27;
-      for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx)
-          if ((dx || dy) && nb[13 + dx + 3 * dy] < 0) p->t2_local = p->t2_slab = false;
-      if (nb[4] < 0 || nb[22] < 0) p->t2_local = false;
-      if (!zcover[(size_t)b * 2] || !zcover[(size_t)b * 2 + 1]) p->t2_slab = false;
+      const char* cv = cover.data() + (size_t)b * 27;
+      for (int d = 0; d < 2 && ok; ++d)
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+          const int code = 13 + sgn * (d == 0 ? 1 : 3);
+          if (nb[code] < 0) { all_inplane = false; if (cv[code]) ok = false; }     // covered but not local: another rank
+        }
+      for (int sy = -1; sy <= 1 && ok; sy += 2)
+        for (int sx = -1; sx <= 1; sx += 2) {
+          const int X = nb[13 + sx], Y = nb[13 + 3 * sy];
+          if (X >= 0 && Y >= 0 && nbr[(size_t)X * 27 + 13 + 3 * sy] < 0) ok = false;   // diagonal box over two faces
+        }
+      for (int sgn = -1; sgn <= 1; sgn += 2) {
+        const int code = 13 + 9 * sgn;
+        if (nb[code] < 0) { all_z_local = false; if (!cv[code]) all_z = false; }
+      }
     }
+    p->t2_local = ok && all_inplane && all_z_local;
+    p->t2_slab = ok && all_inplane && all_z;
+    p->t2_bnd = ok && !(all_inplane && all_z);
   }
   if (st) { sgc_plan_destroy(p); return st; }
   *plan = p;
@@ -1138,7 +1156,8 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
     // edge strips), so no ghost cell is touched until the phase ends; an even number of passes keeps
     // the result in the level the step-by-step schedule would leave it in.
     const int npass = ((nstep - 2) / 2) & ~1;
-    if (npass >= 2 && heat_t2_covers(b, a) && (plan->t2_local || (plan->t2_slab && p2p))) {
+    const bool t2_remote_ok = plan->nremote == 0 || p2p;          // remote z faces need the peer-memory session
+    if (npass >= 2 && heat_t2_covers(b, a) && (plan->t2_local || ((plan->t2_slab || plan->t2_bnd) && t2_remote_ok))) {
       sgc_plan_s::P2P& S = plan->p2p;
       st = launch_build_xe(cur, rt().compute);
       if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);     // our strips are readable
@@ -1155,9 +1174,22 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
           ra.wait_value = S.counter;
           ra.err = S.d_err;
         }
+        if (plan->t2_bnd) {
+          // faces without a neighbour: step t of the run reads level a's ghost cells, step t+1 level b's —
+          // whichever level currently holds the valid cells (s0 is even here, so `a` is the level of step t)
+          ra.ghost[0] = (const double*)a->d_arena;
+          ra.ghost[1] = (const double*)b->d_arena;
+          if (p2p) {
+            const int ia = (a == S.lev[0]) ? 0 : 1;
+            for (int q = 0; q < S.npeer; ++q) {
+              ra.peer_ghost[q][0] = (const double*)((char*)S.peer_base[q][ia] + a->lead * a->esz);
+              ra.peer_ghost[q][1] = (const double*)((char*)S.peer_base[q][ia ^ 1] + b->lead * b->esz);
+            }
+          }
+        }
         {
           ProfScope prof(2, rt().compute);
-          st = launch_heat_t2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, plan->d_push, p2p ? &ra : nullptr, rt().compute);
+          st = launch_heat_t2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, plan->d_push, &ra, rt().compute);
         }
         if (st > 0) st = fail(SGC_ERR_UNSUPPORTED, "two-step sweep: geometry not covered");
         if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);

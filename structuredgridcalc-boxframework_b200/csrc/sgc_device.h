@@ -149,6 +149,12 @@ struct T2Args {
   double* out_level;          // arena base of the level that receives time t+2
   long long xe_in, xe_out;    // element offsets of the edge-strip blocks in the two arenas
   long long xe_spare_plane;   // strip plane index behind the last box: scratch for stores that must go nowhere
+  long long dump;             // element offset (output arena) of a scratch plane for the same purpose
+  long long xg_base;          // element offset of the x-ghost region of an arena
+  // levels with faces that have no neighbour (non-null ghost[0] selects that instance): the arenas whose
+  // ghost cells are read as level t (steps 0, 2, 4 .. of the run: level a) and as level t+1 (level b)
+  const double* ghost[2];
+  const double* peer_ghost[2][2];            // the same arenas on the z neighbours' GPUs, [peer slot][0/1]
   const int* nbr;             // [nbox][27], as PushArgs::nbr
   int nplanes;                // nbox * (vz + 4) virtual planes
   int vz;                     // valid planes per box
@@ -229,6 +235,7 @@ struct sgc_plan_s {
   // two-steps-per-pass sweep (sgc_stream2.cu): every box has its 8 in-plane neighbours locally, and its
   // two z neighbours locally (t2_local) or at least in the plan (t2_slab: the missing ones are remote)
   bool t2_local = false, t2_slab = false;
+  bool t2_bnd = false;                  // as t2_slab, but some faces have no motion item at all (physical boundary)
   // peer-memory halo session (sgc_comm.cu): the two ping-pong levels of a step loop, their arenas on
   // the z neighbours mapped through cudaIpc, and progress counters
   struct P2P {

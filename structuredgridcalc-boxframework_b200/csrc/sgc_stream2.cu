@@ -61,7 +61,7 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
   return v;
 }
 
-template <int V, int NS, int NCW, bool FMA>
+template <int V, int NS, int NCW, bool FMA, bool BND>
 __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   constexpr int NT = NCW * 32;                  // threads: every warp is a consumer
   constexpr int N1 = V + 2;                     // fab rows (one ghost layer)
@@ -78,7 +78,9 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   static_assert(NT % V == 0 && V % G == 0, "thread mapping");
   static_assert(4 * V == NT / 2, "the upper half of the warps owns one flank cell per thread");
   constexpr int NROLE = 6;                      // warps that bring in a piece of each tile
-  constexpr int NARRIVE = 5 + 4;                // arrivals per tile: warps 0-4 + the four corner copies of warp 5
+  // arrivals per tile: warps 0-4 + the four corner copies of warp 5; with physical boundaries (BND) the x
+  // strips may come by 8-byte cp.async copies, so every lane of warps 3 and 4 arrives
+  constexpr int NARRIVE = BND ? 3 + 64 + 4 : 5 + 4;
   static_assert((NS & (NS - 1)) == 0 && NS >= 4, "ring: two tiles being read, two in flight");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -113,7 +115,15 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   // and lanes 0-3 of warp 5 fetch the four corner cells with 8-byte cp.async copies, each arriving on
   // the slot's mbarrier when it lands (cp.async.mbarrier.arrive.noinc).  issue() starts all of that for
   // the tile two iterations ahead; the slot completes on nine arrivals + the bulk copies' bytes.
-  int S = -1, N = 0;                  // source box of the current tiles; this role's neighbour of S
+  // BND: a face of a box without a motion item in the plan (a physical boundary, or a trimmed direction)
+  // keeps its ghost cells for ever, each level its own: step t reads the ghosts of a.ghost[0], step t+1
+  // those of a.ghost[1].  Where a neighbour is missing the tile takes the level-t ghost cells instead of
+  // the neighbour's valid cells, and the slot of the second halo layer (x = -2 / V+1 strip, row y = -2 /
+  // V+1, plane z = -2 / vz+1) — not needed there — carries the level-t+1 ghost cells, which the consumers
+  // copy where they would have computed a flank / halo-plane value.
+  int S = -1, N = 0;                  // source box of the current tiles (bit 30 remote, 29 peer slot, 28 z face
+                                      // missing); this role's neighbour of S (BND: -1 = missing)
+  int ct = 0;                         // BND, warp 5: where the lane's corner cell comes from (see below)
   unsigned waited = 0;                // bit per peer slot
   auto issue = [&](int slot, int tbox, int tl) {          // tile = virtual plane tl of box tbox
     const int z = tl - 2;
@@ -122,50 +132,118 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       if (cls == 1) S = tbox;
       else {
         S = __ldg(a.nbr + (size_t)tbox * 27 + (cls == 0 ? 4 : 22));
-        if (S < 0) {                           // z neighbour lives on another GPU (checked on the host)
-          const int rr = __ldg(a.rz + 2 * tbox + (cls == 0 ? 0 : 1));
-          const int ps = rr >> 28;
-          S = (rr & 0x0fffffff) | (ps ? 0x60000000 : 0x40000000);     // bit 30: remote, bit 29: peer slot
-          if (!(waited >> ps & 1u)) {          // the peer must have finished writing the level we read
-            if (lane == 0) {
-              const volatile unsigned long long* fl = ps ? a.peer_flag[1] : a.peer_flag[0];
-              long long spins = 0;
-              while (*fl < a.wait_value) {
-                if (++spins > (1LL << 20)) { *a.err = 1u; break; }    // ~3 s: report, never hang
-                __nanosleep(64);
+        if (S < 0) {
+          const int rr = a.rz ? __ldg(a.rz + 2 * tbox + (cls == 0 ? 0 : 1)) : -1;
+          if (BND && rr < 0) S = tbox | 0x10000000;          // no z neighbour at all: the box's own ghost planes
+          else {                                 // z neighbour lives on another GPU (checked on the host)
+            const int ps = rr >> 28;
+            S = (rr & 0x0fffffff) | (ps ? 0x60000000 : 0x40000000);     // bit 30: remote, bit 29: peer slot
+            if (!(waited >> ps & 1u)) {          // the peer must have finished writing the level we read
+              if (lane == 0) {
+                const volatile unsigned long long* fl = ps ? a.peer_flag[1] : a.peer_flag[0];
+                long long spins = 0;
+                while (*fl < a.wait_value) {
+                  if (++spins > (1LL << 20)) { *a.err = 1u; break; }    // ~3 s: report, never hang
+                  __nanosleep(64);
+                }
               }
+              __syncwarp();
+              __threadfence_system();
+              asm volatile("fence.proxy.async;" ::: "memory");
+              waited |= 1u << ps;
             }
-            __syncwarp();
-            __threadfence_system();
-            asm volatile("fence.proxy.async;" ::: "memory");
-            waited |= 1u << ps;
           }
         }
       }
       // this role's in-plane neighbour of S (on a z-slab partition the peer's local indices equal ours)
-      int code = 13;
-      if (warp == 1) code = 10; else if (warp == 2) code = 16; else if (warp == 3) code = 12; else if (warp == 4) code = 14;
-      else if (warp == 5) code = 13 + ((lane & 1) ? 1 : -1) + ((lane & 2) ? 3 : -3);   // corner (dx,dy) by lane bits
-      N = warp == 0 ? (S & 0x0fffffff) : __ldg(a.nbr + (size_t)(S & 0x0fffffff) * 27 + code);
+      const int* __restrict__ nb = a.nbr + (size_t)(S & 0x0fffffff) * 27;
+      if (warp == 0) N = S & 0x0fffffff;
+      else if (warp < 5) N = __ldg(nb + (warp == 1 ? 10 : (warp == 2 ? 16 : (warp == 3 ? 12 : 14))));
+      else {
+        // corner (dx,dy) by lane bits: the valid cell of the diagonal box, reached over two faces
+        const int cx = (lane & 1) ? 14 : 12, cy = (lane & 2) ? 16 : 10;
+        const int X = __ldg(nb + cx), Y = __ldg(nb + cy);
+        if (!BND) N = __ldg(a.nbr + (size_t)X * 27 + cy);
+        else if (X >= 0 && Y >= 0) { N = __ldg(a.nbr + (size_t)X * 27 + cy); ct = 0; }
+        else if (X >= 0) { N = X; ct = 1; }                  // y face missing: the x neighbour's ghost row
+        else if (Y >= 0) { N = Y; ct = 2; }                  // x face missing: the y neighbour's ghost column
+        else { N = 0; ct = 3; }                              // neither flank is computed: not needed
+      }
     }
-    const int kz = cls == 0 ? z + vz : (cls == 2 ? z - vz : z);
-    const long long prow = ((long long)(kz + 1) * N1 + 1) * V;      // first valid row of fab plane kz
+    const bool zmiss = BND && (S & 0x10000000);
+    const int kz = cls == 0 ? z + vz : (cls == 2 ? z - vz : z);           // plane of the source box (valid index)
+    // fab plane the tile is read from; a missing z face: the lower / upper GHOST plane of the box and of its
+    // in-plane neighbours (whose cells on that plane are the z neighbours of the flank cells), taken from
+    // the level-t ghosts for the inner halo plane and from the level-t+1 ghosts for the outer one
+    const int fp = !zmiss ? kz + 1 : (cls == 0 ? 0 : vz + 1);
+    const long long prow = ((long long)fp * N1 + 1) * V;            // first valid row of that fab plane
     double* dst = ring + (size_t)slot * SLOT;
-    const double* base = !(S & 0x40000000) ? a.in_level : ((S & 0x20000000) ? a.peer_in[1] : a.peer_in[0]);
+    const bool rem = (S & 0x40000000) != 0, ps1 = (S & 0x20000000) != 0;
+    // BND: the levels whose ghost cells are level t (g0) and level t+1 (g1), on the GPU that owns S
+    const double* g0 = !BND ? nullptr : (!rem ? a.ghost[0] : a.peer_ghost[ps1 ? 1 : 0][0]);
+    const double* g1 = !BND ? nullptr : (!rem ? a.ghost[1] : a.peer_ghost[ps1 ? 1 : 0][1]);
+    const double* base = zmiss ? ((tl == 1 || tl == vz + 2) ? g0 : g1)
+                               : (!rem ? a.in_level : (ps1 ? a.peer_in[1] : a.peer_in[0]));
     if (warp == 5) {
       if (lane < 4) {
-        const double* src = base + N * fabm + prow + (long long)((lane & 2) ? 0 : V - 1) * V + ((lane & 1) ? 0 : V - 1);
-        cp_async8(dst + E((lane & 1) ? 2 : 1) + ((lane & 2) ? V : -1), src);
+        const bool xh = lane & 1, yh = lane & 2;
+        const double* src = base + N * fabm + prow + (long long)(yh ? 0 : V - 1) * V + (xh ? 0 : V - 1);
+        if (BND && ct == 1) src = g0 + N * fabm + ((long long)fp * N1 + (yh ? N1 - 1 : 0)) * V + (xh ? 0 : V - 1);
+        if (BND && ct == 2)
+          src = g0 + a.xg_base + (long long)N * (2 * N1 * (vz + 2)) + ((long long)((xh ? 1 : 0) * (vz + 2) + fp)) * N1 + 1 +
+                (yh ? 0 : V - 1);
+        if (!BND || (ct != 3 && !zmiss)) cp_async8(dst + E(xh ? 2 : 1) + (yh ? V : -1), src);
         cp_async_arrive(full + slot);
       }
+    } else if (BND && warp >= 3) {
+      // x strips: the neighbour's edge strips (two bulk copies), or — no neighbour — the ghost columns of S
+      // itself in the two ghost levels, 8 bytes at a time (a ghost strip starts 8 bytes off a 16-byte
+      // boundary, which bulk copies cannot do)
+      const bool hi = warp == 4;
+      if (zmiss) {
+        // ghost plane: the x neighbour's ghost-plane column next to this box (not part of its edge strips)
+        if (N >= 0) {
+#pragma unroll
+          for (int h = 0; h < V / 32; ++h) {
+            const int y = lane + 32 * h;
+            cp_async8(dst + E(hi ? 2 : 1) + y, base + N * fabm + prow + (long long)y * V + (hi ? 0 : V - 1));
+          }
+        }
+      } else if (N >= 0) {
+        if (lane == 0) {
+          const double* e = base + a.xe_in + ((long long)N * vz + kz) * (4 * V) + (hi ? 0 : 2 * V);
+          mbar_expect_tx_only(full + slot, 2 * V * 8u);
+          bulk_g2s(dst + E(hi ? 2 : 0), e, V * 8u, full + slot);
+          bulk_g2s(dst + E(hi ? 3 : 1), e + V, V * 8u, full + slot);
+        }
+      } else {
+        const long long go = a.xg_base + (long long)(S & 0x0fffffff) * (2 * N1 * (vz + 2)) +
+                             ((long long)((hi ? 1 : 0) * (vz + 2) + fp)) * N1 + 1;
+#pragma unroll
+        for (int h = 0; h < V / 32; ++h) {
+          const int y = lane + 32 * h;
+          cp_async8(dst + E(hi ? 2 : 1) + y, g0 + go + y);      // level t ghosts at x = -1 / V
+          cp_async8(dst + E(hi ? 3 : 0) + y, g1 + go + y);      // level t+1 ghosts, in the unused outer strip
+        }
+      }
+      cp_async_arrive(full + slot);
     } else if (lane == 0) {
       if (warp == 0) {
-        mbar_expect_tx(full + slot, TILE_BYTES);                  // this warp's arrival + the tile's byte count
+        if (BND) mbar_expect_tx(full + slot, V * V * 8u);
+        else mbar_expect_tx(full + slot, TILE_BYTES);             // this warp's arrival + the tile's byte count
         bulk_g2s(dst + 2 * V, base + N * fabm + prow, V * V * 8u, full + slot);                           // rows 0..V-1
-      } else if (warp == 1) {
-        bulk_g2s(dst, base + N * fabm + prow + (long long)(V - 2) * V, 2 * V * 8u, full + slot);           // rows -2,-1
-      } else if (warp == 2) {
-        bulk_g2s(dst + (V + 2) * V, base + N * fabm + prow, 2 * V * 8u, full + slot);                      // rows V,V+1
+      } else if (warp == 1 || warp == 2) {
+        const bool hi = warp == 2;
+        if (BND) mbar_expect_tx_only(full + slot, 2 * V * 8u);
+        if (!BND || N >= 0) {
+          if (!hi) bulk_g2s(dst, base + N * fabm + prow + (long long)(V - 2) * V, 2 * V * 8u, full + slot);   // rows -2,-1
+          else bulk_g2s(dst + (V + 2) * V, base + N * fabm + prow, 2 * V * 8u, full + slot);                  // rows V,V+1
+        } else {
+          // no y neighbour: the ghost row of S in the level-t ghosts, and the level-t+1 ghosts in the outer row
+          const long long ro = (long long)(S & 0x0fffffff) * fabm + ((long long)fp * N1 + (hi ? N1 - 1 : 0)) * V;
+          bulk_g2s(dst + (hi ? (V + 2) * V : V), g0 + ro, V * 8u, full + slot);
+          bulk_g2s(dst + (hi ? (V + 3) * V : 0), g1 + ro, V * 8u, full + slot);
+        }
       } else {
         const double* e = base + a.xe_in + ((long long)N * vz + kz) * (4 * V);
         if (warp == 3) {
@@ -241,7 +319,17 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       else            { hc = (V + 2) * V + p; hym = (V + 1) * V + p; hyp = (V + 3) * V + p;                         // y = V
                         hxm = p > 0 ? hc - 1 : E(1) + V; hxp = p < V - 1 ? hc + 1 : E(2) + V; }
       const double zp = C[hc];
-      if (do1) Tw[hc] = heat_update<FMA>(hX, P[hxm], P[hxp], P[hym], P[hyp], hY, zp, f);
+      if (do1) {
+        double r = heat_update<FMA>(hX, P[hxm], P[hxp], P[hym], P[hyp], hY, zp, f);
+        if (BND) {
+          // no neighbour on this flank's side: the "flank" is this box's ghost cell; its level-t+1 value was
+          // brought in the slot of the outer halo layer
+          const int code = m < 2 ? 12 : (m < 4 ? 14 : (m < 6 ? 10 : 16));
+          const int alt = m < 2 ? E(0) + p : (m < 4 ? E(3) + p : (m < 6 ? p : (V + 3) * V + p));
+          if (__ldg(a.nbr + (size_t)box * 27 + code) < 0) r = P[alt];
+        }
+        Tw[hc] = r;
+      }
       hY = zp;
     }
     if (!do1) {
@@ -249,12 +337,21 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       for (int m = 0; m < CPT; ++m) Y[m] = C[oC0 + m * V];
     } else {
       // output plane inside the fab's valid region.  While the stages are being primed (do2 false) the
-      // stage-2 values are meaningless: they go to the fab's lower ghost plane (kz = -1; ghost cells are
-      // not read by this kernel and are rewritten by the exchange that follows the two-step phase) and
-      // to the spare strip plane behind the edge strips, which keeps the stores free of branches.
-      const int kz = do2 ? l - 4 : -1;
+      // stage-2 values are meaningless: they go to a scratch plane and a spare strip plane behind the edge
+      // strips, which keeps the stores free of branches.
+      const int kz = l - 4;
       // (xi, y0) of fab plane kz: fab-relative offset = tile offset + (N1 - 1) * V
-      double* __restrict__ po = a.out_level + box * fabm + (long long)kz * FABP + (oC0 + (N1 - 1) * V);
+      double* __restrict__ po = do2 ? a.out_level + box * fabm + (long long)kz * FABP + (oC0 + (N1 - 1) * V)
+                                    : a.out_level + a.dump + (oC0 - 2 * V);
+      // BND: a missing z face: level t+1 on the ghost plane below / above the box is not computed but is the
+      // ghost plane of the level-t+1 ghosts, which arrived as the tile of the outer halo plane: it sits in
+      // Y (plane z = -2, read two planes ago) resp. in the arriving tile (plane z = vz+1)
+      bool ovr_lo = false, ovr_hi = false;
+      if (BND && (l == 2 || l == vz + 3)) {
+        const bool hi = l != 2;
+        const bool miss = __ldg(a.nbr + (size_t)box * 27 + (hi ? 22 : 4)) < 0 && !(a.rz && __ldg(a.rz + 2 * box + (hi ? 1 : 0)) >= 0);
+        ovr_lo = miss && !hi; ovr_hi = miss && hi;
+      }
       const int xq = oC0 & (V - 1);                               // = xi; edge-strip index of this column, if any
       const int xs = xq == 0 ? 0 : (xq == 1 ? 1 : (xq == V - 2 ? 2 : (xq == V - 1 ? 3 : -1)));
       const long long eplane = do2 ? (long long)box * vz + kz : a.xe_spare_plane;
@@ -270,8 +367,9 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
       for (int m = 0; m < CPT; ++m) {
         const double zp = zpN, xm = xmN, xp = xpN;
         if (m < CPT - 1) { zpN = C[oC0 + (m + 1) * V]; xmN = lds64(pxm + (m + 1) * sxm); xpN = lds64(pxp + (m + 1) * sxp); }
-        const double r1 = heat_update<FMA>(X[m], xm, xp, m > 0 ? X[m - 1] : yfirst, m < CPT - 1 ? X[m + 1] : ylast,
-                                           Y[m], zp, f);
+        double r1 = heat_update<FMA>(X[m], xm, xp, m > 0 ? X[m - 1] : yfirst, m < CPT - 1 ? X[m + 1] : ylast,
+                                     Y[m], zp, f);
+        if (BND) r1 = ovr_lo ? Y[m] : (ovr_hi ? zp : r1);
         Y[m] = zp;
         Tw[oC0 + m * V] = r1;
         // stage 2
@@ -312,14 +410,21 @@ static int launch_t2_cfg(const T2Args& a, int fma, cudaStream_t s) {
   static_assert(smem <= 232448, "exceeds the 227 KB of shared memory a CTA can have");
   static bool configured = false;
   if (!configured) {
-    SGC_CUDA(cudaFuncSetAttribute(k_heat_t2<V, NS, NCW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SGC_CUDA(cudaFuncSetAttribute(k_heat_t2<V, NS, NCW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGC_CUDA(cudaFuncSetAttribute(k_heat_t2<V, NS, NCW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGC_CUDA(cudaFuncSetAttribute(k_heat_t2<V, NS, NCW, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGC_CUDA(cudaFuncSetAttribute(k_heat_t2<V, NS, NCW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGC_CUDA(cudaFuncSetAttribute(k_heat_t2<V, NS, NCW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   int grid = rt().sm_count;
   if (grid > a.nplanes / 8) grid = a.nplanes / 8 > 0 ? a.nplanes / 8 : 1;
-  if (fma) k_heat_t2<V, NS, NCW, true><<<grid, NCW * 32, smem, s>>>(a);
-  else k_heat_t2<V, NS, NCW, false><<<grid, NCW * 32, smem, s>>>(a);
+  if (a.ghost[0]) {          // levels with faces that have no neighbour (physical boundaries)
+    if (fma) k_heat_t2<V, NS, NCW, true, true><<<grid, NCW * 32, smem, s>>>(a);
+    else k_heat_t2<V, NS, NCW, false, true><<<grid, NCW * 32, smem, s>>>(a);
+  } else {
+    if (fma) k_heat_t2<V, NS, NCW, true, false><<<grid, NCW * 32, smem, s>>>(a);
+    else k_heat_t2<V, NS, NCW, false, false><<<grid, NCW * 32, smem, s>>>(a);
+  }
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
@@ -362,6 +467,8 @@ int launch_heat_t2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, const i
   if (np > 0x7fffffffLL) return 1;
   a.nplanes = (int)np;
   a.xe_spare_plane = (long long)u->nbox * g.vn[2];
+  a.dump = unew->xe_base + (a.xe_spare_plane + 1) * 4 * g.vn[1];     // scratch plane behind the spare strip plane
+  a.xg_base = u->xg_base;
   a.f = f;
   return launch_t2_cfg<64, 4, 16>(a, fma, s);
 }

@@ -90,6 +90,8 @@ def run_gpu(rank, world, local_rank):
     for dlo, dhi, mb, per, f, nstep in (((0, 0, 0), (31, 31, 32 * world - 1), (16, 16, 16), 7, 0.125, 12),
                                         ((0, 0, 0), (63, 63, 64 * world - 1), (64, 64, 64), 7, 1.0 / 6.0, 6),
                                         ((0, 0, 0), (127, 63, 128 * world - 1), (64, 64, 64), 7, 0.2, 11),
+                                        ((0, 0, 0), (127, 63, 128 * world - 1), (64, 64, 64), 3, 0.2, 10),   # z ends: physical
+                                        ((0, 0, 0), (63, 127, 64 * world - 1), (64, 64, 64), 0, 0.125, 9),    # no periodicity
                                         ((0, 0, 0), (63, 31, 64 * world - 1), (32, 32, 32), 3, 0.125, 9),
                                         ((0, 0, 0), (15, 15, 8 * world - 1), (8, 8, 8), 0, 0.125, 5),
                                         ((0, 0, 0), (11, 7, 10 * world - 1), (6, 4, 5), 3, 0.2, 4)):
@@ -119,7 +121,7 @@ def run_gpu(rank, world, local_rank):
         sgc.profile_enable(False)
         got = res.download()
         assert np.array_equal(got, want[goff[b0]:end]), ("heat_run", rank, mb)
-        if mb == (64, 64, 64) and per == 7 and os.environ.get("SGC_P2P", "1") != "0" and not os.environ.get("SGC_NO_T2"):
+        if mb == (64, 64, 64) and os.environ.get("SGC_P2P", "1") != "0" and not os.environ.get("SGC_NO_T2"):
             # the two-step passes pull their z tiles out of the neighbouring GPU's memory
             assert n2 == ((nstep - 2) // 2) & ~1, ("two-step passes", n2, nstep)
         if world > 1:

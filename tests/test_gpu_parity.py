@@ -344,17 +344,27 @@ def test_two_step_sweep_matches_oracle_and_step_by_step(g, oracle, monkeypatch):
     library's own step-by-step schedule, bit for bit, in both FMA modes; odd and even step counts,
     several boxes per direction, flat boxes (vz = 8)."""
     rng = np.random.default_rng(21)
-    cases = [((0, 0, 0), (63, 63, 63), (64, 64, 64), 0.125, 10, 1),       # one box, periodic onto itself
-             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 0.31, 7, 1),
-             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 1.0 / 6.0, 12, 0),
-             ((0, 0, 0), (191, 63, 127), (64, 64, 64), 0.2, 9, 1),
-             ((-64, 0, 8), (-1, 127, 23), (64, 64, 8), 0.2, 11, 0)]
-    for (dlo, dhi, mb, f, nstep, contract) in cases:
+    cases = [((0, 0, 0), (63, 63, 63), (64, 64, 64), 7, 0.125, 10, 1),       # one box, periodic onto itself
+             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 7, 0.31, 7, 1),
+             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 7, 1.0 / 6.0, 12, 0),
+             ((0, 0, 0), (191, 63, 127), (64, 64, 64), 7, 0.2, 9, 1),
+             ((-64, 0, 8), (-1, 127, 23), (64, 64, 8), 7, 0.2, 11, 0),
+             # physical boundaries (faces without a motion item keep their ghost cells, each level its own):
+             # none / some / all directions periodic, one and several boxes per direction
+             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 0, 0.2, 9, 1),
+             ((0, 0, 0), (191, 127, 63), (64, 64, 64), 0, 1.0 / 6.0, 8, 0),
+             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 3, 0.125, 10, 1),
+             ((0, 0, 0), (191, 127, 127), (64, 64, 64), 5, 0.3, 7, 1),
+             ((0, 0, 0), (127, 191, 15), (64, 64, 8), 6, 0.2, 11, 0),
+             ((0, 0, 0), (63, 63, 63), (64, 64, 64), 1, 0.2, 8, 1),
+             ((0, 0, 0), (127, 127, 63), (64, 64, 64), 2, 0.2, 8, 1),
+             ((0, 0, 0), (63, 127, 127), (64, 64, 64), 4, 0.2, 13, 1)]
+    for (dlo, dhi, mb, per, f, nstep, contract) in cases:
         dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
         b = g.LevelData(dbl, 1, 1)
         u0 = rng.standard_normal(a.elems)
         v0 = rng.standard_normal(a.elems)          # the second level starts with different ghosts
-        cp = g.Copier().defineExchangeLD(a, 7, 0)
+        cp = g.Copier().defineExchangeLD(a, per, 0)
         flags = g.SGC_FMA if contract else 0
         outs = []
         for no_t2 in (False, True):
@@ -373,20 +383,27 @@ def test_two_step_sweep_matches_oracle_and_step_by_step(g, oracle, monkeypatch):
             assert (res is b) == bool(nstep & 1)
             outs.append((a.download(), b.download()))
         monkeypatch.delenv("SGC_NO_T2", raising=False)
-        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (dhi, mb, "vs step-by-step")
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (dhi, mb, per, "vs step-by-step")
+        if per != 7:
+            # the oracle ping-pongs against a copy of ITS input level, ghosts included: give it equal ghosts
+            a.upload(u0); b.upload(u0)
+            outs[0] = None
+            res = g.heat_run(a, b, cp, f, nstep, flags)
+            outs[0] = (a.download(), b.download())
         want = u0.copy()
-        oracle.level_heat(dlo, dhi, mb, 1, 7, 0, f, nstep, want, contract)
+        oracle.level_heat(dlo, dhi, mb, 1, per, 0, f, nstep, want, contract)
         got = outs[0][1] if nstep & 1 else outs[0][0]
         # the oracle ping-pongs against a copy of the input level; ghost cells of the result level were
         # last written by the exchange two steps earlier, which both schedules reproduce — compare the
         # valid cells against the oracle and everything (above) against the step-by-step schedule
         assert np.array_equal(oracle.gather(dlo, dhi, dbl.boxes, 1, 1, 0, got),
-                              oracle.gather(dlo, dhi, dbl.boxes, 1, 1, 0, want)), (dhi, mb, "vs oracle")
+                              oracle.gather(dlo, dhi, dbl.boxes, 1, 1, 0, want)), (dhi, mb, per, "vs oracle")
 
 
-def test_two_step_sweep_not_used_without_all_neighbours(g, oracle):
-    """Non-periodic z: boxes at the domain boundary have no z neighbour, so sgc_heat_run must stay on
-    the one-step kernels (ghost cells carry the boundary values) and still match the oracle."""
+def test_two_step_sweep_physical_boundary_and_fallback(g, oracle):
+    """Non-periodic z: boxes at the domain boundary have no z neighbour; the two-step kernel's boundary
+    instance reads the (never exchanged) ghost planes instead — every cell of the result, ghost cells
+    included, equals the oracle's step-by-step run."""
     dlo, dhi, mb = (0, 0, 0), (127, 127, 127), (64, 64, 64)
     dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
     b = g.LevelData(dbl, 1, 1)
@@ -398,9 +415,25 @@ def test_two_step_sweep_not_used_without_all_neighbours(g, oracle):
     res = g.heat_run(a, b, cp, 0.125, 8)
     n2, _ = g.profile_read(2)
     g.profile_enable(False)
-    assert n2 == 0
+    assert n2 == 2
     want = u0.copy()
     oracle.level_heat(dlo, dhi, mb, 1, 3, 0, 0.125, 8, want, 1)
+    assert np.array_equal(res.download(), want)
+    # boxes with an odd number of planes are not covered either (CTA ranges start on even planes)
+    dlo, dhi, mb = (0, 0, 0), (63, 63, 13), (64, 64, 7)
+    dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
+    b = g.LevelData(dbl, 1, 1)
+    u0 = np.random.default_rng(24).standard_normal(a.elems)
+    a.upload(u0); b.upload(u0)
+    cp = g.Copier().defineExchangeLD(a, 7, 0)
+    g.profile_enable(True)
+    g.profile_read(2)
+    res = g.heat_run(a, b, cp, 0.2, 9)
+    n2, _ = g.profile_read(2)
+    g.profile_enable(False)
+    assert n2 == 0
+    want = u0.copy()
+    oracle.level_heat(dlo, dhi, mb, 1, 7, 0, 0.2, 9, want, 1)
     assert np.array_equal(res.download(), want)
 
 
