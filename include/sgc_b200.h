@@ -302,7 +302,7 @@ int sgc_wave_run(sgc_level_t levels[3], sgc_plan_t exchange_plan, sgc_plan_t bc_
  * (the shape of driverAdvanceIterGroup, WavePatch_Cuda.cu:352-378).  *result_in_b = 1 when the
  * last-written level is b (always nstep & 1).  With nproc > 1 each step overlaps the halo with
  * interior boxes.  The library is free to restructure the loop — fused ghost fill inside the sweep,
- * two time steps per pass over memory (uniform levels of 64x64xN boxes whose neighbours all exist),
+ * two time steps per pass over memory (uniform levels of 64x64xN boxes; periodic or physical boundaries),
  * z halos read straight out of the neighbouring GPU's memory — but on return BOTH levels hold, ghost
  * cells included, exactly the bits nstep x { exchange ; sweep } would have left (tests pin this).  */
 int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags,
