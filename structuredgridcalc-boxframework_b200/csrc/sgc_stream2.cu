@@ -10,28 +10,35 @@
 // inputs.
 //
 // Per box the CTA marches along z through VZ+4 "virtual planes" z = -2 .. VZ+1.  For every virtual
-// plane the producer assembles a TILE of level t in a ring slot — entirely from VALID cells (ghost
-// cells are never read, so no exchange is needed between the two steps or between passes):
+// plane a TILE of level t is assembled in a ring slot — entirely from VALID cells (ghost cells are
+// not read where a neighbour exists, so no exchange is needed between the two steps or between passes):
 //     rows y = -2..V+1 of the V valid columns      (own valid rows + 2 rows of each y neighbour)
 //     x strips x = -2,-1,V,V+1 for y = 0..V-1      (the x neighbours' EDGE STRIPS, see below)
-//     the 4 corner cells (-1|V, -1|V)              (the xy-diagonal neighbours; plain loads)
+//     the 4 corner cells (-1|V, -1|V)              (the xy-diagonal neighbours; 8-byte cp.async)
 //   planes z < 0 / z >= VZ are the same tile of the z neighbour (a local fab or, on a z-slab
 //   partition, a fab in the neighbouring GPU's memory over NVLink, gated by its progress counter).
-// Consumers (NCW warps, thread = one x and CPT consecutive rows, all state in registers):
-//   stage 1: t+1 on plane z-1 for the V x V cells; the extra "halo warp" computes t+1 on the four
-//            1-cell-wide flanks (x = -1, V and y = -1, V) — the values the x / y neighbours would
-//            have exchanged.  Results go to registers (z neighbours of stage 2) and to one of two
-//            t+1 plane buffers in shared memory (x / y neighbours of stage 2).
+//   Faces WITHOUT a neighbour (physical boundaries; template flag BND) read the box's own, never
+//   exchanged ghost cells instead — see the comment at the producer roles.
+// All NCW warps are consumers (thread = one x and CPT consecutive rows, all state in registers);
+// six of them also bring in one piece of each tile, the upper half also computes the flanks:
+//   stage 1: t+1 on plane z-1 for the V x V cells and for the four 1-cell-wide flanks (x = -1, V and
+//            y = -1, V) — the values the x / y neighbours would have exchanged.  Results go to
+//            registers (z neighbours of stage 2) and to one of two t+1 plane buffers in shared
+//            memory (x / y neighbours of stage 2).
 //   stage 2: t+2 on plane z-2 from the t+1 planes z-3, z-2, z-1; stored as dense rows.
-//   One named barrier per plane orders the t+1 buffer hand-over between the warps.
+//   One __syncthreads() per plane orders the t+1 buffer hand-over between the warps.
 // EDGE STRIPS (xe): a per-level side array [box][kz][4][V] holding copies of the box's own columns
 // x = 0, 1, V-2, V-1, written by stage 2 straight from the result registers (and built once per
 // sgc_heat_run by k_build_xe).  Reading a neighbour's edge column out of its main block would
 // fetch one 32-byte sector per 8-byte value; the strips make the x halo dense.
 //
 // HBM traffic per plane pass (V = 64): 36.9 KB tile + 32 KB rows + 2 KB strips for TWO cell-updates
-// of 4096 cells = 8.7 B per cell-update (x (VZ+4)/VZ for the z overlap) against 16.8 B for the
-// one-step sweep; the algorithmic figure stays 16 B per cell-update.
+// of 4096 cells = 8.7 B per cell-update (x (VZ+4)/VZ for the z overlap; ncu: 9.1 B) against 16.8 B
+// for the one-step sweep; the algorithmic figure stays 16 B per cell-update.
+//
+// The kernel uses the whole register file (128 x 512) without spilling and is bound by instruction
+// issue / FP64 latency, not HBM; its speed is sensitive to anything that costs a register (DESIGN.md
+// §4.1d has the history; profiles/micro/ab.sh times variants on one GPU).
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
