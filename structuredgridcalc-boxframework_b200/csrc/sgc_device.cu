@@ -437,6 +437,16 @@ void* sgc_level_device_ptr(sgc_level_t l, int box) {
   return (char*)l->d_arena + l->geom[box].off * l->esz;     // main block of the fab (split-x layout)
 }
 
+// whole level between a reference-order staging buffer and the arena: the row kernel for uniform levels of
+// 8-byte elements with one ghost column per side, the item tables otherwise
+static int convert_level(sgc_level_s* l, void* stage, bool to_arena, cudaStream_t s) {
+  const FabGeom& g = l->geom[0];
+  if (l->uniform && l->esz == 8 && l->ng >= 1 && g.ngx == 1 && g.mx >= 1)
+    return launch_convert_level(l->d_arena, stage, (long long)l->nbox * l->ncomp * g.n[2] * g.n[1], g.mx, g.n[1], g.n[2],
+                                l->ncomp, l->xg_base, to_arena, s);
+  return to_arena ? launch_copy(l->conv_in, l->d_arena, stage, l->esz, s) : launch_copy(l->conv_out, stage, l->d_arena, l->esz, s);
+}
+
 static int ensure_stage(size_t bytes) {
   Runtime& r = rt();
   if (r.stage_bytes >= bytes) return 0;
@@ -472,7 +482,7 @@ int sgc_level_upload(sgc_level_t l, int box, const void* host) {
   if (st) return st;
   // H2D in the reference's memory order, then one batched kernel into the split-x arena
   SGC_CUDA(cudaMemcpyAsync(rt().d_stage, host, (size_t)n * l->esz, cudaMemcpyHostToDevice, rt().compute));
-  if (box < 0) return launch_copy(l->conv_in, l->d_arena, rt().d_stage, l->esz, rt().compute);
+  if (box < 0) return convert_level(l, rt().d_stage, true, rt().compute);
   return convert_box(l, box, rt().d_stage, true);
 }
 
@@ -482,7 +492,7 @@ int sgc_level_download(sgc_level_t l, int box, void* host) {
   const long long n = box < 0 ? l->elems : (long long)l->geom[box].n[0] * l->geom[box].n[1] * l->geom[box].n[2] * l->ncomp;
   int st = ensure_stage((size_t)n * l->esz);
   if (st) return st;
-  st = box < 0 ? launch_copy(l->conv_out, rt().d_stage, l->d_arena, l->esz, rt().compute)
+  st = box < 0 ? convert_level(l, rt().d_stage, false, rt().compute)
                : convert_box(l, box, rt().d_stage, false);
   if (st) return st;
   SGC_CUDA(cudaMemcpyAsync(host, rt().d_stage, (size_t)n * l->esz, cudaMemcpyDeviceToHost, rt().compute));
@@ -549,7 +559,7 @@ int sgc_level_upload_async(sgc_level_t l, const void* host, sgc_stream_t x) {
   int st = stream_stage(x, bytes);
   if (st) return st;
   SGC_CUDA(cudaMemcpyAsync(x->d_stage, host, bytes, cudaMemcpyHostToDevice, x->s));
-  return launch_copy(l->conv_in, l->d_arena, x->d_stage, l->esz, x->s);
+  return convert_level(l, x->d_stage, true, x->s);
 }
 
 int sgc_level_download_async(sgc_level_t l, void* host, sgc_stream_t x, sgc_event_t gathered) {
@@ -557,7 +567,7 @@ int sgc_level_download_async(sgc_level_t l, void* host, sgc_stream_t x, sgc_even
   if (!l || !host || !x) return fail(SGC_ERR_ARG, "sgc_level_download_async: bad argument");
   const size_t bytes = (size_t)l->elems * l->esz;
   int st = stream_stage(x, bytes);
-  if (!st) st = launch_copy(l->conv_out, x->d_stage, l->d_arena, l->esz, x->s);
+  if (!st) st = convert_level(l, x->d_stage, false, x->s);
   if (st) return st;
   if (gathered) SGC_CUDA(cudaEventRecord(gathered->ev, x->s));
   SGC_CUDA(cudaMemcpyAsync(host, x->d_stage, bytes, cudaMemcpyDeviceToHost, x->s));

@@ -170,6 +170,8 @@ struct T2Args {
 // launchers implemented in sgc_kernels.cu
 int launch_copy(const CopyTable& t, void* dst_arena, const void* src_arena, int esz, cudaStream_t s);
 int launch_fill(void* p, long long n, int esz, const void* value, cudaStream_t s);
+int launch_convert_level(void* arena, void* stage, long long nrows, int mx, int n1, int n2, int ncomp, long long xg_base,
+                         bool to_arena, cudaStream_t s);
 int launch_fill_fabs(void* arena, const FabGeom* d_geom, int nbox, long long max_elems, int c0, int nc, int esz,
                      const void* value, cudaStream_t s);
 

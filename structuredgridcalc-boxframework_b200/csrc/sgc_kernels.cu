@@ -264,4 +264,54 @@ int launch_wave_generic(const int* d_work, int w0, int nwork, const FabGeom* gin
 int sweep_tile_y() { return kTileY; }
 int sweep_tile_z() { return kTileZ; }
 
+
+// ---------------------------------------------------------------------------------------------
+// Whole-level layout conversion for uniform levels of 8-byte elements with one ghost column per side:
+// reference order (rows of n0 = mx + 2 elements) <-> split-x arena (dense rows of mx elements + the two
+// x-ghost strips).  One warp per row: the row is read once, fully coalesced, and every element goes to its
+// place — the generic item kernel reads the two ghost columns as 8-byte elements of 528-byte rows (a 32-byte
+// sector each).  Rows are numbered (fab, comp, k, j) in memory order of both layouts.
+// ---------------------------------------------------------------------------------------------
+template <bool TO_ARENA>
+__global__ void __launch_bounds__(256)
+k_convert_rows(double* __restrict__ arena, double* __restrict__ stage, long long nrows, int mx, int n1, int n2, int ncomp,
+               long long xg_base) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int n0 = mx + 2;
+  const long long rows_per_fab = (long long)ncomp * n2 * n1;
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
+    const long long fab = r / rows_per_fab;
+    const long long q = r - fab * rows_per_fab;            // (comp, k, j) flattened
+    const int c = (int)(q / ((long long)n2 * n1));
+    const long long kj = q - (long long)c * n2 * n1;       // k * n1 + j
+    double* srow = stage + r * n0;                         // reference order: the rows follow each other
+    double* mrow = arena + r * mx;                         // main blocks: same order, dense rows
+    // xg block of the fab: [comp][side][k][j]
+    double* xlo = arena + xg_base + (fab * ncomp + c) * (2LL * n2 * n1) + kj;
+    double* xhi = xlo + (long long)n2 * n1;
+    if (TO_ARENA) {
+      for (int i = lane; i < n0; i += 32) {
+        const double v = srow[i];
+        if (i == 0) *xlo = v; else if (i == n0 - 1) *xhi = v; else mrow[i - 1] = v;
+      }
+    } else {
+      for (int i = lane; i < n0; i += 32) srow[i] = i == 0 ? *xlo : (i == n0 - 1 ? *xhi : mrow[i - 1]);
+    }
+  }
+}
+
+// 0 = done, 1 = geometry not covered (caller uses the item tables)
+int launch_convert_level(void* arena, void* stage, long long nrows, int mx, int n1, int n2, int ncomp, long long xg_base,
+                         bool to_arena, cudaStream_t s) {
+  const int wpb = 8;
+  long long blocks = (nrows + wpb - 1) / wpb;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  if (to_arena) k_convert_rows<true><<<(unsigned)blocks, wpb * 32, 0, s>>>((double*)arena, (double*)stage, nrows, mx, n1, n2, ncomp, xg_base);
+  else k_convert_rows<false><<<(unsigned)blocks, wpb * 32, 0, s>>>((double*)arena, (double*)stage, nrows, mx, n1, n2, ncomp, xg_base);
+  rt().launches++;
+  SGC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace sgc
