@@ -213,9 +213,26 @@ k_lb_stream_moments(const FabGeom* __restrict__ gf, const FabGeom* __restrict__ 
     const int r = t / F.vn[0];
     const int j = r % F.vn[1], k = r / F.vn[1];
     double f[kQ], m[kMacro];
+    // source of direction q = the cell at -e_q.  With one ghost column per side it lies in the main block at
+    // a fixed offset from this cell, except across the box's x faces (first / last column and e_x = +-1),
+    // where it is in the x-ghost strip; the lattice vectors are compile-time constants after unrolling, so
+    // the 9 directions with e_x = 0 cost one add each (the generic fab_index costs ~10 instructions).
+    const long long c0 = F.off + ((long long)(k + oz) * F.n[1] + (j + oy)) * F.mx + (i + ox - F.ngx);
+    const bool fast = F.ngx == 1 && ox == 1;
+    const bool xlo = i == 0, xhi = i == F.vn[0] - 1;
+    auto source = [&](int q) -> long long {
+      constexpr int E[kQ][3] = {{0, 0, 0},   {-1, 0, 0}, {1, 0, 0},  {0, -1, 0}, {0, 1, 0},   {0, 0, -1}, {0, 0, 1},
+                                {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0},  {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1},
+                                {1, 0, 1},   {0, -1, -1}, {0, 1, -1}, {0, -1, 1}, {0, 1, 1}};     // = c_e
+      const int e0 = E[q][0], e1 = E[q][1], e2 = E[q][2];
+      if (!fast) return fab_index(F, i + ox - e0, j + oy - e1, k + oz - e2, q);
+      long long src = c0 + q * F.cs - (e0 + (long long)e1 * F.mx + (long long)e2 * F.mx * F.n[1]);
+      if (e0 != 0 && (e0 > 0 ? xlo : xhi))
+        src = F.xoff + q * F.xcs + ((long long)(e0 > 0 ? 0 : F.n[2]) + (k + oz - e2)) * F.n[1] + (j + oy - e1);
+      return src;
+    };
 #pragma unroll
-    for (int q = 0; q < kQ; ++q)
-      f[q] = cur[fab_index(F, i + ox - c_e[q][0], j + oy - c_e[q][1], k + oz - c_e[q][2], q)];
+    for (int q = 0; q < kQ; ++q) f[q] = cur[source(q)];
     moments_cell(f, m);
     const long long cm = fab_index(M, i + ox, j + oy, k + oz, 0);
 #pragma unroll
@@ -225,12 +242,11 @@ k_lb_stream_moments(const FabGeom* __restrict__ gf, const FabGeom* __restrict__ 
       collide_cell<false>(f, m[0], m[1], m[2], m[3], bad);
       if (bad) {                                 // an operand outside the proven range: real divisions
 #pragma unroll
-        for (int q = 0; q < kQ; ++q)
-          f[q] = cur[fab_index(F, i + ox - c_e[q][0], j + oy - c_e[q][1], k + oz - c_e[q][2], q)];
+        for (int q = 0; q < kQ; ++q) f[q] = cur[source(q)];
         collide_cell<true>(f, m[0], m[1], m[2], m[3], bad);
       }
     }
-    const long long cf = fab_index(F, i + ox, j + oy, k + oz, 0);
+    const long long cf = fast ? c0 : fab_index(F, i + ox, j + oy, k + oz, 0);
 #pragma unroll
     for (int q = 0; q < kQ; ++q) nxt[cf + q * F.cs] = f[q];
   }
