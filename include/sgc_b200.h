@@ -137,6 +137,15 @@ int sgc_layout_define(const int dlo[3], const int dhi[3], const int maxbox[3], i
 /* Copier::defineExchangeDBL (Copier.H:521-659) as seen by rank `rank` of `nproc`: motion
  * items in the reference's order (per local box: interior neighbours in x-fastest [-1,1]^3
  * order, then periodic images).  Writes up to cap items; returns the item count.  Needs no GPU. */
+/* Which device-resident step loops sgc_heat_run may use for rank `rank`'s part of this layout and exchange
+ * (host only; the level's box shape decides on top of it): a mask of               */
+#define SGC_LOOP_FUSED 1            /* ghost fill fused into the one-step sweep                             */
+#define SGC_LOOP_TWO_STEP_LOCAL 2   /* two steps per pass; every neighbour the kernel reads is on this rank  */
+#define SGC_LOOP_TWO_STEP_SLAB 4    /* ... z neighbours may be on another rank (read over NVLink)            */
+#define SGC_LOOP_TWO_STEP_BND 8     /* ... some faces have no motion item (physical boundary / trimmed)      */
+int sgc_step_loop_class(const int dlo[3], const int dhi[3], const int maxbox[3], int nghost,
+                        unsigned periodic, unsigned trim, int nproc, int rank);
+
 int sgc_copier_define(const int dlo[3], const int dhi[3], const int maxbox[3], int nghost,
                       unsigned periodic, unsigned trim, int nproc, int rank,
                       sgc_motion_item* items, int cap);

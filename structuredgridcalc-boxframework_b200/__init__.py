@@ -30,7 +30,7 @@ SYMBOLS = [
     "sgc_plan_create_exchange", "sgc_plan_create_items", "sgc_plan_destroy", "sgc_plan_num_items",
     "sgc_plan_num_remote_items", "sgc_plan_num_cells", "sgc_exchange", "sgc_exchange_begin", "sgc_exchange_end",
     "sgc_plan_create_bc_zero_gradient", "sgc_heat_sweep", "sgc_heat_sweep_range", "sgc_heat_sweep_ranges", "sgc_laplacian_apply",
-    "sgc_wave_step", "sgc_wave_run", "sgc_heat_run", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
+    "sgc_wave_step", "sgc_wave_run", "sgc_heat_run", "sgc_step_loop_class", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
     "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
     "sgc_level_upload_async", "sgc_level_download_async", "sgc_copyset_create", "sgc_copyset_run", "sgc_copyset_destroy",
     "sgc_copyset_num_cells", "sgc_level_valid_elems", "sgc_level_download_valid", "sgc_level_download_valid_async", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run", "sgc_lb_selftest_divconst",
@@ -94,6 +94,7 @@ def lib():
     L.sgc_device_info.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
     L.sgc_layout_define.argtypes = [_i3, _i3, _i3, C.c_int, C.c_void_p, C.c_void_p, C.c_int, _i3]
     L.sgc_copier_define.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.sgc_step_loop_class.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int]
     L.sgc_halo_describe.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_int), C.c_void_p, C.c_int]
     L.sgc_level_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -540,6 +541,18 @@ def wave_run(levels, copier, bc, factor, nstep, flags=SGC_FMA):
     latest = (C.c_int * 3)()
     check(lib().sgc_wave_run(hs, copier.h if copier else None, bc.h if bc else None, factor, flags, nstep, latest))
     return tuple(levels[i] for i in latest)
+
+
+LOOP_FUSED, LOOP_TWO_STEP_LOCAL, LOOP_TWO_STEP_SLAB, LOOP_TWO_STEP_BND = 1, 2, 4, 8
+
+
+def step_loop_class(dlo, dhi, maxbox, nghost=1, periodic=7, trim=0, nproc=1, rank=0):
+    """Mask of LOOP_* bits: the device-resident step loops the exchange plan of this layout admits (host only)."""
+    mb = (maxbox,) * 3 if np.isscalar(maxbox) else maxbox
+    r = lib().sgc_step_loop_class(_i3(*dlo), _i3(*dhi), _i3(*mb), nghost, periodic, trim, nproc, rank)
+    if r < 0:
+        check(r)
+    return r
 
 
 def heat_run(a, b, copier, f, nstep, flags=SGC_FMA):

@@ -252,6 +252,22 @@ int comm_p2p_check(sgc_plan_s* p) {
   return 0;
 }
 
+// min over all ranks of a small integer (collective; used to take the same code path everywhere)
+int comm_all_min(int v, int* out) {
+  Comm& c = cm();
+  *out = v;
+  if (!c.ready || c.nproc < 2) return 0;
+  Runtime& r = rt();
+  int* d = nullptr;
+  SGC_CUDA(cudaMalloc(&d, 256));
+  SGC_CUDA(cudaMemcpy(d, &v, sizeof v, cudaMemcpyHostToDevice));
+  SGC_NCCL(c.api.AllReduce(d, d, 1, ncclInt, ncclMin, c.comm, r.comm));
+  SGC_CUDA(cudaStreamSynchronize(r.comm));
+  SGC_CUDA(cudaMemcpy(out, d, sizeof v, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
+
 // Returns 0 when the call went through (p->p2p.ready tells whether the session is usable on EVERY
 // rank — decided by an all-reduce, so all ranks take the same path); < 0 on hard errors.
 int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {

@@ -34,6 +34,7 @@ int comm_p2p_setup(sgc_plan_s* plan, sgc_level_s* a, sgc_level_s* b);
 void comm_p2p_release(sgc_plan_s* plan);
 int comm_p2p_signal(sgc_plan_s* plan, unsigned long long value, cudaStream_t s);
 int comm_p2p_check(sgc_plan_s* plan);
+int comm_all_min(int v, int* out);
 bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u);
 bool heat_t2_covers(const sgc_level_s* unew, const sgc_level_s* u);
 int launch_build_xe(sgc_level_s* l, cudaStream_t s);
@@ -853,52 +854,16 @@ int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], 
   if (!st) st = upload_local_items(p, l);
   if (!st && p->nremote > 0) st = comm_plan_setup(p, l, g, periodic, trim);
   if (!st && l->ng == 1 && l->ncomp == 1 && comp_begin == 0 && ncomp == 1 && l->uniform && l->esz == 8) {
-    // direction table for the fused sweep: the box S that a motion item reads from pushes into the
-    // box D that receives, in direction S -> D = -(item direction)
-    std::vector<int> nbr((size_t)l->nbox * 27, -1);
-    for (const sgc_motion_item& it : p->items) {
-      if (it.recv_proc != it.send_proc) continue;
-      const int S = it.send_box - l->gidx0, D = it.recv_box - l->gidx0;
-      const int code = (1 - it.dir[0]) + 3 * (1 - it.dir[1]) + 9 * (1 - it.dir[2]);
-      nbr[(size_t)S * 27 + code] = D;
-    }
+    // neighbour table of the fused / two-step sweeps and the step loops the plan admits (sgc_plan.cpp)
+    std::vector<int> nbr;
+    const int loops = classify_step_loops(p->items, l->nbox, l->gidx0, nbr);
     cudaError_t e = st ? cudaErrorUnknown : cudaMalloc(&p->d_push, sizeof(int) * nbr.size());
     if (e == cudaSuccess) e = cudaMemcpy(p->d_push, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess && !st) st = fail(SGC_ERR_CUDA, std::string("push table: ") + cudaGetErrorString(e));
     p->fusable = (st == 0);
-    // two-step sweep: the 8 in-plane neighbours must be local boxes; z neighbours local, or remote
-    // on a z-slab partition (then the plan has remote items and the peer-memory session decides)
-    // Two-step sweep (sgc_stream2.cu).  t2_local: every box has its 8 in-plane neighbours and both z
-    // neighbours locally; t2_slab: the z neighbours may live on another rank (peer memory).  t2_bnd: some
-    // FACES have no motion item at all — a physical boundary or a trimmed direction, whose ghost cells the
-    // exchange never writes — which the kernel's boundary instance handles; what it cannot handle is an
-    // in-plane neighbour on another rank, or a diagonal box missing although both faces towards it exist.
-    std::vector<char> cover((size_t)l->nbox * 27, 0);   // (box, direction) has a face item, local or remote
-    for (const sgc_motion_item& it : p->items)
-      if (abs(it.dir[0]) + abs(it.dir[1]) + abs(it.dir[2]) == 1)
-        cover[(size_t)(it.recv_box - l->gidx0) * 27 + 13 + it.dir[0] + 3 * it.dir[1] + 9 * it.dir[2]] = 1;
-    bool ok = p->fusable, all_inplane = true, all_z_local = true, all_z = true;
-    for (int b = 0; b < l->nbox && ok; ++b) {
-      const int* nb = nbr.data() + (size_t)b * 27;
-      const char* cv = cover.data() + (size_t)b * 27;
-      for (int d = 0; d < 2 && ok; ++d)
-        for (int sgn = -1; sgn <= 1; sgn += 2) {
-          const int code = 13 + sgn * (d == 0 ? 1 : 3);
-          if (nb[code] < 0) { all_inplane = false; if (cv[code]) ok = false; }     // covered but not local: another rank
-        }
-      for (int sy = -1; sy <= 1 && ok; sy += 2)
-        for (int sx = -1; sx <= 1; sx += 2) {
-          const int X = nb[13 + sx], Y = nb[13 + 3 * sy];
-          if (X >= 0 && Y >= 0 && nbr[(size_t)X * 27 + 13 + 3 * sy] < 0) ok = false;   // diagonal box over two faces
-        }
-      for (int sgn = -1; sgn <= 1; sgn += 2) {
-        const int code = 13 + 9 * sgn;
-        if (nb[code] < 0) { all_z_local = false; if (!cv[code]) all_z = false; }
-      }
-    }
-    p->t2_local = ok && all_inplane && all_z_local;
-    p->t2_slab = ok && all_inplane && all_z;
-    p->t2_bnd = ok && !(all_inplane && all_z);
+    p->t2_local = p->fusable && (loops & SGC_LOOP_TWO_STEP_LOCAL);
+    p->t2_slab = p->fusable && (loops & SGC_LOOP_TWO_STEP_SLAB);
+    p->t2_bnd = p->fusable && (loops & SGC_LOOP_TWO_STEP_BND);
   }
   if (st) { sgc_plan_destroy(p); return st; }
   *plan = p;
@@ -1167,7 +1132,19 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
     // the result in the level the step-by-step schedule would leave it in.
     const int npass = ((nstep - 2) / 2) & ~1;
     const bool t2_remote_ok = plan->nremote == 0 || p2p;          // remote z faces need the peer-memory session
-    if (npass >= 2 && heat_t2_covers(b, a) && (plan->t2_local || ((plan->t2_slab || plan->t2_bnd) && t2_remote_ok))) {
+    bool t2 = heat_t2_covers(b, a) && (plan->t2_local || ((plan->t2_slab || plan->t2_bnd) && t2_remote_ok));
+    if (plan->nremote > 0) {
+      // ranks may classify differently (the end ranks of a non-periodic slab partition see physical faces,
+      // the others do not); the passes signal each other, so all ranks run them or none does
+      if (plan->t2_agreed < 0) {
+        int all = 0;
+        st = comm_all_min(t2 ? 1 : 0, &all);
+        if (st) return st;
+        plan->t2_agreed = all;
+      }
+      t2 = t2 && plan->t2_agreed == 1;
+    }
+    if (npass >= 2 && t2) {
       sgc_plan_s::P2P& S = plan->p2p;
       st = launch_build_xe(cur, rt().compute);
       if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);     // our strips are readable

@@ -238,6 +238,7 @@ struct sgc_plan_s {
   // two z neighbours locally (t2_local) or at least in the plan (t2_slab: the missing ones are remote)
   bool t2_local = false, t2_slab = false;
   bool t2_bnd = false;                  // as t2_slab, but some faces have no motion item at all (physical boundary)
+  int t2_agreed = -1;                   // multi-rank: every rank can run the two-step passes (-1: not asked yet)
   // peer-memory halo session (sgc_comm.cu): the two ping-pong levels of a step loop, their arenas on
   // the z neighbours mapped through cudaIpc, and progress counters
   struct P2P {

@@ -63,6 +63,11 @@ struct Grid {
 int build_exchange_items(const Grid& g, int ng, unsigned periodic, unsigned trim, int rank,
                          std::vector<sgc_motion_item>& out);
 
+// Which device-resident step loops a rank's exchange plan admits (host only).  Fills `nbr`, the table
+// [nbox][27] of the LOCAL box in direction code 13 + dx + 3 dy + 9 dz of each local box (-1: none, or owned
+// by another rank), and returns a mask of SGC_LOOP_* bits (sgc_b200.h).
+int classify_step_loops(const std::vector<sgc_motion_item>& items, int nbox, int gidx0, std::vector<int>& nbr);
+
 void set_error(const std::string& msg);
 int fail(int status, const std::string& msg);
 

@@ -126,6 +126,51 @@ int build_exchange_items(const Grid& g, int ng, unsigned periodic, unsigned trim
   return 0;
 }
 
+
+// The fused one-step sweep (sgc_stream.cu) works from the neighbour table alone.  The two-step sweep
+// (sgc_stream2.cu) needs more: LOCAL — every box has its 8 in-plane neighbours and both z neighbours on this
+// rank; SLAB — the z neighbours may live on another rank (peer memory); BND — some FACES have no motion item
+// at all (a physical boundary or a trimmed direction, whose ghost cells the exchange never writes), which the
+// kernel's boundary instance handles.  What it cannot handle is an in-plane neighbour on another rank, or a
+// diagonal box missing although both faces towards it exist.
+int classify_step_loops(const std::vector<sgc_motion_item>& items, int nbox, int gidx0, std::vector<int>& nbr) {
+  nbr.assign((size_t)nbox * 27, -1);
+  std::vector<char> cover((size_t)nbox * 27, 0);      // (box, face direction) has a motion item, local or remote
+  for (const sgc_motion_item& it : items) {
+    const int D = it.recv_box - gidx0;
+    if (abs(it.dir[0]) + abs(it.dir[1]) + abs(it.dir[2]) == 1) cover[(size_t)D * 27 + 13 + it.dir[0] + 3 * it.dir[1] + 9 * it.dir[2]] = 1;
+    if (it.recv_proc != it.send_proc) continue;
+    // the box S an item reads from sits, seen from the receiving box D, in the item's direction; seen from S,
+    // D sits in the opposite one
+    const int S = it.send_box - gidx0;
+    nbr[(size_t)S * 27 + (1 - it.dir[0]) + 3 * (1 - it.dir[1]) + 9 * (1 - it.dir[2])] = D;
+  }
+  bool ok = true, all_inplane = true, all_z_local = true, all_z = true;
+  for (int b = 0; b < nbox && ok; ++b) {
+    const int* nb = nbr.data() + (size_t)b * 27;
+    const char* cv = cover.data() + (size_t)b * 27;
+    for (int d = 0; d < 2 && ok; ++d)
+      for (int sgn = -1; sgn <= 1; sgn += 2) {
+        const int code = 13 + sgn * (d == 0 ? 1 : 3);
+        if (nb[code] < 0) { all_inplane = false; if (cv[code]) ok = false; }     // covered but not local: another rank
+      }
+    for (int sy = -1; sy <= 1 && ok; sy += 2)
+      for (int sx = -1; sx <= 1; sx += 2) {
+        const int X = nb[13 + sx], Y = nb[13 + 3 * sy];
+        if (X >= 0 && Y >= 0 && nbr[(size_t)X * 27 + 13 + 3 * sy] < 0) ok = false;   // diagonal box over two faces
+      }
+    for (int sgn = -1; sgn <= 1; sgn += 2) {
+      const int code = 13 + 9 * sgn;
+      if (nb[code] < 0) { all_z_local = false; if (!cv[code]) all_z = false; }
+    }
+  }
+  int mask = SGC_LOOP_FUSED;
+  if (ok && all_inplane && all_z_local) mask |= SGC_LOOP_TWO_STEP_LOCAL;
+  if (ok && all_inplane && all_z) mask |= SGC_LOOP_TWO_STEP_SLAB;
+  if (ok && !(all_inplane && all_z)) mask |= SGC_LOOP_TWO_STEP_BND;
+  return mask;
+}
+
 }  // namespace sgc
 
 extern "C" {
@@ -159,6 +204,18 @@ int sgc_copier_define(const int dlo[3], const int dhi[3], const int maxbox[3], i
   if (st) return st;
   for (size_t i = 0; i < v.size() && (int)i < cap; ++i) items[i] = v[i];
   return (int)v.size();
+}
+
+int sgc_step_loop_class(const int dlo[3], const int dhi[3], const int maxbox[3], int nghost, unsigned periodic,
+                        unsigned trim, int nproc, int rank) {
+  if (!dlo || !dhi || !maxbox) return sgc::fail(SGC_ERR_ARG, "sgc_step_loop_class: null argument");
+  sgc::Grid g(dlo, dhi, maxbox, nproc);
+  if (g.status) return sgc::fail(SGC_ERR_ARG, "sgc_step_loop_class: boxes must tile the domain and divide among ranks");
+  std::vector<sgc_motion_item> v;
+  const int st = sgc::build_exchange_items(g, nghost, periodic, trim, rank, v);
+  if (st) return st;
+  std::vector<int> nbr;
+  return sgc::classify_step_loops(v, g.bpp, rank * g.bpp, nbr);
 }
 
 }  // extern "C"

@@ -121,3 +121,34 @@ def test_halo_lists_pair_up_across_ranks(sgc):
                     assert np.array_equal(send, precv)       # same items, same order
                     assert np.array_equal(recv, psend)
                     assert (recv["send_proc"] == peer).all() and (recv["recv_proc"] == r).all()
+
+
+def test_step_loop_classification(sgc):
+    """Which device-resident step loops a plan admits (sgc_plan.cpp: classify_step_loops; host only).  The
+    two-step sweep reads its halo from the neighbours' VALID cells: it needs the in-plane neighbours on the same
+    rank; z neighbours may be remote (slab partitions); faces without any motion item (physical boundary or
+    trimmed) are handled by the boundary instance; edge / corner items are not needed at all."""
+    F, LOCAL, SLAB, BND = sgc.LOOP_FUSED, sgc.LOOP_TWO_STEP_LOCAL, sgc.LOOP_TWO_STEP_SLAB, sgc.LOOP_TWO_STEP_BND
+    dlo, dhi = (0, 0, 0), (127, 127, 255)
+    PX, PY, PZ = 1, 2, 4                       # LayoutIterator.H:35-41
+    TRIM_FACE, TRIM_EDGE, TRIM_CORNER = 2, 4, 8
+    # fully periodic, one rank: everything local
+    assert sgc.step_loop_class(dlo, dhi, 64, 1, 7, 0) == F | LOCAL | SLAB
+    # one box, periodic onto itself
+    assert sgc.step_loop_class((0, 0, 0), (63, 63, 63), 64, 1, 7, 0) == F | LOCAL | SLAB
+    # physical boundaries in some / all directions: the boundary instance, never the plain ones
+    for per in (0, PX, PY, PZ, PX | PY, PX | PZ, PY | PZ):
+        assert sgc.step_loop_class(dlo, dhi, 64, 1, per, 0) == F | BND, per
+    # edge / corner items trimmed (the LB application's plan): the diagonal boxes are reached over two faces
+    assert sgc.step_loop_class(dlo, dhi, 64, 1, 7, TRIM_CORNER) == F | LOCAL | SLAB
+    assert sgc.step_loop_class(dlo, dhi, 64, 1, 7, TRIM_EDGE | TRIM_CORNER) == F | LOCAL | SLAB
+    # z-slab partitions (the reference's ownership rule, DisjointBoxLayout.cpp:121-139): z neighbours remote
+    for nproc in (2, 4):
+        for rank in range(nproc):
+            assert sgc.step_loop_class(dlo, dhi, 64, 1, 7, 0, nproc, rank) == F | SLAB, (nproc, rank)
+            got = sgc.step_loop_class(dlo, dhi, 64, 1, PX | PY, 0, nproc, rank)     # physical z ends of the domain:
+            want = F | BND if rank in (0, nproc - 1) else F | SLAB                  # only the end ranks see them
+            assert got == want, (nproc, rank, got)
+    # a partition that cuts a box layer in y (8 ranks x 2 boxes of the 2 x 2 x 4 layout): in-plane neighbours
+    # on another rank -> only the one-step loop
+    assert sgc.step_loop_class(dlo, dhi, 64, 1, 7, 0, 8, 3) == F
