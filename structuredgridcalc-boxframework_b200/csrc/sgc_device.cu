@@ -47,6 +47,33 @@ void comm_plan_release(sgc_plan_s* plan);
 int comm_exchange_begin(sgc_level_s* level, sgc_plan_s* plan);
 int comm_exchange_end(sgc_level_s* level, sgc_plan_s* plan);
 
+bool step_graph_ok(int nremote_a, int nremote_b) {
+  return !rt().profiling && nremote_a == 0 && nremote_b == 0 && !getenv("SGC_NO_GRAPH");
+}
+int StepGraph::begin() {
+  launches_before = rt().launches;
+  SGC_CUDA(cudaStreamBeginCapture(rt().compute, cudaStreamCaptureModeThreadLocal));
+  return 0;
+}
+int StepGraph::end() {
+  cudaGraph_t g = nullptr;
+  SGC_CUDA(cudaStreamEndCapture(rt().compute, &g));
+  unit = rt().launches - launches_before;
+  rt().launches = launches_before;                 // the captured launches have not run
+  const cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(SGC_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+  return 0;
+}
+int StepGraph::replay(int times) {
+  for (int i = 0; i < times; ++i) SGC_CUDA(cudaGraphLaunch(exec, rt().compute));
+  rt().launches += unit * times;
+  return 0;
+}
+StepGraph::~StepGraph() {
+  if (exec) cudaGraphExecDestroy(exec);
+}
+
 ProfScope::ProfScope(int klass_, cudaStream_t s_) : klass(klass_), s(s_), slot(-1) {
   Runtime& r = rt();
   if (!r.profiling) return;
@@ -1060,14 +1087,29 @@ int sgc_wave_run(sgc_level_t levels[3], sgc_plan_t exchange_plan, sgc_plan_t bc_
   SGC_REQUIRE_RT();
   if (!levels || !levels[0] || !levels[1] || !levels[2] || nstep < 0) return fail(SGC_ERR_ARG, "sgc_wave_run: bad argument");
   int n = 0, np1 = 1, nm1 = 2;
-  for (int s = 0; s < nstep; ++s) {
+  auto step = [&]() -> int {
     int st = 0;
     if (exchange_plan) st = sgc_exchange(levels[n], exchange_plan);
     if (!st && bc_plan) st = sgc_exchange(levels[n], bc_plan);
     if (!st) st = sgc_wave_step(levels[np1], levels[n], levels[nm1], factor, flags);
-    if (st) return st;
     const int t = nm1; nm1 = n; n = np1; np1 = t;      // unp1 -> un, un -> unm1 (WavePatch::advanceStepIndex)
+    return st;
+  };
+  int s = 0;
+  // three steps rotate the levels back to their roles: run three, then replay them as one graph
+  if (nstep >= 12 && step_graph_ok(exchange_plan ? exchange_plan->nremote : 0, bc_plan ? bc_plan->nremote : 0)) {
+    for (; s < 3; ++s) { const int st = step(); if (st) return st; }
+    StepGraph g;
+    int st = g.begin();
+    for (int k = 0; k < 3 && !st; ++k) st = step();
+    const int st2 = g.end();
+    if (st || st2) return st ? st : st2;
+    const int times = (nstep - s) / 3;
+    st = g.replay(times);
+    if (st) return st;
+    s += 3 * times;
   }
+  for (; s < nstep; ++s) { const int st = step(); if (st) return st; }
   if (latest) { latest[0] = n; latest[1] = np1; latest[2] = nm1; }
   return 0;
 }

@@ -112,6 +112,20 @@ struct Runtime {
 };
 Runtime& rt();
 
+// A captured unit of a step loop (a few launches on the compute stream that return the ping-pong levels to
+// their starting roles), replayed as one CUDA graph: on the small levels of the reference's own applications
+// a step is three ~10 us kernels and the loop is bound by launch latency.  Only pure launch sequences are
+// captured: single rank, profiling off (sgc_device.cu: step_graph_ok).
+struct StepGraph {
+  cudaGraphExec_t exec = nullptr;
+  long long launches_before = 0, unit = 0;
+  int begin();                 // start capturing on the compute stream
+  int end();                   // stop, instantiate; nothing has executed yet
+  int replay(int times);
+  ~StepGraph();
+};
+bool step_graph_ok(int nremote_a, int nremote_b = 0);
+
 #define SGC_CUDA(expr)                                                                      \
   do {                                                                                      \
     cudaError_t _e = (expr);                                                                \

@@ -383,9 +383,10 @@ int sgc_lb_run(sgc_level_t fi, sgc_level_t prev, sgc_level_t macro, sgc_plan_t e
   sgc_level_s* cur = fi;
   sgc_level_s* nxt = prev;
   const dim3 grid = lb_grid(fi);
-  for (int s = 0; s < nstep; ++s) {
+  auto step = [&](int s) -> int {
     // the collision of step s: stand-alone for the first step, otherwise already applied by the
     // fused kernel of step s-1
+    int st = 0;
     if (!fuse || s == 0) { st = sgc_lb_collide(cur, macro); if (st) return st; }
     st = sgc_exchange(cur, exchange);
     if (!st) st = sgc_copyset_run(bounce, cur, cur);
@@ -405,7 +406,24 @@ int sgc_lb_run(sgc_level_t fi, sgc_level_t prev, sgc_level_t macro, sgc_plan_t e
       SGC_CUDA(cudaGetLastError());
     }
     std::swap(cur, nxt);
+    return 0;
+  };
+  int s = 0;
+  // The shipped configuration is 64 x 32 x 32 cells: a step is three ~10 us launches, i.e. launch latency.
+  // Steps 1 .. nstep-2 are identical up to the ping-pong, so two of them are captured and replayed as a graph.
+  if (nstep >= 12 && step_graph_ok(exchange->nremote)) {
+    for (; s < 3; ++s) { st = step(s); if (st) return st; }       // step 0 (with its own collision) + one pair
+    StepGraph g;
+    st = g.begin();
+    for (int k = 0; k < 2 && !st; ++k) st = step(s + k);           // (s + k + 1 < nstep: the <true> kernel)
+    const int st2 = g.end();
+    if (st || st2) return st ? st : st2;
+    const int times = (nstep - 1 - s) / 2;                         // leaves at least the last step
+    st = g.replay(times);
+    if (st) return st;
+    s += 2 * times;
   }
+  for (; s < nstep; ++s) { st = step(s); if (st) return st; }
   if (result_in_prev) *result_in_prev = (cur == prev) ? 1 : 0;
   return 0;
 }

@@ -821,6 +821,52 @@ def test_lb_advance_fused_and_unfused_vs_oracle(g, oracle):
                 assert np.array_equal(p, prev), mode    # fused: m_prev's valid cells hold post-collision values
 
 
+def test_step_loops_replayed_as_graphs(g, oracle, monkeypatch):
+    """Long runs of sgc_lb_run (fused) and sgc_wave_run replay a captured unit of steps as a CUDA graph (the
+    reference's application configurations are so small that a step is launch latency); the bits and the
+    launch accounting equal the launch-by-launch loop (SGC_NO_GRAPH=1), and the LB run equals the oracle."""
+    dlo, dhi, mb, nstep = (0, 0, 0), (31, 15, 15), (16, 16, 16), 27
+    outs = []
+    for nograph in (False, True):
+        if nograph:
+            monkeypatch.setenv("SGC_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("SGC_NO_GRAPH", raising=False)
+        dbl, lb, fi, prev, mac = _lb_setup(g, oracle, dlo, dhi, mb, 321)
+        n0 = g.launch_count()
+        lb.advance(nstep, fuse=True)
+        assert g.launch_count() - n0 == 3 * nstep + 1
+        outs.append((lb.curr.download(), lb.macro.download()))
+    monkeypatch.delenv("SGC_NO_GRAPH", raising=False)
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    oracle.lb_advance(dlo, dhi, mb, nstep, fi, prev, mac)
+    assert np.array_equal(outs[0][0], fi) and np.array_equal(outs[0][1], mac)
+    # wave: three levels rotate, so the unit is three steps; periodic exchange + zero-gradient BC plans
+    dlo, dhi, mb = (0, 0, 0), (31, 31, 15), (16, 16, 16)
+    dbl, un = make_level(g, dlo, dhi, mb, 1, 1)
+    lv = [un, g.LevelData(dbl, 1, 1), g.LevelData(dbl, 1, 1)]
+    rng = np.random.default_rng(31)
+    init = [rng.standard_normal(un.elems) for _ in range(3)]
+    cp = g.Copier().defineExchangeLD(un, 3, 0)
+    bc = g.Copier().defineBCZeroGradient(un, g.Box(dlo, dhi))
+    res = []
+    for nograph in (False, True):
+        if nograph:
+            monkeypatch.setenv("SGC_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("SGC_NO_GRAPH", raising=False)
+        for l, x in zip(lv, init):
+            l.upload(x)
+        n0 = g.launch_count()
+        a, b, c = g.wave_run(lv, cp, bc, 0.0625, 25)
+        assert g.launch_count() - n0 == 3 * 25
+        res.append((a.download(), b.download(), c.download(), [lv.index(a), lv.index(b), lv.index(c)]))
+    monkeypatch.delenv("SGC_NO_GRAPH", raising=False)
+    assert res[0][3] == res[1][3]
+    for k in range(3):
+        assert np.array_equal(res[0][k], res[1][k]), k
+
+
 def test_lb_matches_reference_golden(g, golden, oracle):
     meta, arr = golden
     for c in meta["lb"]:
