@@ -1,5 +1,5 @@
 """Two-steps-per-pass sweep (sgc_stream2.cu): parity against the oracle, then timing on the C2 level.
-    python profiles/micro/t2_probe.py [parity|perf|all] [periodic flags for perf, default 7]
+    python profiles/micro/t2_probe.py [parity|perf|all] [periodic flags for perf, default 7] [box, default 64]
 Test infrastructure: imports oracle/ as the checker only.
 """
 import json
@@ -45,7 +45,13 @@ if what in ("parity", "all"):
              ((0, 0, 0), (127, 127, 127), (64, 64, 64), 0, 0.2, 9, 1),
              ((0, 0, 0), (191, 127, 63), (64, 64, 64), 4, 1.0 / 6.0, 8, 0),
              ((0, 0, 0), (63, 191, 127), (64, 64, 64), 1, 0.3, 10, 1),
-             ((0, 0, 0), (127, 127, 15), (64, 64, 8), 2, 0.3, 7, 1)]
+             ((0, 0, 0), (127, 127, 15), (64, 64, 8), 2, 0.3, 7, 1),
+             # 32^2 boxes (8 warps, three CTAs per SM)
+             ((0, 0, 0), (31, 31, 31), (32, 32, 32), 7, 0.2, 10, 1),
+             ((0, 0, 0), (95, 63, 63), (32, 32, 32), 7, 1.0 / 6.0, 9, 0),
+             ((0, 0, 0), (63, 95, 15), (32, 32, 8), 7, 0.3, 12, 1),
+             ((0, 0, 0), (63, 63, 63), (32, 32, 32), 0, 0.2, 8, 1),
+             ((0, 0, 0), (95, 63, 31), (32, 32, 16), 5, 0.3, 7, 1)]
     for (dlo, dhi, mb, per, f, nstep, contract) in cases:
         dbl = sgc.DisjointBoxLayout(sgc.Box(dlo, dhi), mb)
         rng = np.random.default_rng(3)
@@ -77,7 +83,8 @@ if what in ("parity", "all"):
     print("PARITY", "GREEN" if ok else "RED", flush=True)
 
 if what in ("perf", "all"):
-    n, box, sweeps = 512, 64, 100
+    n, sweeps = 512, 100
+    box = int(sys.argv[3]) if len(sys.argv) > 3 else 64
     dbl = sgc.DisjointBoxLayout(sgc.Box((0, 0, 0), (n - 1,) * 3), box)
     a, b = sgc.LevelData(dbl, 1, 1), sgc.LevelData(dbl, 1, 1)
     rng = np.random.default_rng(0)
@@ -102,7 +109,7 @@ if what in ("perf", "all"):
     n0, t0 = sgc.profile_read(0)
     n2, t2 = sgc.profile_read(2)
     cells = float(n) ** 3
-    print(json.dumps({"periodic": per, "ms_per_100_sweeps": ms, "gcell_per_s": cells * sweeps / (ms * 1e-3) / 1e9,
+    print(json.dumps({"box": box, "periodic": per, "ms_per_100_sweeps": ms, "gcell_per_s": cells * sweeps / (ms * 1e-3) / 1e9,
                       "one_step_launches": n0, "one_step_ms": t0 / max(n0, 1),
                       "two_step_launches": n2, "two_step_ms": t2 / max(n2, 1),
                       "two_step_gcell_per_s": 2 * cells / (t2 / max(n2, 1) * 1e-3) / 1e9 if n2 else None}), flush=True)

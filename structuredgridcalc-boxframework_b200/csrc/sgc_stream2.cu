@@ -36,7 +36,8 @@
 // of 4096 cells = 8.7 B per cell-update (x (VZ+4)/VZ for the z overlap; ncu: 9.1 B) against 16.8 B
 // for the one-step sweep; the algorithmic figure stays 16 B per cell-update.
 //
-// The kernel uses the whole register file (128 x 512) without spilling and is bound by instruction
+// Instances: V = 64 (16 warps, 8 rows per thread, one CTA per SM) and V = 32 (8 warps, 4 rows per thread, three
+// CTAs per SM).  The V = 64 kernel uses the whole register file (128 x 512) without spilling and is bound by instruction
 // issue / FP64 latency, not HBM; its speed is sensitive to anything that costs a register (DESIGN.md
 // §4.1d has the history; profiles/micro/ab.sh times variants on one GPU).
 #include <cstdint>
@@ -68,8 +69,12 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
   return v;
 }
 
+// CTAs per SM: the 64^2 instance fills the SM (221 KB of shared memory, the whole register file); the 32^2
+// instance (256 threads, 62 KB) runs three to a SM
+constexpr int t2_ctas_per_sm(int v) { return v >= 64 ? 1 : 3; }
+
 template <int V, int NS, int NCW, bool FMA, bool BND>
-__global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
+__global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args a) {
   constexpr int NT = NCW * 32;                  // threads: every warp is a consumer
   constexpr int N1 = V + 2;                     // fab rows (one ghost layer)
   constexpr int FABP = V * N1;                  // elements of one fab plane in the main block
@@ -83,7 +88,8 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
   constexpr int CPT = V / G;                    // consecutive rows per thread
   constexpr uint32_t TILE_BYTES = (uint32_t)(V * V + 4 * V + 4 * V) * 8u;   // rows + 2x2 y rows + 4 strips
   static_assert(NT % V == 0 && V % G == 0, "thread mapping");
-  static_assert(4 * V == NT / 2, "the upper half of the warps owns one flank cell per thread");
+  static_assert(4 * V == NT / 2 && V % 32 == 0, "the upper half of the warps owns one flank cell per thread");
+  static_assert(NCW >= 8, "six warps bring in the tile");
   constexpr int NROLE = 6;                      // warps that bring in a piece of each tile
   // arrivals per tile: warps 0-4 + the four corner copies of warp 5; with physical boundaries (BND) the x
   // strips may come by 8-byte cp.async copies, so every lane of warps 3 and 4 arrives
@@ -317,11 +323,12 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
     if (flank) {
       // tile offsets of the flank cell and its four in-plane neighbours (a handful of integer
       // instructions per plane; keeping them in registers would cost more than recomputing)
-      const int m = warp - NCW / 2, p = (m & 1) * 32 + lane;
+      // flank cell number (warp - NCW/2) * 32 + lane: side 0..3 = x = -1, x = V, y = -1, y = V; position p along it
+      const int side = ((warp - NCW / 2) * 32) / V, p = ((warp - NCW / 2) * 32) % V + lane;
       int hc, hxm, hxp, hym, hyp;
-      if (m < 2)      { hc = E(1) + p; hxm = E(0) + p; hxp = (p + 2) * V; hym = hc - 1; hyp = hc + 1; }             // x = -1
-      else if (m < 4) { hc = E(2) + p; hxm = (p + 2) * V + V - 1; hxp = E(3) + p; hym = hc - 1; hyp = hc + 1; }     // x = V
-      else if (m < 6) { hc = V + p; hym = p; hyp = 2 * V + p;                                                       // y = -1
+      if (side == 0)      { hc = E(1) + p; hxm = E(0) + p; hxp = (p + 2) * V; hym = hc - 1; hyp = hc + 1; }             // x = -1
+      else if (side == 1) { hc = E(2) + p; hxm = (p + 2) * V + V - 1; hxp = E(3) + p; hym = hc - 1; hyp = hc + 1; }     // x = V
+      else if (side == 2) { hc = V + p; hym = p; hyp = 2 * V + p;                                                       // y = -1
                         hxm = p > 0 ? hc - 1 : E(1) - 1; hxp = p < V - 1 ? hc + 1 : E(2) - 1; }
       else            { hc = (V + 2) * V + p; hym = (V + 1) * V + p; hyp = (V + 3) * V + p;                         // y = V
                         hxm = p > 0 ? hc - 1 : E(1) + V; hxp = p < V - 1 ? hc + 1 : E(2) + V; }
@@ -331,8 +338,8 @@ __global__ void __launch_bounds__(NCW * 32, 1) k_heat_t2(T2Args a) {
         if (BND) {
           // no neighbour on this flank's side: the "flank" is this box's ghost cell; its level-t+1 value was
           // brought in the slot of the outer halo layer
-          const int code = m < 2 ? 12 : (m < 4 ? 14 : (m < 6 ? 10 : 16));
-          const int alt = m < 2 ? E(0) + p : (m < 4 ? E(3) + p : (m < 6 ? p : (V + 3) * V + p));
+          const int code = side == 0 ? 12 : (side == 1 ? 14 : (side == 2 ? 10 : 16));
+          const int alt = side == 0 ? E(0) + p : (side == 1 ? E(3) + p : (side == 2 ? p : (V + 3) * V + p));
           if (__ldg(a.nbr + (size_t)box * 27 + code) < 0) r = P[alt];
         }
         Tw[hc] = r;
@@ -423,7 +430,7 @@ static int launch_t2_cfg(const T2Args& a, int fma, cudaStream_t s) {
     SGC_CUDA(cudaFuncSetAttribute(k_heat_t2<V, NS, NCW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  int grid = rt().sm_count;
+  int grid = rt().sm_count * t2_ctas_per_sm(V);
   if (grid > a.nplanes / 8) grid = a.nplanes / 8 > 0 ? a.nplanes / 8 : 1;
   if (a.ghost[0]) {          // levels with faces that have no neighbour (physical boundaries)
     if (fma) k_heat_t2<V, NS, NCW, true, true><<<grid, NCW * 32, smem, s>>>(a);
@@ -443,7 +450,7 @@ bool heat_t2_covers(const sgc_level_s* unew, const sgc_level_s* u) {
   if (u->esz != 8 || unew->esz != 8 || !u->xe_elems || !unew->xe_elems || getenv("SGC_NO_T2")) return false;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0 || u->nbox != unew->nbox) return false;
-  return g.vn[0] == 64 && g.vn[1] == 64 && g.vn[2] >= 4 && g.vn[2] % 2 == 0;
+  return ((g.vn[0] == 64 && g.vn[1] == 64) || (g.vn[0] == 32 && g.vn[1] == 32)) && g.vn[2] >= 4 && g.vn[2] % 2 == 0;
 }
 
 int launch_build_xe(sgc_level_s* l, cudaStream_t s) {
@@ -477,7 +484,8 @@ int launch_heat_t2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, const i
   a.dump = unew->xe_base + (a.xe_spare_plane + 1) * 4 * g.vn[1];     // scratch plane behind the spare strip plane
   a.xg_base = u->xg_base;
   a.f = f;
-  return launch_t2_cfg<64, 4, 16>(a, fma, s);
+  // 64^2 boxes: 16 warps, 8 rows per thread; 32^2 boxes: 8 warps, 4 rows per thread, three CTAs per SM
+  return g.vn[0] == 64 ? launch_t2_cfg<64, 4, 16>(a, fma, s) : launch_t2_cfg<32, 4, 8>(a, fma, s);
 }
 
 }  // namespace sgc

@@ -121,7 +121,7 @@ def run_gpu(rank, world, local_rank):
         sgc.profile_enable(False)
         got = res.download()
         assert np.array_equal(got, want[goff[b0]:end]), ("heat_run", rank, mb)
-        if mb == (64, 64, 64) and os.environ.get("SGC_P2P", "1") != "0" and not os.environ.get("SGC_NO_T2"):
+        if mb in ((64, 64, 64), (32, 32, 32)) and os.environ.get("SGC_P2P", "1") != "0" and not os.environ.get("SGC_NO_T2"):
             # the two-step passes pull their z tiles out of the neighbouring GPU's memory
             assert n2 == ((nstep - 2) // 2) & ~1, ("two-step passes", n2, nstep)
         if world > 1:

@@ -338,8 +338,8 @@ def test_heat_random_vs_oracle_both_fma_modes(g, oracle):
 
 
 def test_two_step_sweep_matches_oracle_and_step_by_step(g, oracle, monkeypatch):
-    """sgc_heat_run's two-steps-per-pass kernel (sgc_stream2.cu, 64x64 boxes with all in-plane and z
-    neighbours): level t is read once and level t+2 written once.  Valid AND ghost cells of BOTH levels
+    """sgc_heat_run's two-steps-per-pass kernel (sgc_stream2.cu; 64x64 and 32x32 boxes, periodic or with
+    physical boundaries): level t is read once and level t+2 written once.  Valid AND ghost cells of BOTH levels
     must equal the oracle's nstep x {exchange; sweep} (LevelData.H:455-566 + the sweep loop) and the
     library's own step-by-step schedule, bit for bit, in both FMA modes; odd and even step counts,
     several boxes per direction, flat boxes (vz = 8)."""
@@ -358,7 +358,14 @@ def test_two_step_sweep_matches_oracle_and_step_by_step(g, oracle, monkeypatch):
              ((0, 0, 0), (127, 191, 15), (64, 64, 8), 6, 0.2, 11, 0),
              ((0, 0, 0), (63, 63, 63), (64, 64, 64), 1, 0.2, 8, 1),
              ((0, 0, 0), (127, 127, 63), (64, 64, 64), 2, 0.2, 8, 1),
-             ((0, 0, 0), (63, 127, 127), (64, 64, 64), 4, 0.2, 13, 1)]
+             ((0, 0, 0), (63, 127, 127), (64, 64, 64), 4, 0.2, 13, 1),
+             # the 32 x 32 instance (8 warps, 4 rows per thread, three CTAs per SM)
+             ((0, 0, 0), (31, 31, 31), (32, 32, 32), 7, 0.2, 10, 1),
+             ((0, 0, 0), (95, 63, 63), (32, 32, 32), 7, 1.0 / 6.0, 9, 0),
+             ((-32, 0, 4), (31, 95, 19), (32, 32, 8), 7, 0.3, 12, 1),
+             ((0, 0, 0), (63, 63, 63), (32, 32, 32), 0, 0.2, 8, 0),
+             ((0, 0, 0), (95, 63, 31), (32, 32, 16), 5, 0.3, 7, 1),
+             ((0, 0, 0), (63, 95, 63), (32, 32, 32), 2, 0.3, 11, 1)]
     for (dlo, dhi, mb, per, f, nstep, contract) in cases:
         dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
         b = g.LevelData(dbl, 1, 1)
