@@ -20,7 +20,7 @@
 //   Faces WITHOUT a neighbour (physical boundaries; template flag BND) read the box's own, never
 //   exchanged ghost cells instead — see the comment at the producer roles.
 // All NCW warps are consumers (thread = one x and CPT consecutive rows, all state in registers);
-// six of them also bring in one piece of each tile, the upper half also computes the flanks:
+// six of them also bring in one piece of each tile, the last 4V/32 warps also compute the flanks:
 //   stage 1: t+1 on plane z-1 for the V x V cells and for the four 1-cell-wide flanks (x = -1, V and
 //            y = -1, V) — the values the x / y neighbours would have exchanged.  Results go to
 //            registers (z neighbours of stage 2) and to one of two t+1 plane buffers in shared
@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   constexpr int CPT = V / G;                    // consecutive rows per thread
   constexpr uint32_t TILE_BYTES = (uint32_t)(V * V + 4 * V + 4 * V) * 8u;   // rows + 2x2 y rows + 4 strips
   static_assert(NT % V == 0 && V % G == 0, "thread mapping");
-  static_assert(4 * V == NT / 2 && V % 32 == 0, "the upper half of the warps owns one flank cell per thread");
+  constexpr int FW = 4 * V / 32;                // flank warps: the last FW warps own one flank cell per thread
+  static_assert(V % 32 == 0 && FW <= NCW, "flank cells");
   static_assert(NCW >= 8, "six warps bring in the tile");
   constexpr int NROLE = 6;                      // warps that bring in a piece of each tile
   // arrivals per tile: warps 0-4 + the four corner copies of warp 5; with physical boundaries (BND) the x
@@ -278,9 +279,9 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
     }
   }
 
-  // ---------------- flank role (upper half of the warps): one cell of the x / y flanks per thread ----------------
+  // ---------------- flank role (the last FW warps): one cell of the x / y flanks per thread ----------------
   // warp-uniform m = 0..3: x flanks (side m>>1, y = (m&1)*32 + lane); m = 4..7: y flanks (side, x likewise)
-  const bool flank = warp >= NCW / 2;
+  const bool flank = warp >= NCW - FW;
   double hA = 0.0, hB = 0.0;          // the flank cell at the two latest planes of level t (roles alternate)
 
   // ---------------- regular role (every thread): x = xi, rows y0 .. y0+CPT-1 ----------------
@@ -323,8 +324,8 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
     if (flank) {
       // tile offsets of the flank cell and its four in-plane neighbours (a handful of integer
       // instructions per plane; keeping them in registers would cost more than recomputing)
-      // flank cell number (warp - NCW/2) * 32 + lane: side 0..3 = x = -1, x = V, y = -1, y = V; position p along it
-      const int side = ((warp - NCW / 2) * 32) / V, p = ((warp - NCW / 2) * 32) % V + lane;
+      // flank cell number (warp - first flank warp) * 32 + lane: side 0..3 = x = -1, x = V, y = -1, y = V; position p along it
+      const int side = ((warp - (NCW - FW)) * 32) / V, p = ((warp - (NCW - FW)) * 32) % V + lane;
       int hc, hxm, hxp, hym, hyp;
       if (side == 0)      { hc = E(1) + p; hxm = E(0) + p; hxp = (p + 2) * V; hym = hc - 1; hyp = hc + 1; }             // x = -1
       else if (side == 1) { hc = E(2) + p; hxm = (p + 2) * V + V - 1; hxp = E(3) + p; hym = hc - 1; hyp = hc + 1; }     // x = V
@@ -485,6 +486,7 @@ int launch_heat_t2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, const i
   a.xg_base = u->xg_base;
   a.f = f;
   // 64^2 boxes: 16 warps, 8 rows per thread; 32^2 boxes: 8 warps, 4 rows per thread, three CTAs per SM
+  // (V = 64 with 32 warps of 4 rows — a 64-register cap — spills and is 1.5x slower)
   return g.vn[0] == 64 ? launch_t2_cfg<64, 4, 16>(a, fma, s) : launch_t2_cfg<32, 4, 8>(a, fma, s);
 }
 
