@@ -51,7 +51,12 @@ if what in ("parity", "all"):
              ((0, 0, 0), (95, 63, 63), (32, 32, 32), 7, 1.0 / 6.0, 9, 0),
              ((0, 0, 0), (63, 95, 15), (32, 32, 8), 7, 0.3, 12, 1),
              ((0, 0, 0), (63, 63, 63), (32, 32, 32), 0, 0.2, 8, 1),
-             ((0, 0, 0), (95, 63, 31), (32, 32, 16), 5, 0.3, 7, 1)]
+             ((0, 0, 0), (95, 63, 31), (32, 32, 16), 5, 0.3, 7, 1),
+             # 16^2 boxes (4 warps, two roles per warp; experimental: SGC_T2_16=1)
+             ((0, 0, 0), (15, 15, 15), (16, 16, 16), 7, 0.2, 10, 1),
+             ((0, 0, 0), (63, 47, 31), (16, 16, 16), 7, 1.0 / 6.0, 9, 0),
+             ((0, 0, 0), (31, 47, 15), (16, 16, 8), 0, 0.3, 12, 1),
+             ((0, 0, 0), (47, 31, 31), (16, 16, 16), 6, 0.3, 7, 1)]
     for (dlo, dhi, mb, per, f, nstep, contract) in cases:
         dbl = sgc.DisjointBoxLayout(sgc.Box(dlo, dhi), mb)
         rng = np.random.default_rng(3)

@@ -397,7 +397,8 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
   l->xe_base = (l->arena_elems + 63) / 64 * 64;
   {
     const FabGeom& g0 = l->geom[0];
-    if (l->uniform && ncomp == 1 && nghost == 1 && elem_bytes == 8 && ((g0.vn[0] == 64 && g0.vn[1] == 64) || (g0.vn[0] == 32 && g0.vn[1] == 32)) && g0.vn[2] >= 4)
+    if (l->uniform && ncomp == 1 && nghost == 1 && elem_bytes == 8 && ((g0.vn[0] == 64 && g0.vn[1] == 64) || (g0.vn[0] == 32 && g0.vn[1] == 32) ||
+         (g0.vn[0] == 16 && g0.vn[1] == 16 && getenv("SGC_T2_16"))) && g0.vn[2] >= 4)
       l->xe_elems = ((long long)nbox * g0.vn[2] + 1) * 4 * g0.vn[1] + (long long)g0.vn[0] * g0.vn[1];   // + a spare strip plane + a scratch plane
   }
   const size_t bytes = (size_t)(l->lead + l->xe_base + l->xe_elems + 64) * elem_bytes;

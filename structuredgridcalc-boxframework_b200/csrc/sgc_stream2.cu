@@ -36,8 +36,8 @@
 // of 4096 cells = 8.7 B per cell-update (x (VZ+4)/VZ for the z overlap; ncu: 9.1 B) against 16.8 B
 // for the one-step sweep; the algorithmic figure stays 16 B per cell-update.
 //
-// Instances: V = 64 (16 warps, 8 rows per thread, one CTA per SM) and V = 32 (8 warps, 4 rows per thread, three
-// CTAs per SM).  The V = 64 kernel uses the whole register file (128 x 512) without spilling and is bound by instruction
+// Instances: V = 64 (16 warps, 8 rows per thread, one CTA per SM), V = 32 (8 warps, 4 rows per thread, three
+// CTAs per SM) and, on request only, V = 16 (4 warps, 2 rows per thread: slower than the one-step sweep).  The V = 64 kernel uses the whole register file (128 x 512) without spilling and is bound by instruction
 // issue / FP64 latency, not HBM; its speed is sensitive to anything that costs a register (DESIGN.md
 // §4.1d has the history; profiles/micro/ab.sh times variants on one GPU).
 #include <cstdint>
@@ -71,7 +71,7 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
 
 // CTAs per SM: the 64^2 instance fills the SM (221 KB of shared memory, the whole register file); the 32^2
 // instance (256 threads, 62 KB) runs three to a SM
-constexpr int t2_ctas_per_sm(int v) { return v >= 64 ? 1 : 3; }
+constexpr int t2_ctas_per_sm(int v) { return v >= 64 ? 1 : (v >= 32 ? 3 : 8); }
 
 template <int V, int NS, int NCW, bool FMA, bool BND>
 __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args a) {
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   constexpr uint32_t TILE_BYTES = (uint32_t)(V * V + 4 * V + 4 * V) * 8u;   // rows + 2x2 y rows + 4 strips
   static_assert(NT % V == 0 && V % G == 0, "thread mapping");
   constexpr int FW = 4 * V / 32;                // flank warps: the last FW warps own one flank cell per thread
-  static_assert(V % 32 == 0 && FW <= NCW, "flank cells");
-  static_assert(NCW >= 8, "six warps bring in the tile");
+  static_assert((4 * V) % 32 == 0 && FW <= NCW, "flank cells");
+  static_assert(2 * NCW >= 6, "six roles bring in the tile, at most two per warp");
   constexpr int NROLE = 6;                      // warps that bring in a piece of each tile
   // arrivals per tile: warps 0-4 + the four corner copies of warp 5; with physical boundaries (BND) the x
   // strips may come by 8-byte cp.async copies, so every lane of warps 3 and 4 arrives
@@ -135,11 +135,12 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   // the neighbour's valid cells, and the slot of the second halo layer (x = -2 / V+1 strip, row y = -2 /
   // V+1, plane z = -2 / vz+1) — not needed there — carries the level-t+1 ghost cells, which the consumers
   // copy where they would have computed a flank / halo-plane value.
-  int S = -1, N = 0;                  // source box of the current tiles (bit 30 remote, 29 peer slot, 28 z face
-                                      // missing); this role's neighbour of S (BND: -1 = missing)
-  int ct = 0;                         // BND, warp 5: where the lane's corner cell comes from (see below)
+  // per role a warp plays (one for NCW >= 6; with fewer warps a warp plays roles `warp` and `warp + NCW`):
+  // S = source box of the current tiles (bit 30 remote, 29 peer slot, 28 z face missing), N = this role's
+  // neighbour of S (BND: -1 = missing), ct = BND corner role: where the lane's corner cell comes from
+  int Sa = -1, Na = 0, cta = 0, Sb = -1, Nb = 0, ctb = 0;
   unsigned waited = 0;                // bit per peer slot
-  auto issue = [&](int slot, int tbox, int tl) {          // tile = virtual plane tl of box tbox
+  auto issue = [&](int slot, int tbox, int tl, const int role, int& S, int& N, int& ct) {   // tile = virtual plane tl of box tbox
     const int z = tl - 2;
     const int cls = z < 0 ? 0 : (z >= vz ? 2 : 1);
     if (S < 0 || tl == 0 || tl == 2 || tl == vz + 2) {    // first tile, or the source box changes here
@@ -171,8 +172,8 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
       }
       // this role's in-plane neighbour of S (on a z-slab partition the peer's local indices equal ours)
       const int* __restrict__ nb = a.nbr + (size_t)(S & 0x0fffffff) * 27;
-      if (warp == 0) N = S & 0x0fffffff;
-      else if (warp < 5) N = __ldg(nb + (warp == 1 ? 10 : (warp == 2 ? 16 : (warp == 3 ? 12 : 14))));
+      if (role == 0) N = S & 0x0fffffff;
+      else if (role < 5) N = __ldg(nb + (role == 1 ? 10 : (role == 2 ? 16 : (role == 3 ? 12 : 14))));
       else {
         // corner (dx,dy) by lane bits: the valid cell of the diagonal box, reached over two faces
         const int cx = (lane & 1) ? 14 : 12, cy = (lane & 2) ? 16 : 10;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
     const double* g1 = !BND ? nullptr : (!rem ? a.ghost[1] : a.peer_ghost[ps1 ? 1 : 0][1]);
     const double* base = zmiss ? ((tl == 1 || tl == vz + 2) ? g0 : g1)
                                : (!rem ? a.in_level : (ps1 ? a.peer_in[1] : a.peer_in[0]));
-    if (warp == 5) {
+    if (role == 5) {
       if (lane < 4) {
         const bool xh = lane & 1, yh = lane & 2;
         const double* src = base + N * fabm + prow + (long long)(yh ? 0 : V - 1) * V + (xh ? 0 : V - 1);
@@ -209,19 +210,17 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
         if (!BND || (ct != 3 && !zmiss)) cp_async8(dst + E(xh ? 2 : 1) + (yh ? V : -1), src);
         cp_async_arrive(full + slot);
       }
-    } else if (BND && warp >= 3) {
+    } else if (BND && role >= 3) {
       // x strips: the neighbour's edge strips (two bulk copies), or — no neighbour — the ghost columns of S
       // itself in the two ghost levels, 8 bytes at a time (a ghost strip starts 8 bytes off a 16-byte
       // boundary, which bulk copies cannot do)
-      const bool hi = warp == 4;
+      const bool hi = role == 4;
       if (zmiss) {
         // ghost plane: the x neighbour's ghost-plane column next to this box (not part of its edge strips)
         if (N >= 0) {
 #pragma unroll
-          for (int h = 0; h < V / 32; ++h) {
-            const int y = lane + 32 * h;
+          for (int y = lane; y < V; y += 32)
             cp_async8(dst + E(hi ? 2 : 1) + y, base + N * fabm + prow + (long long)y * V + (hi ? 0 : V - 1));
-          }
         }
       } else if (N >= 0) {
         if (lane == 0) {
@@ -234,20 +233,19 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
         const long long go = a.xg_base + (long long)(S & 0x0fffffff) * (2 * N1 * (vz + 2)) +
                              ((long long)((hi ? 1 : 0) * (vz + 2) + fp)) * N1 + 1;
 #pragma unroll
-        for (int h = 0; h < V / 32; ++h) {
-          const int y = lane + 32 * h;
+        for (int y = lane; y < V; y += 32) {
           cp_async8(dst + E(hi ? 2 : 1) + y, g0 + go + y);      // level t ghosts at x = -1 / V
           cp_async8(dst + E(hi ? 3 : 0) + y, g1 + go + y);      // level t+1 ghosts, in the unused outer strip
         }
       }
       cp_async_arrive(full + slot);
     } else if (lane == 0) {
-      if (warp == 0) {
+      if (role == 0) {
         if (BND) mbar_expect_tx(full + slot, V * V * 8u);
         else mbar_expect_tx(full + slot, TILE_BYTES);             // this warp's arrival + the tile's byte count
         bulk_g2s(dst + 2 * V, base + N * fabm + prow, V * V * 8u, full + slot);                           // rows 0..V-1
-      } else if (warp == 1 || warp == 2) {
-        const bool hi = warp == 2;
+      } else if (role == 1 || role == 2) {
+        const bool hi = role == 2;
         if (BND) mbar_expect_tx_only(full + slot, 2 * V * 8u);
         if (!BND || N >= 0) {
           if (!hi) bulk_g2s(dst, base + N * fabm + prow + (long long)(V - 2) * V, 2 * V * 8u, full + slot);   // rows -2,-1
@@ -260,7 +258,7 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
         }
       } else {
         const double* e = base + a.xe_in + ((long long)N * vz + kz) * (4 * V);
-        if (warp == 3) {
+        if (role == 3) {
           bulk_g2s(dst + E(0), e + 2 * V, V * 8u, full + slot);     // x = -2  <- x neighbour's column V-2
           bulk_g2s(dst + E(1), e + 3 * V, V * 8u, full + slot);     // x = -1  <- column V-1
         } else {
@@ -268,15 +266,18 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
           bulk_g2s(dst + E(3), e + V, V * 8u, full + slot);         // x = V+1 <- column 1
         }
       }
-      if (warp != 0) mbar_arrive(full + slot);
+      if (role != 0) mbar_arrive(full + slot);
     }
   };
-  if (warp < NROLE) {
+  // a warp's role(s) for one tile
+  auto issue_roles = [&](int slot, int tbox, int tl) {
+    if (warp < NROLE) issue(slot, tbox, tl, warp, Sa, Na, cta);
+    if (NCW < NROLE && warp + NCW < NROLE) issue(slot, tbox, tl, warp + NCW, Sb, Nb, ctb);
+  };
+  {
     const int b0 = l_begin / VP, l0 = l_begin - b0 * VP;
-    issue(0, b0, l0);
-    if (l_begin + 1 < s_end) {
-      issue(1, l0 + 1 == VP ? b0 + 1 : b0, l0 + 1 == VP ? 0 : l0 + 1);
-    }
+    issue_roles(0, b0, l0);
+    if (l_begin + 1 < s_end) issue_roles(1, l0 + 1 == VP ? b0 + 1 : b0, l0 + 1 == VP ? 0 : l0 + 1);
   }
 
   // ---------------- flank role (the last FW warps): one cell of the x / y flanks per thread ----------------
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
     mbar_wait(full + slot, (i / NS) & 1u);
     __syncthreads();                 // t+1 buffer hand-over; every warp has left tile i-2 and t+1 plane i-3
     const bool more = i + 2 < n_iter;
-    if (warp < NROLE && more) issue((i + 2) & (NS - 1), l + 2 >= VP ? box + 1 : box, l + 2 >= VP ? l + 2 - VP : l + 2);
+    if (more) issue_roles((i + 2) & (NS - 1), l + 2 >= VP ? box + 1 : box, l + 2 >= VP ? l + 2 - VP : l + 2);
     const double* __restrict__ C = ring + (size_t)slot * SLOT;
     const double* __restrict__ P = ring + (size_t)((i + NS - 1) & (NS - 1)) * SLOT;
     const bool do1 = (l >= 2) && (i >= 2);
@@ -325,7 +326,9 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
       // tile offsets of the flank cell and its four in-plane neighbours (a handful of integer
       // instructions per plane; keeping them in registers would cost more than recomputing)
       // flank cell number (warp - first flank warp) * 32 + lane: side 0..3 = x = -1, x = V, y = -1, y = V; position p along it
-      const int side = ((warp - (NCW - FW)) * 32) / V, p = ((warp - (NCW - FW)) * 32) % V + lane;
+      const int fidx = (warp - (NCW - FW)) * 32 + lane;
+      const int side = V >= 32 ? ((warp - (NCW - FW)) * 32) / V : fidx / V;      // warp-uniform for V >= 32
+      const int p = V >= 32 ? ((warp - (NCW - FW)) * 32) % V + lane : fidx % V;
       int hc, hxm, hxp, hym, hyp;
       if (side == 0)      { hc = E(1) + p; hxm = E(0) + p; hxp = (p + 2) * V; hym = hc - 1; hyp = hc + 1; }             // x = -1
       else if (side == 1) { hc = E(2) + p; hxm = (p + 2) * V + V - 1; hxp = E(3) + p; hym = hc - 1; hyp = hc + 1; }     // x = V
@@ -451,7 +454,12 @@ bool heat_t2_covers(const sgc_level_s* unew, const sgc_level_s* u) {
   if (u->esz != 8 || unew->esz != 8 || !u->xe_elems || !unew->xe_elems || getenv("SGC_NO_T2")) return false;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0 || u->nbox != unew->nbox) return false;
-  return ((g.vn[0] == 64 && g.vn[1] == 64) || (g.vn[0] == 32 && g.vn[1] == 32)) && g.vn[2] >= 4 && g.vn[2] % 2 == 0;
+  // the 16^2 instance (4 warps, two tile roles per warp, 8 CTAs per SM) is bit-exact but SLOWER than the one-step
+  // sweep (163 against 271 Gcell/s on 32 768 boxes: with 2 rows per thread the per-plane barrier, tile issue and
+  // flank work dominate), so it only runs on request
+  const bool shape = (g.vn[0] == 64 && g.vn[1] == 64) || (g.vn[0] == 32 && g.vn[1] == 32) ||
+                     (g.vn[0] == 16 && g.vn[1] == 16 && getenv("SGC_T2_16"));
+  return shape && g.vn[2] >= 4 && g.vn[2] % 2 == 0;
 }
 
 int launch_build_xe(sgc_level_s* l, cudaStream_t s) {
@@ -487,7 +495,8 @@ int launch_heat_t2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, const i
   a.f = f;
   // 64^2 boxes: 16 warps, 8 rows per thread; 32^2 boxes: 8 warps, 4 rows per thread, three CTAs per SM
   // (V = 64 with 32 warps of 4 rows — a 64-register cap — spills and is 1.5x slower)
-  return g.vn[0] == 64 ? launch_t2_cfg<64, 4, 16>(a, fma, s) : launch_t2_cfg<32, 4, 8>(a, fma, s);
+  return g.vn[0] == 64 ? launch_t2_cfg<64, 4, 16>(a, fma, s)
+                       : (g.vn[0] == 32 ? launch_t2_cfg<32, 4, 8>(a, fma, s) : launch_t2_cfg<16, 4, 4>(a, fma, s));
 }
 
 }  // namespace sgc
