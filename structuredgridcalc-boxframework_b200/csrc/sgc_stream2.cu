@@ -121,12 +121,12 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
 
   auto E = [](int s) { return NR + s * ESTR + 2; };       // tile offset of strip s at y = 0
 
-  // ---------------- producer roles (warps 0-5, one piece of the tile each) ----------------
+  // ---------------- tile roles (six, one piece of the tile each; warp r plays role r, and role r + NCW if NCW < 6) ----------------
   // Tile t goes to ring slot (t - l_begin) % NS.  The address arithmetic of a tile is spread over six
-  // warps so that no warp lags at the per-plane barrier: lane 0 of warp r issues
+  // roles so that no warp lags at the per-plane barrier: lane 0 of the warp playing role r issues
   //   r = 0: the V own rows (+ announces the tile's bytes)   r = 1 / 2: the two rows of the -y / +y neighbour
   //   r = 3 / 4: the two edge strips of the -x / +x neighbour
-  // and lanes 0-3 of warp 5 fetch the four corner cells with 8-byte cp.async copies, each arriving on
+  // and lanes 0-3 of role 5 fetch the four corner cells with 8-byte cp.async copies, each arriving on
   // the slot's mbarrier when it lands (cp.async.mbarrier.arrive.noinc).  issue() starts all of that for
   // the tile two iterations ahead; the slot completes on nine arrivals + the bulk copies' bytes.
   // BND: a face of a box without a motion item in the plan (a physical boundary, or a trimmed direction)
