@@ -152,3 +152,30 @@ def test_step_loop_classification(sgc):
     # a partition that cuts a box layer in y (8 ranks x 2 boxes of the 2 x 2 x 4 layout): in-plane neighbours
     # on another rank -> only the one-step loop
     assert sgc.step_loop_class(dlo, dhi, 64, 1, 7, 0, 8, 3) == F
+
+
+def test_committed_bench_line_follows_the_contract():
+    """profiles/r01_bench_n1.json is bench.py's line from a B200: the keys the driver and the judge read."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    j = json.load(open(os.path.join(root, "profiles", "r01_bench_n1.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches"):
+        assert k in j, k
+    assert j["metric"] == "Gcell-updates/s" and j["dtype"] == "f64" and j["scaling"] == "weak" and j["vs_baseline"] is None
+    assert "workload" in j["config"] and "model" not in j["config"]
+    r = j["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    # the dominant kernel advances two steps per launch: its algorithmic bytes are 2 x 16 B per cell, and
+    # its real DRAM traffic (ncu) is below them
+    assert r["cell_updates_per_cell_per_launch"] == 2 and r["traffic"] < r["algorithmic_bytes_per_launch"]
+    c = j["cpu_baseline"]
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in c, k
+    assert c["kind"] == "reference"
+    e = j["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < j["value"]
+    assert j["gpu_launches"] > 0 and j["clocks"]["sm_mhz"] > 0
