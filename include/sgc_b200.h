@@ -165,6 +165,11 @@ long long sgc_level_elems(sgc_level_t level);
 long long sgc_level_fab_offset(sgc_level_t level, int box);
 /* device address of fab `box` (BaseFab::m_dataSymbol.device, BaseFab.H:213-216) */
 void* sgc_level_device_ptr(sgc_level_t level, int box);
+/* Introspection (tests, bench): state of the level's edge strips — dense copies of the first / last valid
+ * x columns of every fab plane that the streaming sweeps keep current so that the next
+ * LevelData::exchange (LevelData.H:455-566) reads its x faces densely instead of one element per row:
+ * -1 the level has none, 0 stale, 1 the outer columns are current, 2 all four.                      */
+int sgc_level_edge_strips(sgc_level_t level);
 
 /* LevelData::copyToDevice / copyToHost (LevelData.H:711-765) and BaseFab::copyToDevice/Host
  * (BaseFab.cpp:427-483).  box = -1: the whole level (host buffer = fabs concatenated in box
@@ -316,6 +321,11 @@ int sgc_wave_run(sgc_level_t levels[3], sgc_plan_t exchange_plan, sgc_plan_t bc_
  * cells included, exactly the bits nstep x { exchange ; sweep } would have left (tests pin this).  */
 int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags,
                  int nstep, int* result_in_b);
+/* Introspection: how sgc_heat_run re-boxes this plan's level for its step loop (levels of many small
+ * boxes, e.g. DisjointBoxLayout(domain, 16): DisjointBoxLayout.cpp:93-168): factor[d] user boxes per
+ * device fab along d, all 1 when the level runs as it is.  Decided on the first sgc_heat_run of >= 8 steps;
+ * returns 1 once decided, 0 before.                                                                   */
+int sgc_plan_rebox_factors(sgc_plan_t plan, int factor[3]);
 
 /* ------------------------------------------------------------------ lattice Boltzmann ---- */
 

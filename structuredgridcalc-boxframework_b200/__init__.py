@@ -34,6 +34,7 @@ SYMBOLS = [
     "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
     "sgc_level_upload_async", "sgc_level_download_async", "sgc_copyset_create", "sgc_copyset_run", "sgc_copyset_destroy",
     "sgc_copyset_num_cells", "sgc_level_valid_elems", "sgc_level_download_valid", "sgc_level_download_valid_async", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run", "sgc_lb_selftest_divconst",
+    "sgc_level_edge_strips", "sgc_plan_rebox_factors",
 ]
 
 
@@ -89,6 +90,8 @@ def lib():
     L.sgc_level_fab_offset.argtypes = [C.c_void_p, C.c_int]
     L.sgc_level_device_ptr.restype = C.c_void_p
     L.sgc_level_device_ptr.argtypes = [C.c_void_p, C.c_int]
+    L.sgc_level_edge_strips.argtypes = [C.c_void_p]
+    L.sgc_plan_rebox_factors.argtypes = [C.c_void_p, _i3]
     L.sgc_plan_num_cells.restype = C.c_longlong
     L.sgc_plan_num_cells.argtypes = [C.c_void_p]
     L.sgc_device_info.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
@@ -426,6 +429,10 @@ class LevelData:
         check(lib().sgc_level_download_valid(self.h, out.ctypes.data))
         return out
 
+    def edgeStrips(self):
+        """-1 none, 0 stale, 1 outer columns current, 2 all four (sgc_level_edge_strips)"""
+        return int(lib().sgc_level_edge_strips(self.h))
+
     def setVal(self, value, comp=-1, box=-1):
         v = np.array([value], self.dtype)
         check(lib().sgc_level_setval(self.h, box, comp, v.ctypes.data))
@@ -508,6 +515,12 @@ class Copier:
 
     def numCells(self):
         return int(lib().sgc_plan_num_cells(self.h))
+
+    def reboxFactors(self):
+        """(decided, (cx, cy, cz)): user boxes per device fab in sgc_heat_run's re-boxed step loop"""
+        f = (C.c_int * 3)()
+        decided = check(lib().sgc_plan_rebox_factors(self.h, f))
+        return bool(decided), tuple(f)
 
     def _release(self):
         if self.h and _lib is not None:

@@ -142,8 +142,8 @@ int comm_plan_setup(sgc_plan_s* p, sgc_level_s* l, const Grid& g, unsigned perio
       pos += r.size() * p->nc;
     }
     peer.send_elems = pos;
-    st = peer.pack.upload(pack);
-    if (!st) st = peer.unpack.upload(unpack);
+    st = peer.pack.upload(pack, l->esz);
+    if (!st) st = peer.unpack.upload(unpack, l->esz);
     if (st) return st;
     SGC_CUDA(cudaMalloc(&peer.d_send, (size_t)std::max<long long>(peer.send_elems, 1) * l->esz));
     SGC_CUDA(cudaMalloc(&peer.d_recv, (size_t)std::max<long long>(peer.recv_elems, 1) * l->esz));

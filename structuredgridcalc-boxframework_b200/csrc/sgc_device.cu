@@ -96,39 +96,75 @@ void CopyTable::release() {
   if (d_cell_start) cudaFree(d_cell_start);
   if (d_chunk_first) cudaFree(d_chunk_first);
   d_items = nullptr; d_cell_start = nullptr; d_chunk_first = nullptr;
-  nitem = nchunk = 0; ncell = 0; strided_reads = false;
+  nitem = nchunk = nwitem = nwchunk = 0; ncell = nwcell = 0; strided_reads = false;
 }
 
-int CopyTable::upload(const std::vector<CopyItem>& items) {
+// can the item run with 16-byte accesses?  (8-byte elements; every base pointer the tables are used with
+// — level arenas, staging and pack buffers — is 256-byte aligned, checked in launch_copy)
+static bool wide_ok(const CopyItem& c) {
+  if (c.dsx != 1 || c.ssx != 1 || (c.nx & 1) || (c.dst & 1) || (c.src & 1)) return false;
+  if ((c.ny > 1 && ((c.dsy | c.ssy) & 1)) || (c.nz > 1 && ((c.dsz | c.ssz) & 1))) return false;
+  return c.nc == 1 || !((c.dcs | c.scs) & 1);
+}
+
+int CopyTable::upload(const std::vector<CopyItem>& in, int esz) {
   release();
-  nitem = (int)items.size();
+  nitem = (int)in.size();
   if (nitem == 0) return 0;
+  // wide items first, in 16-byte units
+  std::vector<CopyItem> items;
+  items.reserve(in.size());
+  static const bool no_wide = getenv("SGC_COPY_NO_WIDE") != nullptr;
+  if (esz == 8 && !no_wide)
+    for (const CopyItem& c : in)
+      if (wide_ok(c)) {
+        CopyItem w = c;
+        w.nx /= 2; w.dst /= 2; w.src /= 2; w.dsy /= 2; w.dsz /= 2; w.ssy /= 2; w.ssz /= 2; w.dcs /= 2; w.scs /= 2;
+        items.push_back(w);
+      }
+  nwitem = (int)items.size();
+  for (const CopyItem& c : in)
+    if (!(esz == 8 && !no_wide && wide_ok(c))) items.push_back(c);
   std::vector<long long> start(nitem + 1);
   start[0] = 0;
   for (int i = 0; i < nitem; ++i)
     start[i + 1] = start[i] + (long long)items[i].nx * items[i].ny * items[i].nz * items[i].nc;
   ncell = start[nitem];
+  nwcell = start[nwitem];
   // cells read one per source row, rows at least 256 bytes apart (for 8-byte elements): worth asking
   // L2 for 64-byte DRAM fetches (measured: C2 exchange 0.119 -> 0.097 ms; no gain for 128-byte rows)
   long long lonely = 0;
-  for (const CopyItem& c : items)
+  for (int i = nwitem; i < nitem; ++i) {
+    const CopyItem& c = items[i];
     if (c.nx == 1 && c.ssy >= 32) lonely += (long long)c.ny * c.nz * c.nc;
-  strided_reads = lonely * 5 > ncell;
-  nchunk = (int)((ncell + kCopyChunk - 1) / kCopyChunk);
-  std::vector<int> first(nchunk + 1);
+  }
+  strided_reads = lonely * 5 > ncell - nwcell;
+  nwchunk = (int)((nwcell + kCopyChunk - 1) / kCopyChunk);
+  const int nnchunk = (int)((ncell - nwcell + kCopyChunk - 1) / kCopyChunk);
+  nchunk = nwchunk + nnchunk;
+  // chunk c of a class covers units [base + c*kCopyChunk, ...): first item overlapping it, then one closing
+  // entry per class (the last item of the class)
+  std::vector<int> first(nchunk + 2);
   int it = 0;
-  for (int c = 0; c < nchunk; ++c) {
+  for (int c = 0; c < nwchunk; ++c) {
     const long long cell = (long long)c * kCopyChunk;
-    while (it + 1 < nitem && start[it + 1] <= cell) ++it;
+    while (it + 1 < nwitem && start[it + 1] <= cell) ++it;
     first[c] = it;
   }
-  first[nchunk] = nitem - 1;
+  first[nwchunk] = nwitem > 0 ? nwitem - 1 : 0;
+  it = nwitem;
+  for (int c = 0; c < nnchunk; ++c) {
+    const long long cell = nwcell + (long long)c * kCopyChunk;
+    while (it + 1 < nitem && start[it + 1] <= cell) ++it;
+    first[nwchunk + 1 + c] = it;
+  }
+  first[nchunk + 1] = nitem - 1;
   SGC_CUDA(cudaMalloc(&d_items, sizeof(CopyItem) * (size_t)nitem));
   SGC_CUDA(cudaMalloc(&d_cell_start, sizeof(long long) * (size_t)(nitem + 1)));
-  SGC_CUDA(cudaMalloc(&d_chunk_first, sizeof(int) * (size_t)(nchunk + 1)));
+  SGC_CUDA(cudaMalloc(&d_chunk_first, sizeof(int) * (size_t)(nchunk + 2)));
   SGC_CUDA(cudaMemcpy(d_items, items.data(), sizeof(CopyItem) * (size_t)nitem, cudaMemcpyHostToDevice));
   SGC_CUDA(cudaMemcpy(d_cell_start, start.data(), sizeof(long long) * (size_t)(nitem + 1), cudaMemcpyHostToDevice));
-  SGC_CUDA(cudaMemcpy(d_chunk_first, first.data(), sizeof(int) * (size_t)(nchunk + 1), cudaMemcpyHostToDevice));
+  SGC_CUDA(cudaMemcpy(d_chunk_first, first.data(), sizeof(int) * (size_t)(nchunk + 2), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -363,6 +399,8 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
   if (elem_bytes != 8 && elem_bytes != 4 && elem_bytes != 1)
     return fail(SGC_ERR_UNSUPPORTED, "sgc_level_create: elem_bytes must be 8, 4 or 1");
   sgc_level_s* l = new sgc_level_s;
+  static unsigned long long next_generation = 0;
+  l->generation = ++next_generation;
   l->nbox = nbox; l->ncomp = ncomp; l->ng = nghost; l->esz = elem_bytes; l->gidx0 = global_index0;
   l->boxes.resize(nbox); l->off.resize(nbox); l->geom.resize(nbox);
   long long off = 0, moff = 0, xoff = 0;
@@ -415,8 +453,8 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
       make_items(cin, l->geom[b], f, 0, dg, f, 0, ncomp, ~0u);
       make_items(cout, dg, f, 0, l->geom[b], f, 0, ncomp, ~0u);
     }
-    int st = l->conv_in.upload(cin);
-    if (!st) st = l->conv_out.upload(cout);
+    int st = l->conv_in.upload(cin, elem_bytes);
+    if (!st) st = l->conv_out.upload(cout, elem_bytes);
     if (st) { sgc_level_destroy(l); return st; }
   }
   e = cudaMalloc(&l->d_geom, sizeof(FabGeom) * (size_t)nbox);
@@ -457,12 +495,15 @@ int sgc_level_destroy(sgc_level_t l) {
 }
 
 long long sgc_level_elems(sgc_level_t l) { return l ? l->elems : -1; }
+int sgc_level_edge_strips(sgc_level_t l) { return (!l || !l->xe_elems) ? -1 : l->xe_valid; }
 long long sgc_level_fab_offset(sgc_level_t l, int box) {
   if (!l || box < 0 || box >= l->nbox) return -1;
   return l->off[box];
 }
 void* sgc_level_device_ptr(sgc_level_t l, int box) {
   if (!l || box < 0 || box >= l->nbox) return nullptr;
+  l->xe_extern = true;           // the caller may write valid cells behind the edge strips' back from now on
+  l->xe_valid = 0;
   return (char*)l->d_arena + l->geom[box].off * l->esz;     // main block of the fab (split-x layout)
 }
 
@@ -495,7 +536,8 @@ static int convert_box(sgc_level_s* l, int box, void* buf, bool to_device) {
   if (to_device) make_items(v, l->geom[box], f, 0, dg, f, 0, l->ncomp, ~0u);
   else make_items(v, dg, f, 0, l->geom[box], f, 0, l->ncomp, ~0u);
   CopyTable t;
-  int st = t.upload(v);
+  int st = t.upload(v, l->esz);
+  if (to_device) level_written(l);
   if (!st) st = to_device ? launch_copy(t, l->d_arena, buf, l->esz, rt().compute)
                           : launch_copy(t, buf, l->d_arena, l->esz, rt().compute);
   if (!st) cudaStreamSynchronize(rt().compute);
@@ -511,6 +553,7 @@ int sgc_level_upload(sgc_level_t l, int box, const void* host) {
   if (st) return st;
   // H2D in the reference's memory order, then one batched kernel into the split-x arena
   SGC_CUDA(cudaMemcpyAsync(rt().d_stage, host, (size_t)n * l->esz, cudaMemcpyHostToDevice, rt().compute));
+  level_written(l);
   if (box < 0) return convert_level(l, rt().d_stage, true, rt().compute);
   return convert_box(l, box, rt().d_stage, true);
 }
@@ -588,6 +631,7 @@ int sgc_level_upload_async(sgc_level_t l, const void* host, sgc_stream_t x) {
   int st = stream_stage(x, bytes);
   if (st) return st;
   SGC_CUDA(cudaMemcpyAsync(x->d_stage, host, bytes, cudaMemcpyHostToDevice, x->s));
+  level_written(l);
   return convert_level(l, x->d_stage, true, x->s);
 }
 
@@ -623,7 +667,7 @@ static int ensure_valid_table(sgc_level_s* l) {
     off += vb.size() * l->ncomp;
   }
   l->valid_elems = off;
-  return l->conv_valid.upload(v);
+  return l->conv_valid.upload(v, l->esz);
 }
 
 int sgc_level_download_valid(sgc_level_t l, void* host) {
@@ -656,6 +700,7 @@ int sgc_level_setval(sgc_level_t l, int box, int comp, const void* value) {
   if (!l || !value || box < -1 || box >= l->nbox || comp < -1 || comp >= l->ncomp)
     return fail(SGC_ERR_ARG, "sgc_level_setval: bad argument");
   const int b0 = box < 0 ? 0 : box, b1 = box < 0 ? l->nbox : box + 1;
+  level_written(l);
   if (comp < 0 && box < 0) {
     int st = launch_fill(l->d_arena, l->main_elems, l->esz, value, rt().compute);
     if (!st && l->arena_elems > l->xg_base)
@@ -683,6 +728,7 @@ int sgc_level_copy(sgc_level_t dst, sgc_level_t src) {
   if (!dst || !src) return fail(SGC_ERR_ARG, "sgc_level_copy: null level");
   if (!same_geometry(dst, src)) return fail(SGC_ERR_GEOMETRY, "sgc_level_copy: levels must share geometry");
   if (dst == src) return 0;
+  level_written(dst);
   SGC_CUDA(cudaMemcpyAsync(dst->d_arena, src->d_arena, (size_t)dst->arena_elems * dst->esz, cudaMemcpyDeviceToDevice,
                            rt().compute));
   return 0;
@@ -708,7 +754,8 @@ int sgc_fab_copy(sgc_level_t dst, int dst_box, const int dlo[3], const int dhi[3
   std::vector<CopyItem> v;
   make_items(v, gd, dr, dst_comp, gs, sr, src_comp, ncomp, comp_flags);
   CopyTable t;
-  int st = t.upload(v);
+  int st = t.upload(v, dst->esz);
+  level_written(dst);
   if (!st) st = launch_copy(t, dst->d_arena, src->d_arena, dst->esz, rt().compute);
   if (!st) cudaStreamSynchronize(rt().compute);
   t.release();
@@ -755,7 +802,7 @@ int sgc_copyset_create(sgc_level_t dst, sgc_level_t src, const sgc_copy_op* ops,
   }
   c->esz = dst->esz;
   c->ncell = ncell;
-  const int st = c->table.upload(v);
+  const int st = c->table.upload(v, dst->esz);
   if (st) { delete c; return st; }
   *set = c;
   return 0;
@@ -766,6 +813,7 @@ int sgc_copyset_run(sgc_copyset_t c, sgc_level_t dst, sgc_level_t src) {
   if (!c || !dst || !src) return fail(SGC_ERR_ARG, "sgc_copyset_run: null argument");
   if (!set_matches(c, 0, dst) || !set_matches(c, 1, src))
     return fail(SGC_ERR_GEOMETRY, "sgc_copyset_run: levels differ from the ones the set was recorded on");
+  level_written(dst);
   return launch_copy(c->table, dst->d_arena, src->d_arena, c->esz, rt().compute);
 }
 
@@ -801,7 +849,7 @@ static int linear_io(sgc_level_t l, int box, const int rlo[3], const int rhi[3],
   int st = ensure_scratch(l, (size_t)pos * l->esz);
   if (st) return st;
   CopyTable t;
-  st = t.upload(v);
+  st = t.upload(v, l->esz);
   if (st) return st;
   if (out) {
     st = launch_copy(t, l->d_scratch, l->d_arena, l->esz, rt().compute);
@@ -813,6 +861,7 @@ static int linear_io(sgc_level_t l, int box, const int rlo[3], const int rhi[3],
   } else {
     cudaError_t e = cudaMemcpyAsync(l->d_scratch, buffer, (size_t)pos * l->esz, cudaMemcpyHostToDevice, rt().compute);
     if (e != cudaSuccess) st = fail(SGC_ERR_CUDA, cudaGetErrorString(e));
+    level_written(l);
     if (!st) st = launch_copy(t, l->d_arena, l->d_scratch, l->esz, rt().compute);
     if (!st) cudaStreamSynchronize(rt().compute);
   }
@@ -840,8 +889,12 @@ static sgc_plan_s* new_plan_for(sgc_level_s* l, int c0, int nc) {
 }
 
 static int upload_local_items(sgc_plan_s* p, sgc_level_s* l) {
-  std::vector<CopyItem> v;
+  std::vector<CopyItem> v, vx;
   v.reserve(p->items.size());
+  // a second table whose x-face / x-edge / corner sources (one column of the neighbour: nghost = 1) are the
+  // level's edge strips xe[box][kz][4][vny] instead of one 8-byte element per 8*vnx-byte row
+  const bool strips = l->xe_elems > 0 && p->c0 == 0 && p->nc == 1;
+  if (strips) vx.reserve(p->items.size());
   p->nremote = 0;
   for (const sgc_motion_item& it : p->items) {
     const int ld = it.recv_box - l->gidx0;
@@ -854,11 +907,31 @@ static int upload_local_items(sgc_plan_s* p, sgc_level_s* l) {
     if (dr.empty()) continue;
     if (!fab_contains(l->geom[ld], dr) || !fab_contains(l->geom[ls], sr))
       return fail(SGC_ERR_ARG, "plan: motion item region outside its fab (nghost of the level too small?)");
+    const size_t n0 = v.size();
     make_items(v, l->geom[ld], dr, p->c0, l->geom[ls], sr, p->c0, p->nc, it.comp_flags);
+    if (strips) {
+      const FabGeom& gs = l->geom[ls];
+      const int vhi = gs.vlo[0] + gs.vn[0] - 1;
+      bool valid_src = sr.ext(0) == 1 && (sr.lo[0] == gs.vlo[0] || sr.lo[0] == vhi) && v.size() == n0 + 1;
+      for (int d = 1; d < 3; ++d) valid_src = valid_src && sr.lo[d] >= gs.vlo[d] && sr.hi[d] < gs.vlo[d] + gs.vn[d];
+      for (size_t k = n0; k < v.size(); ++k) {
+        CopyItem c = v[k];
+        if (valid_src) {
+          const int strip = sr.lo[0] == gs.vlo[0] ? 0 : 3;
+          c.src = l->xe_base + (((long long)ls * gs.vn[2] + (sr.lo[2] - gs.vlo[2])) * 4 + strip) * gs.vn[1] + (sr.lo[1] - gs.vlo[1]);
+          c.ssx = 0; c.ssy = 1; c.ssz = 4 * gs.vn[1];
+        }
+        vx.push_back(c);
+      }
+    }
   }
   p->n_boundary_boxes = 0;
   for (char c : p->box_is_boundary) p->n_boundary_boxes += c;
-  return p->local.upload(v);
+  if (strips) {
+    const int st = p->local_xe.upload(vx, l->esz);
+    if (st) return st;
+  }
+  return p->local.upload(v, l->esz);
 }
 
 int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], const int maxbox[3], unsigned periodic,
@@ -878,6 +951,10 @@ int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], 
   }
   sgc_plan_s* p = new_plan_for(l, comp_begin, ncomp);
   p->nproc = nproc; p->rank = rank;
+  p->ghost_only = true;          // motion items of an exchange write ghost cells only (Copier.H:521-659)
+  p->has_grid = true;
+  for (int d = 0; d < 3; ++d) { p->dlo[d] = dlo[d]; p->dhi[d] = dhi[d]; p->maxbox[d] = maxbox[d]; }
+  p->periodic = periodic; p->trim = trim;
   int st = build_exchange_items(g, l->ng, periodic, trim, rank, p->items);
   if (!st) st = upload_local_items(p, l);
   if (!st && p->nremote > 0) st = comm_plan_setup(p, l, g, periodic, trim);
@@ -945,16 +1022,22 @@ int sgc_plan_create_bc_zero_gradient(sgc_level_t l, const int dlo[3], const int 
         items.push_back(it);
       }
   }
-  return sgc_plan_create_items(l, items.data(), (int)items.size(), 0, l->ncomp, plan);
+  const int st = sgc_plan_create_items(l, items.data(), (int)items.size(), 0, l->ncomp, plan);
+  if (!st) (*plan)->ghost_only = true;
+  return st;
 }
+
+static void rebox_release(sgc_plan_s* p);
 
 int sgc_plan_destroy(sgc_plan_t p) {
   if (!p) return 0;
   if (rt().ready) { cudaStreamSynchronize(rt().compute); cudaStreamSynchronize(rt().comm); }
   p->local.release();
+  p->local_xe.release();
   if (p->d_push) cudaFree(p->d_push);
   comm_p2p_release(p);
   comm_plan_release(p);
+  rebox_release(p);
   delete p;
   return 0;
 }
@@ -984,7 +1067,10 @@ int sgc_exchange_begin(sgc_level_t l, sgc_plan_t p) {
   int st;
   {
     ProfScope prof(1, rt().compute);
-    st = launch_copy(p->local, l->d_arena, l->d_arena, l->esz, rt().compute);
+    // x-face sources: the level's edge strips (dense) when they mirror its valid cells, else the main blocks
+    const bool strips = p->local_xe.nitem > 0 && l->xe_valid >= 1 && !getenv("SGC_NO_XE");
+    if (!p->ghost_only) level_written(l);
+    st = launch_copy(strips ? p->local_xe : p->local, l->d_arena, l->d_arena, l->esz, rt().compute);
   }
   if (st) return st;
   p->in_flight = true;
@@ -1031,6 +1117,7 @@ int sgc_heat_sweep_range(sgc_level_t unew, sgc_level_t u, double f, unsigned fla
   st = launch_heat_stream(unew, u, f, fma, box_begin, box_end, rt().compute);
   if (st <= 0) return st;
   const int w0 = unew->work_begin[box_begin], w1 = unew->work_begin[box_end];
+  level_written(unew);
   return launch_heat_generic(unew->d_work, w0, w1 - w0, u->d_geom, unew->d_geom, (const double*)u->d_arena,
                              (double*)unew->d_arena, f, fma, rt().compute);
 }
@@ -1048,6 +1135,7 @@ int sgc_laplacian_apply(sgc_level_t B, sgc_level_t A, double coef, int niter, in
   if (niter < 0) return fail(SGC_ERR_ARG, "sgc_laplacian_apply: niter");
   const int launches = fuse_iters ? 1 : niter;
   const int per = fuse_iters ? niter : 1;
+  level_written(B);
   for (int i = 0; i < launches && !st; ++i)
     st = launch_lap_generic(B->d_work, 0, B->nwork, A->d_geom, B->d_geom, (const double*)A->d_arena,
                             (double*)B->d_arena, coef, (flags & SGC_FMA) ? 1 : 0, per, rt().compute);
@@ -1061,6 +1149,7 @@ int sgc_wave_step(sgc_level_t unp1, sgc_level_t un, sgc_level_t unm1, double fac
   if (!unm1 || !same_geometry(un, unm1)) return fail(SGC_ERR_GEOMETRY, "sgc_wave_step: un and unm1 must share geometry");
   if (unm1 == unp1) return fail(SGC_ERR_ARG, "sgc_wave_step: unp1 must not alias unm1");
   ProfScope prof(0, rt().compute);
+  level_written(unp1);
   const int wf = (int)(flags & (SGC_FMA | SGC_WAVE_DIRSUM));      // bit 0 fma, bit 1 dirsum form
   st = launch_wave_stream(unp1, un, unm1, factor, wf, rt().compute);
   if (st <= 0) return st;
@@ -1128,6 +1217,140 @@ static int fused_sweep(sgc_level_t nxt, sgc_level_t cur, double f, unsigned flag
   return st > 0 ? fail(SGC_ERR_UNSUPPORTED, "fused sweep: no streaming kernel for this geometry") : st;
 }
 
+// `npass` two-step passes (sgc_stream2.cu) starting from level `cur` of the pair (a, b); a is the level whose
+// physical-boundary ghost cells belong to the even steps.  p2p: z tiles come out of the neighbouring GPUs' memory.
+static int run_t2_passes(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags, int npass, bool p2p,
+                         sgc_level_t& cur, sgc_level_t& nxt) {
+  sgc_plan_s::P2P& S = plan->p2p;
+  int st = 0;
+  if (cur->xe_valid != 2) st = launch_build_xe(cur, rt().compute);
+  if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);     // our strips are readable
+  for (int k = 0; k < npass && !st; ++k) {
+    T2Args ra;
+    memset(&ra, 0, sizeof ra);
+    if (p2p) {
+      const int li = (cur == S.lev[0]) ? 0 : 1;
+      ra.rz = S.d_rz;
+      for (int q = 0; q < S.npeer; ++q) {
+        ra.peer_in[q] = (const double*)((char*)S.peer_base[q][li] + cur->lead * cur->esz);
+        ra.peer_flag[q] = (const unsigned long long*)S.peer_flag_base[q];
+      }
+      ra.wait_value = S.counter;
+      ra.err = S.d_err;
+    }
+    if (plan->t2_bnd) {
+      // faces without a neighbour: step t of the run reads level a's ghost cells, step t+1 level b's —
+      // whichever level currently holds the valid cells (passes start on even steps)
+      ra.ghost[0] = (const double*)a->d_arena;
+      ra.ghost[1] = (const double*)b->d_arena;
+      if (p2p) {
+        const int ia = (a == S.lev[0]) ? 0 : 1;
+        for (int q = 0; q < S.npeer; ++q) {
+          ra.peer_ghost[q][0] = (const double*)((char*)S.peer_base[q][ia] + a->lead * a->esz);
+          ra.peer_ghost[q][1] = (const double*)((char*)S.peer_base[q][ia ^ 1] + b->lead * b->esz);
+        }
+      }
+    }
+    {
+      ProfScope prof(2, rt().compute);
+      st = launch_heat_t2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, plan->d_push, &ra, rt().compute);
+    }
+    if (st > 0) st = fail(SGC_ERR_UNSUPPORTED, "two-step sweep: geometry not covered");
+    if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);
+    std::swap(cur, nxt);
+  }
+  if (!st && p2p) st = comm_p2p_check(plan);
+  return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Re-boxed step loop for levels of many small boxes (BASELINE config "32 768 boxes of 16^3").
+// A 16^3 fab carries 18^3 cells, its two-step tile would carry 20^2 per plane: the halo overhead, not
+// HBM, bounds such levels (one-step sweep: 273 Gcell-updates/s at 0.86 of the copy bandwidth).  Valid
+// cells do not depend on how the domain is cut into boxes (every cell is updated with the same operations
+// in the same order from the same neighbours), so inside sgc_heat_run the level is advanced on a
+// library-owned pair of levels whose fabs are UNIONS of cx x cy x cz of the user's boxes (64^2 footprint,
+// up to 64 planes): one batched copy gathers the valid cells (and, on non-periodic sides, the physical
+// ghost faces of both levels, which no exchange ever writes), the two-step passes run on the unions,
+// one batched copy scatters the result back, and the user's levels run the last two (three) steps
+// themselves, which restores every ghost cell of both levels exactly as the step-by-step schedule leaves it.
+// ---------------------------------------------------------------------------------------------
+static void rebox_release(sgc_plan_s* p) {
+  sgc_plan_s::Rebox& R = p->rebox;
+  R.f2c.release(); R.f2c_ghost.release(); R.c2f.release();
+  if (R.plan) sgc_plan_destroy(R.plan);
+  for (int k = 0; k < 2; ++k) if (R.lev[k]) sgc_level_destroy(R.lev[k]);
+  R = sgc_plan_s::Rebox();
+}
+
+static int rebox_setup(sgc_plan_s* p, sgc_level_s* a) {
+  sgc_plan_s::Rebox& R = p->rebox;
+  if (R.tried) return 0;
+  R.tried = true;
+  if (!p->has_grid || p->nproc != 1 || !a->uniform || a->ncomp != 1 || a->ng != 1 || a->esz != 8 || (p->trim & SGC_TRIM_FACE) ||
+      getenv("SGC_NO_REBOX"))
+    return 0;
+  Grid g(p->dlo, p->dhi, p->maxbox, 1);
+  if (g.status) return 0;
+  // union factors: 64^2 (else 32^2) footprint, as many planes as divide the grid up to 64
+  int c[3] = {1, 1, 1};
+  bool found = false;
+  for (int T = 64; T >= 32 && !found; T /= 2) {
+    if (T % p->maxbox[0] || T % p->maxbox[1]) continue;
+    c[0] = T / p->maxbox[0]; c[1] = T / p->maxbox[1];
+    if (g.nb[0] % c[0] || g.nb[1] % c[1]) continue;
+    c[2] = 1;
+    for (int k = 64 / p->maxbox[2]; k >= 1; --k)
+      if (k * p->maxbox[2] <= 64 && g.nb[2] % k == 0) { c[2] = k; break; }
+    const int vz = c[2] * p->maxbox[2];
+    found = (c[0] > 1 || c[1] > 1) && vz >= 4 && vz % 2 == 0;
+  }
+  if (!found) return 0;
+  int cmb[3];
+  for (int d = 0; d < 3; ++d) { cmb[d] = p->maxbox[d] * c[d]; R.factor[d] = c[d]; }
+  Grid cg(p->dlo, p->dhi, cmb, 1);
+  if (cg.status) return 0;
+  std::vector<int> boxes6((size_t)cg.nbox * 6);
+  for (int i = 0; i < cg.nbox; ++i) {
+    const IBox bx = cg.box(i);
+    for (int d = 0; d < 3; ++d) { boxes6[6 * i + d] = bx.lo[d]; boxes6[6 * i + 3 + d] = bx.hi[d]; }
+  }
+  int st = sgc_level_create(boxes6.data(), cg.nbox, 1, 1, 8, 0, &R.lev[0]);
+  if (!st) st = sgc_level_create(boxes6.data(), cg.nbox, 1, 1, 8, 0, &R.lev[1]);
+  if (!st) st = sgc_plan_create_exchange(R.lev[0], p->dlo, p->dhi, cmb, p->periodic, 0, 0, 1, 1, 0, &R.plan);
+  if (st || !heat_t2_covers(R.lev[1], R.lev[0]) || !(R.plan->t2_local || R.plan->t2_bnd)) { rebox_release(p); R.tried = true; return st; }
+  std::vector<CopyItem> in, gh, out;
+  for (int i = 0; i < g.nbox; ++i) {
+    const int ci = (i % g.nb[0]) / c[0] + cg.nb[0] * (((i / g.nb[0]) % g.nb[1]) / c[1] + cg.nb[1] * ((i / (g.nb[0] * g.nb[1])) / c[2]));
+    const IBox& vb = a->boxes[i];
+    const FabGeom& fg = a->geom[i];
+    const FabGeom& ug = R.lev[0]->geom[ci];
+    make_items(in, ug, vb, 0, fg, vb, 0, 1, ~0u);
+    make_items(out, fg, vb, 0, ug, vb, 0, 1, ~0u);
+    for (int d = 0; d < 3; ++d) {
+      if (p->periodic & (1u << d)) continue;
+      for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? vb.lo[d] != p->dlo[d] : vb.hi[d] != p->dhi[d]) continue;
+        IBox face = vb;
+        face.lo[d] = face.hi[d] = side == 0 ? vb.lo[d] - 1 : vb.hi[d] + 1;
+        make_items(gh, ug, face, 0, fg, face, 0, 1, ~0u);
+      }
+    }
+  }
+  st = R.f2c.upload(in, 8);
+  if (!st) st = R.c2f.upload(out, 8);
+  if (!st) st = R.f2c_ghost.upload(gh, 8);
+  if (st) { rebox_release(p); R.tried = true; return st; }
+  R.ok = true;
+  return 0;
+}
+
+int sgc_plan_rebox_factors(sgc_plan_t p, int factor[3]) {
+  if (!p || !factor) return fail(SGC_ERR_ARG, "sgc_plan_rebox_factors: null argument");
+  for (int d = 0; d < 3; ++d) factor[d] = p->rebox.ok ? p->rebox.factor[d] : 1;
+  return p->rebox.tried ? 1 : 0;
+}
+
 int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags, int nstep, int* result_in_b) {
   SGC_REQUIRE_RT();
   if (!a || !b || !plan || nstep < 0) return fail(SGC_ERR_ARG, "sgc_heat_run: bad argument");
@@ -1146,6 +1369,32 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
   }
   sgc_level_t cur = a, nxt = b;
   int st = 0;
+  int s0 = 0;
+
+  // ---- re-boxed passes (levels of many small boxes, single rank): all but the last two / three steps run as
+  // two-step passes on the union fabs; the plain schedule at the bottom finishes on the user's levels
+  if (nstep >= 8 && !plan->rebox.tried) { st = rebox_setup(plan, a); if (st) return st; }
+  const bool reboxed = nstep >= 8 && plan->rebox.ok;
+  if (reboxed) {
+    sgc_plan_s::Rebox& R = plan->rebox;
+    const int sc = (nstep - 2) & ~1;
+    {
+      ProfScope prof(1, rt().compute);
+      level_written(R.lev[0]);
+      st = launch_copy(R.f2c, R.lev[0]->d_arena, a->d_arena, 8, rt().compute);
+      if (!st) st = launch_copy(R.f2c_ghost, R.lev[0]->d_arena, a->d_arena, 8, rt().compute);
+      if (!st) st = launch_copy(R.f2c_ghost, R.lev[1]->d_arena, b->d_arena, 8, rt().compute);
+    }
+    sgc_level_t ccur = R.lev[0], cnxt = R.lev[1];
+    if (!st) st = run_t2_passes(R.lev[0], R.lev[1], R.plan, f, flags, sc / 2, false, ccur, cnxt);
+    if (!st) {
+      ProfScope prof(1, rt().compute);
+      level_written(a);
+      st = launch_copy(R.c2f, a->d_arena, ccur->d_arena, 8, rt().compute);
+    }
+    if (st) return st;
+    s0 = sc;                     // even: the step-by-step schedule has this state in level a, too
+  }
 
   // ---- fused schedule ("pull y/z, push x", sgc_stream.cu): no exchange launch inside the loop.
   // One full exchange first (x strips and the ghosts facing physical boundaries / other GPUs);
@@ -1156,11 +1405,10 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
   // Boxes at least 32 cells wide: x faces pushed by the consumers, y/z pulled by the producer.
   // Narrower boxes: everything pulled — z planes by the producer, x strips and y rows by the gather
   // warp (sgc_stream.cu) — because on 16^3 boxes every 8th cell lies on an x face.
-  const bool fused = plan->fusable && nstep >= 3 && heat_stream_covers(b, a) && !getenv("SGC_NO_FUSE");
+  const bool fused = !reboxed && plan->fusable && nstep >= 3 && heat_stream_covers(b, a) && !getenv("SGC_NO_FUSE");
   const int fmask = 7;                                 // bit 0 push x, bit 1 pull z, bit 2 pull y
   const char* cs = getenv("SGC_COMM_SMS");
   const int comm_sms = cs ? atoi(cs) : 8;              // SMs left to pack / NCCL / unpack during the interior sweep
-  int s0 = 0;
   if (fused) {
     // Multi-GPU, z-slab partitions: the z ghost planes facing another GPU are pulled by the sweep's
     // producer straight out of that GPU's memory (cudaIpc-mapped arenas over NVLink), gated by a
@@ -1188,46 +1436,9 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
       t2 = t2 && plan->t2_agreed == 1;
     }
     if (npass >= 2 && t2) {
-      sgc_plan_s::P2P& S = plan->p2p;
-      st = launch_build_xe(cur, rt().compute);
-      if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);     // our strips are readable
-      for (int k = 0; k < npass && !st; ++k) {
-        T2Args ra;
-        memset(&ra, 0, sizeof ra);
-        if (p2p) {
-          const int li = (cur == S.lev[0]) ? 0 : 1;
-          ra.rz = S.d_rz;
-          for (int q = 0; q < S.npeer; ++q) {
-            ra.peer_in[q] = (const double*)((char*)S.peer_base[q][li] + cur->lead * cur->esz);
-            ra.peer_flag[q] = (const unsigned long long*)S.peer_flag_base[q];
-          }
-          ra.wait_value = S.counter;
-          ra.err = S.d_err;
-        }
-        if (plan->t2_bnd) {
-          // faces without a neighbour: step t of the run reads level a's ghost cells, step t+1 level b's —
-          // whichever level currently holds the valid cells (s0 is even here, so `a` is the level of step t)
-          ra.ghost[0] = (const double*)a->d_arena;
-          ra.ghost[1] = (const double*)b->d_arena;
-          if (p2p) {
-            const int ia = (a == S.lev[0]) ? 0 : 1;
-            for (int q = 0; q < S.npeer; ++q) {
-              ra.peer_ghost[q][0] = (const double*)((char*)S.peer_base[q][ia] + a->lead * a->esz);
-              ra.peer_ghost[q][1] = (const double*)((char*)S.peer_base[q][ia ^ 1] + b->lead * b->esz);
-            }
-          }
-        }
-        {
-          ProfScope prof(2, rt().compute);
-          st = launch_heat_t2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, plan->d_push, &ra, rt().compute);
-        }
-        if (st > 0) st = fail(SGC_ERR_UNSUPPORTED, "two-step sweep: geometry not covered");
-        if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);
-        std::swap(cur, nxt);
-        s0 += 2;
-      }
-      if (!st && p2p) st = comm_p2p_check(plan);
+      st = run_t2_passes(a, b, plan, f, flags, npass, p2p, cur, nxt);
       if (st) return st;
+      s0 += 2 * npass;
     }
     // the exchange below also orders the phases on a multi-GPU run: its receives complete only after
     // the neighbours have left their last pass, so their reads of our levels are over

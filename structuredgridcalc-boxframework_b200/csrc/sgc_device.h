@@ -62,16 +62,21 @@ struct CopyItem {
   int c0;          // first destination component (for the mask test)
 };
 
+// Items of 8-byte elements whose rows are even-length, contiguous and 16-byte aligned on both sides are
+// WIDE: they are stored first, in units of 16 bytes (offsets, x extent and strides halved), and run by
+// the first `nwchunk` CTAs of the launch with 16-byte loads / stores.  "Cells" below are work units:
+// 16-byte units [0, nwcell) of the wide items, then elements [nwcell, ncell) of the others.
 struct CopyTable {
   CopyItem* d_items = nullptr;
-  long long* d_cell_start = nullptr;   // exclusive prefix sum of item cell counts, n+1 entries
-  int* d_chunk_first = nullptr;        // first item overlapping chunk c, nchunk+1 entries
+  long long* d_cell_start = nullptr;   // exclusive prefix sum of item unit counts, n+1 entries
+  int* d_chunk_first = nullptr;        // first item overlapping chunk c; one past each class a closing entry
   int nitem = 0;
-  int nchunk = 0;
-  long long ncell = 0;
+  int nchunk = 0;                      // CTAs of the launch: nwchunk wide + the rest
+  int nwitem = 0, nwchunk = 0;
+  long long ncell = 0, nwcell = 0;
   bool strided_reads = false;          // a good share of the cells are single elements of long rows (x faces)
   void release();
-  int upload(const std::vector<CopyItem>& items);
+  int upload(const std::vector<CopyItem>& items, int esz = 0);   // esz 8 enables the wide class
 };
 
 // geometry helpers (sgc_device.cu)
@@ -155,6 +160,9 @@ struct PushArgs {
   const unsigned long long* peer_flag[2];    // the peers' progress counters (cudaIpc-mapped)
   unsigned long long wait_value;             // counter value that makes the peers' input level readable
   unsigned int* err;                         // set to 1 when a wait timed out
+  // edge strips of the OUTPUT level (sgc_level_s::xe_base), or null: the threads that compute the first /
+  // last cell of a row also store it there, so that the next exchange reads its x faces densely
+  double* xe_out;
 };
 
 // Arguments of the two-steps-per-pass sweep (sgc_stream2.cu).
@@ -206,6 +214,13 @@ struct sgc_level_s {
   // edge strips [box][kz][4][vny] (copies of the valid columns 0, 1, vnx-2, vnx-1) read by the two-step
   // sweep (sgc_stream2.cu); allocated behind the arena for levels that kernel covers, else xe_elems = 0
   long long xe_base = 0, xe_elems = 0;
+  // which strips mirror the valid cells right now: 0 none, 1 the outer columns (0 and vnx-1: what an
+  // exchange needs for its x faces), 2 all four.  Every writer of valid cells either keeps them current
+  // (the streaming sweeps, k_build_xe) or resets this (sgc::level_written); handing out the raw device
+  // pointer (sgc_level_device_ptr) turns the mechanism off for the level for good.
+  int xe_valid = 0;
+  bool xe_extern = false;
+  unsigned long long generation = 0;    // unique per created level (peer-memory sessions are keyed on it)
   sgc::CopyTable conv_in, conv_out;     // reference-order staging <-> split-x arena, whole level
   sgc::CopyTable conv_valid;            // arena -> [box][comp] valid cells only (plot output), built on first use
   long long valid_elems = 0;
@@ -221,6 +236,10 @@ struct sgc_level_s {
   size_t scratch_bytes = 0;
 };
 
+namespace sgc {
+inline void level_written(sgc_level_s* l) { l->xe_valid = 0; }      // valid cells changed behind the strips' back
+}
+
 struct sgc_plan_s {
   // geometry signature of the level the plan was built for
   int nbox = 0, ncomp = 0, ng = 0, esz = 0, gidx0 = 0;
@@ -230,6 +249,14 @@ struct sgc_plan_s {
   std::vector<sgc_motion_item> items;   // this rank's items, reference order
   int nremote = 0;
   sgc::CopyTable local;                 // local items: arena -> arena
+  // the same items with every x-face / x-edge source column read from the level's edge strips (dense)
+  // instead of one 8-byte element per row of the neighbour's main block; used when level->xe_valid
+  sgc::CopyTable local_xe;
+  bool ghost_only = false;              // every item writes ghost cells only (exchange and BC plans)
+  // the uniform layout the plan was derived from (sgc_plan_create_exchange), for re-boxing
+  bool has_grid = false;
+  int dlo[3] = {0, 0, 0}, dhi[3] = {0, 0, 0}, maxbox[3] = {0, 0, 0};
+  unsigned periodic = 0, trim = 0;
   // multi-rank: per-peer staging
   struct Peer {
     int rank = -1;
@@ -266,7 +293,19 @@ struct sgc_plan_s {
     unsigned int* d_err = nullptr;
     int* d_rz = nullptr;                     // [nbox][2]
     unsigned long long counter = 0;          // value last signalled
+    unsigned long long gen[2] = {0, 0};      // generations of lev[0], lev[1] (a recycled address is not the same level)
   } p2p;
+  // Re-boxed step loop (sgc_device.cu: rebox_setup): a level of many small boxes (16^3, 32^3, 8^3) is
+  // advanced on a library-owned pair of levels whose device fabs are 64^2-footprint unions of the user's
+  // boxes, so that the two-step sweep runs at its 64^3-box speed; the user's levels receive the result
+  // and run the last steps themselves.  Built on first use, lives as long as the plan.
+  struct Rebox {
+    bool tried = false, ok = false;
+    sgc_level_s* lev[2] = {nullptr, nullptr};
+    sgc_plan_s* plan = nullptr;
+    sgc::CopyTable f2c, f2c_ghost, c2f;      // user's fabs -> union fabs (valid cells; physical ghost faces) and back
+    int factor[3] = {1, 1, 1};
+  } rebox;
 };
 
 struct sgc_event_s {

@@ -14,7 +14,8 @@ namespace sgc {
 // bit-identical to the reference's serial loop, LevelData.H:471-486).
 //
 // Work split: the items' cells are numbered consecutively (prefix sum cell_start[]); CTA c owns
-// cells [c*kCopyChunk, (c+1)*kCopyChunk).  chunk_first[c] is the first item overlapping the
+// cells [c*kCopyChunk, (c+1)*kCopyChunk) of its class (16-byte "wide" items first, see CopyTable in
+// sgc_device.h).  chunk_first[c] is the first item overlapping the
 // chunk, so a thread finds its item with a short binary search over a handful of entries (one
 // entry for a 64x64 face, up to kCopyChunk entries when the chunk is all single-cell corners).
 // Balanced regardless of the face/edge/corner mix (C3: 851 968 items from 1 to 256 cells).
@@ -30,18 +31,15 @@ __device__ __forceinline__ uint64_t ld_small_fetch<uint64_t>(const uint64_t* p) 
   return v;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kCopyThreads)
-k_copy_items(const CopyItem* __restrict__ items, const long long* __restrict__ cell_start,
-             const int* __restrict__ chunk_first, T* __restrict__ dst_arena,
-             const T* __restrict__ src_arena, long long ncell, int getenv_small_fetch) {
-  const long long base = (long long)blockIdx.x * kCopyChunk;
-  const int it_lo = chunk_first[blockIdx.x];
-  const int it_hi = chunk_first[blockIdx.x + 1];   // last item that can overlap this chunk
+// one unit (an element, or 16 bytes of a wide item) per thread and iteration
+template <typename T, bool SMALL_FETCH_OK>
+__device__ __forceinline__ void copy_units(const CopyItem* __restrict__ items, const long long* __restrict__ cell_start,
+                                           int it_lo, int it_hi, long long base, long long end, T* __restrict__ dst_arena,
+                                           const T* __restrict__ src_arena, int small_fetch) {
 #pragma unroll 2
   for (int t = threadIdx.x; t < kCopyChunk; t += kCopyThreads) {
     const long long cell = base + t;
-    if (cell >= ncell) break;
+    if (cell >= end) break;
     // largest it in [it_lo, it_hi] with cell_start[it] <= cell
     int lo = it_lo, hi = it_hi;
     while (lo < hi) {
@@ -59,26 +57,50 @@ k_copy_items(const CopyItem* __restrict__ items, const long long* __restrict__ c
     if (dc < 32u && !((I->flags >> dc) & 1u)) continue;
     const long long d = I->dst + c * I->dcs + (long long)x * I->dsx + (long long)y * I->dsy + (long long)z * I->dsz;
     const long long s = I->src + c * I->scs + (long long)x * I->ssx + (long long)y * I->ssy + (long long)z * I->ssz;
-    dst_arena[d] = (getenv_small_fetch != 0) ? ld_small_fetch(src_arena + s) : src_arena[s];
+    if (SMALL_FETCH_OK) dst_arena[d] = (small_fetch != 0) ? ld_small_fetch(src_arena + s) : src_arena[s];
+    else dst_arena[d] = src_arena[s];
   }
+}
+
+// CTAs [0, nwchunk) run the wide items (16-byte units, 8-byte element tables only), the others the rest.
+template <typename T>
+__global__ void __launch_bounds__(kCopyThreads)
+k_copy_items(const CopyItem* __restrict__ items, const long long* __restrict__ cell_start,
+             const int* __restrict__ chunk_first, T* __restrict__ dst_arena,
+             const T* __restrict__ src_arena, long long ncell, int getenv_small_fetch, int nwchunk, long long nwcell) {
+  if (sizeof(T) == 8 && (int)blockIdx.x < nwchunk) {
+    const long long base = (long long)blockIdx.x * kCopyChunk;
+    const long long end = base + kCopyChunk < nwcell ? base + kCopyChunk : nwcell;
+    copy_units<ulonglong2, false>(items, cell_start, chunk_first[blockIdx.x], chunk_first[blockIdx.x + 1], base, end,
+                                  reinterpret_cast<ulonglong2*>(dst_arena), reinterpret_cast<const ulonglong2*>(src_arena), 0);
+    return;
+  }
+  const int c = (int)blockIdx.x - nwchunk;
+  const long long base = nwcell + (long long)c * kCopyChunk;
+  const long long end = base + kCopyChunk < ncell ? base + kCopyChunk : ncell;
+  copy_units<T, true>(items, cell_start, chunk_first[blockIdx.x + 1], chunk_first[blockIdx.x + 2], base, end, dst_arena,
+                      src_arena, getenv_small_fetch);
 }
 
 int launch_copy(const CopyTable& t, void* dst_arena, const void* src_arena, int esz, cudaStream_t s) {
   if (t.nitem == 0 || t.ncell == 0) return 0;
   static const char* sf_env = getenv("SGC_COPY_SMALL_FETCH");
   const int small_fetch = sf_env ? atoi(sf_env) : (t.strided_reads ? 1 : 0);
+  if (t.nwchunk > 0 && (esz != 8 || (((uintptr_t)dst_arena | (uintptr_t)src_arena) & 15)))
+    return fail(SGC_ERR_ARG, "copy table has 16-byte items but the buffers are not 16-byte aligned 8-byte arrays");
   switch (esz) {
     case 8:
       k_copy_items<uint64_t><<<t.nchunk, kCopyThreads, 0, s>>>(t.d_items, t.d_cell_start, t.d_chunk_first,
-                                                               (uint64_t*)dst_arena, (const uint64_t*)src_arena, t.ncell, small_fetch);
+                                                               (uint64_t*)dst_arena, (const uint64_t*)src_arena, t.ncell, small_fetch,
+                                                               t.nwchunk, t.nwcell);
       break;
     case 4:
       k_copy_items<uint32_t><<<t.nchunk, kCopyThreads, 0, s>>>(t.d_items, t.d_cell_start, t.d_chunk_first,
-                                                               (uint32_t*)dst_arena, (const uint32_t*)src_arena, t.ncell, small_fetch);
+                                                               (uint32_t*)dst_arena, (const uint32_t*)src_arena, t.ncell, small_fetch, 0, 0);
       break;
     case 1:
       k_copy_items<uint8_t><<<t.nchunk, kCopyThreads, 0, s>>>(t.d_items, t.d_cell_start, t.d_chunk_first,
-                                                              (uint8_t*)dst_arena, (const uint8_t*)src_arena, t.ncell, small_fetch);
+                                                              (uint8_t*)dst_arena, (const uint8_t*)src_arena, t.ncell, small_fetch, 0, 0);
       break;
     default:
       return fail(SGC_ERR_UNSUPPORTED, "element size must be 1, 4 or 8 bytes");

@@ -334,6 +334,9 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   const int fx = at_lo ? -1 : (at_hi ? 1 : 0);
   const long long fab_xg = (long long)2 * STRIP * n2;
   double* xdst = nullptr;      // x-face destination strip of the current fab (threads on an x face only)
+  // edge strips of the output level ([box][valid plane][4][VNY], columns 0 and VNX-1 = strips 0 and 3)
+  constexpr bool XE = (VNX >= 32 && OP == 0 && MODE == 0);
+  double* const xe_col = (XE && (at_lo || at_hi) && push.xe_out) ? push.xe_out + (at_lo ? 0 : 3 * VNY) + j0 : nullptr;
   int pbox = -1;               // box whose destination is cached
   int bcur = 0;                // box of plane q (tracked incrementally)
 
@@ -382,6 +385,8 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
           }
           if (xdst) xrow = xdst + (long long)kz_prev * N1;
         }
+        double* __restrict__ erow = nullptr;
+        if (XE) { if (xe_col) erow = xe_col + ((long long)bprev * (n2 - 2 * NG) + (kz_prev - NG)) * (4 * VNY); }
 #pragma unroll
         for (int m = 0; m < CPT; ++m) {
           const double zp = cur[m * NT];
@@ -408,6 +413,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
           }
           if (MODE != 2 || zp == 1.2345e300) po[m * NT] = r;
           if (PUSH && !GATHER) { if (xrow) xrow[m * ROWS] = r; }
+          if (XE) { if (erow) erow[m * ROWS] = r; }
           zm[m] = c;
           cc[m] = zp;
         }
@@ -476,15 +482,24 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
   pa.in_level = (const double*)u->d_arena;
   pa.xg_base = unew->xg_base;
   pa.box0 = a0;
+  // the sweep keeps the outer edge strips of its output current when it covers the whole level
+  const bool whole = (a0 == 0 && a1 == unew->nbox) || (a0 == 0 && b1 == unew->nbox && a1 == b0);
+  static const bool no_xe = getenv("SGC_NO_XE") != nullptr;
+  pa.xe_out = (whole && unew->xe_elems && !unew->xe_extern && !no_xe) ? (double*)unew->d_arena + unew->xe_base : nullptr;
+  unew->xe_valid = 0;
   if (const char* pm = getenv("SGC_PUSH_MASK")) pa.mask = atoi(pm);      // diagnostics
 #define SGC_STREAM_CASE(VX, VY, PS_, NS_, NCW_)                                                      \
   if (vnx == VX && vny == VY && n2 % PS_ == 0) {                                                     \
+    int st_;                                                                                         \
     if (fuse)                                                                                        \
-      return launch_cfg<VX, VY, 1, PS_, NS_, NCW_, 0, true, 0, (VX < 32)>(in_main, in_xg, out, (int)(planes / PS_), n2, \
-                                                                          f, fma, (int)(planesA / PS_),   \
-                                                                          (int)(gap / PS_), s, pa);       \
-    return launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
-                                                 (int)(planesA / PS_), (int)(gap / PS_), s);         \
+      st_ = launch_cfg<VX, VY, 1, PS_, NS_, NCW_, 0, true, 0, (VX < 32)>(in_main, in_xg, out, (int)(planes / PS_), n2, \
+                                                                         f, fma, (int)(planesA / PS_),   \
+                                                                         (int)(gap / PS_), s, pa);       \
+    else                                                                                             \
+      st_ = launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
+                                                  (int)(planesA / PS_), (int)(gap / PS_), s, pa);    \
+    if (st_ == 0 && pa.xe_out && VX >= 32) unew->xe_valid = 1;                                       \
+    return st_;                                                                                      \
   }
   if (const char* m = getenv("SGC_STREAM_MODE")) {      // diagnostics only
     if (vnx == 64 && vny == 64) {

@@ -470,6 +470,7 @@ int launch_build_xe(sgc_level_s* l, cudaStream_t s) {
                                   g.vn[2]);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
+  l->xe_valid = l->xe_extern ? 0 : 2;
   return 0;
 }
 
@@ -495,6 +496,7 @@ int launch_heat_t2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, const i
   a.f = f;
   // 64^2 boxes: 16 warps, 8 rows per thread; 32^2 boxes: 8 warps, 4 rows per thread, three CTAs per SM
   // (V = 64 with 32 warps of 4 rows — a 64-register cap — spills and is 1.5x slower)
+  unew->xe_valid = unew->xe_extern ? 0 : 2;        // stage 2 stores all four edge columns of every plane
   return g.vn[0] == 64 ? launch_t2_cfg<64, 4, 16>(a, fma, s)
                        : (g.vn[0] == 32 ? launch_t2_cfg<32, 4, 8>(a, fma, s) : launch_t2_cfg<16, 4, 4>(a, fma, s));
 }

@@ -342,7 +342,9 @@ def test_two_step_sweep_matches_oracle_and_step_by_step(g, oracle, monkeypatch):
     physical boundaries): level t is read once and level t+2 written once.  Valid AND ghost cells of BOTH levels
     must equal the oracle's nstep x {exchange; sweep} (LevelData.H:455-566 + the sweep loop) and the
     library's own step-by-step schedule, bit for bit, in both FMA modes; odd and even step counts,
-    several boxes per direction, flat boxes (vz = 8)."""
+    several boxes per direction, flat boxes (vz = 8).  (Re-boxing of the 32^3-box levels into 64^3 unions is
+    switched off here: this test is about the kernel instances themselves.)"""
+    monkeypatch.setenv("SGC_NO_REBOX", "1")
     rng = np.random.default_rng(21)
     cases = [((0, 0, 0), (63, 63, 63), (64, 64, 64), 7, 0.125, 10, 1),       # one box, periodic onto itself
              ((0, 0, 0), (127, 127, 127), (64, 64, 64), 7, 0.31, 7, 1),
@@ -442,6 +444,126 @@ def test_two_step_sweep_physical_boundary_and_fallback(g, oracle):
     want = u0.copy()
     oracle.level_heat(dlo, dhi, mb, 1, 7, 0, 0.2, 9, want, 1)
     assert np.array_equal(res.download(), want)
+
+
+def test_exchange_after_sweep_reads_edge_strips(g, oracle, monkeypatch):
+    """The drop-in path of an unmodified application — LevelData::exchange (LevelData.H:455-566), then the
+    sweep, step after step.  The streaming sweep leaves dense copies of its first / last x column (edge
+    strips) and the next exchange takes its x faces, x edges and corners from them; every cell of both
+    levels, ghost cells included, must equal the oracle's exchange + sweep after every step, and any other
+    writer of valid cells (upload, setVal, BaseFab::copy, linearIn) must switch the exchange back to the
+    fabs themselves."""
+    rng = np.random.default_rng(31)
+    for (dlo, dhi, mb, per, trim) in (((0, 0, 0), (127, 127, 63), (64, 64, 32), 7, 0),
+                                      ((0, 0, 0), (127, 63, 63), (64, 64, 64), 0, 0),
+                                      ((-32, 0, 0), (63, 63, 31), (32, 32, 16), 5, 0),
+                                      ((0, 0, 0), (95, 63, 31), (32, 32, 32), 7, 8),          # TrimCorner
+                                      ((0, 0, 0), (127, 127, 7), (64, 64, 4), 3, 4)):         # TrimEdge
+        dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
+        b = g.LevelData(dbl, 1, 1)
+        items = oracle.copier_items(dlo, dhi, mb, 1, per, trim)
+        hu, hv = rng.standard_normal(a.elems), rng.standard_normal(a.elems)
+        a.upload(hu); b.upload(hv)
+        assert a.edgeStrips() == 0
+        cp = g.Copier().defineExchangeLD(a, per, trim)
+        cur, nxt, hc, hn = a, b, hu, hv
+        for step in range(4):
+            cur.exchange(cp)
+            oracle.level_exchange(dbl.boxes, 1, 1, items, hc)
+            assert np.array_equal(cur.download(), hc), (mb, per, step, "exchange")
+            g.heat_sweep(nxt, cur, 0.2)
+            oracle.level_heat_sweep(dbl.boxes, 1, hc, hn, 0.2, 1)
+            assert nxt.edgeStrips() == 1, "the whole-level streaming sweep keeps the outer strips current"
+            assert np.array_equal(nxt.download(), hn), (mb, per, step, "sweep")
+            cur, nxt, hc, hn = nxt, cur, hn, hc
+        # cur's strips are current; every other writer of valid cells must invalidate them
+        n = (mb[0] + 2) * (mb[1] + 2) * (mb[2] + 2)
+        fab = rng.standard_normal(n)
+        cur.upload(fab, box=1)
+        hc[cur.fab_offset(1):cur.fab_offset(1) + n] = fab
+        assert cur.edgeStrips() == 0
+        cur.exchange(cp)
+        oracle.level_exchange(dbl.boxes, 1, 1, items, hc)
+        assert np.array_equal(cur.download(), hc), (mb, per, "after upload")
+        for writer in ("setval", "copy", "linear_in"):
+            g.heat_sweep(nxt, cur, 0.125)
+            oracle.level_heat_sweep(dbl.boxes, 1, hc, hn, 0.125, 1)
+            cur, nxt, hc, hn = nxt, cur, hn, hc
+            assert cur.edgeStrips() == 1
+            lo = [int(x) for x in dbl.boxes[0][:3]]
+            f0 = hc[:n].reshape(mb[2] + 2, mb[1] + 2, mb[0] + 2)
+            if writer == "setval":
+                cur.setVal(-3.0, comp=0, box=0)
+                f0[...] = -3.0
+            elif writer == "copy":            # first valid x column of box 0 <- its second one
+                r0, r1 = (lo[0], lo[1], lo[2]), (lo[0], lo[1] + mb[1] - 1, lo[2] + mb[2] - 1)
+                s0, s1 = (lo[0] + 1, lo[1], lo[2]), (lo[0] + 1, lo[1] + mb[1] - 1, lo[2] + mb[2] - 1)
+                cur.copy(0, r0, r1, 0, cur, 0, s0, s1, 0, 1)
+                f0[1:-1, 1:-1, 1] = f0[1:-1, 1:-1, 2].copy()
+            else:
+                r0, r1 = (lo[0], lo[1], lo[2]), (lo[0], lo[1] + 1, lo[2] + 1)
+                cur.linearIn(0, r0, r1, 0, 1, np.arange(4.0))
+                f0[1:3, 1:3, 1] = np.arange(4.0).reshape(2, 2)
+            assert cur.edgeStrips() == 0, writer
+            cur.exchange(cp)
+            oracle.level_exchange(dbl.boxes, 1, 1, items, hc)
+            assert np.array_equal(cur.download(), hc), (mb, per, writer)
+        # the strip-sourced table and the plain one are interchangeable (SGC_NO_XE selects the plain one)
+        g.heat_sweep(nxt, cur, 0.125)
+        oracle.level_heat_sweep(dbl.boxes, 1, hc, hn, 0.125, 1)
+        monkeypatch.setenv("SGC_NO_XE", "1")
+        nxt.exchange(cp)
+        monkeypatch.delenv("SGC_NO_XE")
+        oracle.level_exchange(dbl.boxes, 1, 1, items, hn)
+        assert np.array_equal(nxt.download(), hn)
+
+
+def test_reboxed_step_loop_small_boxes(g, oracle, monkeypatch):
+    """Levels of many small boxes (BASELINE: 32 768 boxes of 16^3; the reference's own multi-box application
+    uses 16^3 boxes, latticeBoltzmann.cpp:16,36): sgc_heat_run advances them on 64^2-footprint unions of the
+    user's boxes with the two-step sweep and hands the result back.  Valid AND ghost cells of BOTH levels
+    must equal the library's own per-box schedule (SGC_NO_REBOX) bit for bit, the valid cells the oracle's
+    nstep x {exchange; sweep}; periodic and physical boundaries, both FMA modes, odd and even step counts."""
+    rng = np.random.default_rng(33)
+    cases = [((0, 0, 0), (127, 127, 127), (16, 16, 16), 7, 0.125, 13, 1, (4, 4, 4)),
+             ((0, 0, 0), (63, 127, 63), (16, 16, 16), 0, 0.2, 10, 0, (4, 4, 4)),
+             ((0, 0, 0), (127, 63, 95), (16, 16, 16), 5, 1.0 / 6.0, 9, 1, (4, 4, 3)),
+             ((0, 0, 0), (127, 63, 63), (32, 32, 32), 3, 0.3, 12, 1, (2, 2, 2)),
+             ((-64, 0, 0), (-1, 63, 31), (8, 8, 8), 6, 0.2, 8, 1, (8, 8, 4)),
+             ((0, 0, 0), (63, 63, 47), (16, 32, 12), 7, 0.2, 11, 0, (4, 2, 4))]
+    for (dlo, dhi, mb, per, f, nstep, contract, want_c) in cases:
+        dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
+        b = g.LevelData(dbl, 1, 1)
+        u0, v0 = rng.standard_normal(a.elems), rng.standard_normal(a.elems)
+        flags = g.SGC_FMA if contract else 0
+        outs = []
+        for no_rebox in (False, True):
+            if no_rebox:
+                monkeypatch.setenv("SGC_NO_REBOX", "1")
+            else:
+                monkeypatch.delenv("SGC_NO_REBOX", raising=False)
+            cp = g.Copier().defineExchangeLD(a, per, 0)
+            a.upload(u0); b.upload(v0)
+            g.profile_enable(True)
+            g.profile_read(2)
+            res = g.heat_run(a, b, cp, f, nstep, flags)
+            n2, _ = g.profile_read(2)
+            g.profile_enable(False)
+            decided, fac = cp.reboxFactors()
+            assert decided and fac == ((1, 1, 1) if no_rebox else want_c), (mb, fac)
+            if not no_rebox:
+                assert n2 == ((nstep - 2) & ~1) // 2, "two-step passes on the union fabs"
+            assert (res is b) == bool(nstep & 1)
+            outs.append((a.download(), b.download()))
+        monkeypatch.delenv("SGC_NO_REBOX", raising=False)
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (dhi, mb, per, "vs per-box schedule")
+        # oracle: ping-pongs against a copy of its input level -> give both levels the same ghosts
+        cp = g.Copier().defineExchangeLD(a, per, 0)
+        a.upload(u0); b.upload(u0)
+        res = g.heat_run(a, b, cp, f, nstep, flags)
+        want = u0.copy()
+        oracle.level_heat(dlo, dhi, mb, 1, per, 0, f, nstep, want, contract)
+        assert np.array_equal(res.download(), want), (dhi, mb, per, "vs oracle")
 
 
 def test_heat_tolerance_across_fma_modes(g, oracle):
