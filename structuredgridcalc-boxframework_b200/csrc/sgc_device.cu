@@ -111,24 +111,44 @@ int CopyTable::upload(const std::vector<CopyItem>& in, int esz) {
   release();
   nitem = (int)in.size();
   if (nitem == 0) return 0;
-  // wide items first, in 16-byte units
+  // Two classes, wide (16-byte units) first.  Items are independent, so their order is free:
+  // within a class the items smaller than a chunk go FIRST (their chunks hold many items and are the slow
+  // ones: at the front of the grid they overlap with everything else instead of forming its tail), then one
+  // masked-out padding item up to the next chunk boundary, then the big items in their original order —
+  // faces and planes (whole multiples of the chunk size on the levels that matter) therefore start on chunk
+  // boundaries and their chunks take the kernel's single-item path.
+  auto units = [](const CopyItem& c) { return (long long)c.nx * c.ny * c.nz * c.nc; };
+  static const char* nw_env = getenv("SGC_COPY_NO_WIDE");
+  static const bool no_wide = nw_env && nw_env[0] == '1';
+  static const char* ns_env = getenv("SGC_COPY_NO_SORT");
+  static const bool no_sort = ns_env && ns_env[0] == '1';
   std::vector<CopyItem> items;
-  items.reserve(in.size());
-  static const bool no_wide = getenv("SGC_COPY_NO_WIDE") != nullptr;
-  if (esz == 8 && !no_wide)
-    for (const CopyItem& c : in)
-      if (wide_ok(c)) {
-        CopyItem w = c;
-        w.nx /= 2; w.dst /= 2; w.src /= 2; w.dsy /= 2; w.dsz /= 2; w.ssy /= 2; w.ssz /= 2; w.dcs /= 2; w.scs /= 2;
-        items.push_back(w);
-      }
-  nwitem = (int)items.size();
-  for (const CopyItem& c : in)
-    if (!(esz == 8 && !no_wide && wide_ok(c))) items.push_back(c);
+  items.reserve(in.size() + 2);
+  for (int wide = 1; wide >= 0; --wide) {
+    std::vector<CopyItem> small, big;
+    for (const CopyItem& c : in) {
+      const bool w = esz == 8 && !no_wide && wide_ok(c);
+      if ((int)w != wide) continue;
+      CopyItem u = c;
+      if (w) { u.nx /= 2; u.dst /= 2; u.src /= 2; u.dsy /= 2; u.dsz /= 2; u.ssy /= 2; u.ssz /= 2; u.dcs /= 2; u.scs /= 2; }
+      (units(u) >= kCopyChunk && !no_sort ? big : small).push_back(u);
+    }
+    long long n = 0;
+    for (const CopyItem& c : small) n += units(c);
+    if (!big.empty() && n % kCopyChunk) {
+      CopyItem pad;
+      memset(&pad, 0, sizeof pad);       // flags = 0, c0 = 0: every unit is masked out, nothing is touched
+      pad.nx = (int)(kCopyChunk - n % kCopyChunk); pad.ny = pad.nz = pad.nc = 1;
+      small.push_back(pad);
+    }
+    items.insert(items.end(), small.begin(), small.end());
+    items.insert(items.end(), big.begin(), big.end());
+    if (wide) nwitem = (int)items.size();
+  }
+  nitem = (int)items.size();
   std::vector<long long> start(nitem + 1);
   start[0] = 0;
-  for (int i = 0; i < nitem; ++i)
-    start[i + 1] = start[i] + (long long)items[i].nx * items[i].ny * items[i].nz * items[i].nc;
+  for (int i = 0; i < nitem; ++i) start[i + 1] = start[i] + units(items[i]);
   ncell = start[nitem];
   nwcell = start[nwitem];
   // cells read one per source row, rows at least 256 bytes apart (for 8-byte elements): worth asking
