@@ -249,6 +249,12 @@ class Reference:
     def threads(self):
         return int(self.lib.sgcref_openmp_threads())
 
+    def set_threads(self, n):
+        """OpenMP builds only: use n threads regardless of OMP_NUM_THREADS (torchrun exports 1)"""
+        if hasattr(self.lib, "sgcref_set_threads"):
+            return int(self.lib.sgcref_set_threads(int(n)))
+        return self.threads()
+
     def layout(self, dlo, dhi, maxbox, nproc=1):
         n = 1
         for d in range(3):

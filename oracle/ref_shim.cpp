@@ -109,6 +109,18 @@ void heatSweep(LevelData<FArrayBox>& unew, LevelData<FArrayBox>& u,
 
 extern "C" {
 
+/* bench.py forces the thread count: torchrun exports OMP_NUM_THREADS=1 to its children */
+int sgcref_set_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 int sgcref_openmp_threads()
 {
 #ifdef _OPENMP
