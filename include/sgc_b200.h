@@ -237,6 +237,17 @@ int sgc_fab_linear_in(sgc_level_t level, int box, const int rlo[3], const int rh
 int sgc_plan_create_exchange(sgc_level_t level, const int dlo[3], const int dhi[3],
                              const int maxbox[3], unsigned periodic, unsigned trim,
                              int comp_begin, int ncomp, int nproc, int rank, sgc_plan_t* plan);
+/* The general form.  nghost_exchange: ghost width the items fill (Copier::defineExchangeDBL's a_numGhost,
+ * Copier.H:521-528; 0 = the level's own width, which must not be smaller).  item_flags (or NULL): one
+ * component mask per motion item, in sgc_copier_define's order, replacing the default ~0u — the state of a
+ * Copier after Motion2Way::setCompRecvFlags (Copier.H:430-444) on some of its items, local OR remote (the
+ * masks of remote items are applied when their message is unpacked).                                  */
+int sgc_plan_create_exchange_ex(sgc_level_t level, const int dlo[3], const int dhi[3], const int maxbox[3],
+                                int nghost_exchange, unsigned periodic, unsigned trim, int comp_begin, int ncomp,
+                                int nproc, int rank, const unsigned* item_flags, int nitem, sgc_plan_t* plan);
+/* 1 when `plan` was built for a level of this geometry (boxes, components, ghost width, element size): a
+ * Copier may serve several LevelData on its layout (LevelData.H:455: any level whose tag matches).      */
+int sgc_plan_matches_level(sgc_plan_t plan, sgc_level_t level);
 /* Same from caller-supplied items (all local), e.g. after Motion2Way::setCompRecvFlags
  * (Copier.H:430-444) or for physical-BC copies.                                            */
 int sgc_plan_create_items(sgc_level_t level, const sgc_motion_item* items, int nitem,

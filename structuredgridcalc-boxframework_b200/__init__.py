@@ -34,7 +34,7 @@ SYMBOLS = [
     "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
     "sgc_level_upload_async", "sgc_level_download_async", "sgc_copyset_create", "sgc_copyset_run", "sgc_copyset_destroy",
     "sgc_copyset_num_cells", "sgc_level_valid_elems", "sgc_level_download_valid", "sgc_level_download_valid_async", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run", "sgc_lb_selftest_divconst",
-    "sgc_level_edge_strips", "sgc_plan_rebox_factors",
+    "sgc_level_edge_strips", "sgc_plan_rebox_factors", "sgc_plan_create_exchange_ex", "sgc_plan_matches_level",
 ]
 
 
@@ -112,6 +112,9 @@ def lib():
     L.sgc_fab_linear_in.argtypes = [C.c_void_p, C.c_int, _i3, _i3, C.c_int, C.c_int, C.c_uint, C.c_void_p]
     L.sgc_plan_create_exchange.argtypes = [C.c_void_p, _i3, _i3, _i3, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int,
                                            C.c_int, C.POINTER(C.c_void_p)]
+    L.sgc_plan_create_exchange_ex.argtypes = [C.c_void_p, _i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.sgc_plan_matches_level.argtypes = [C.c_void_p, C.c_void_p]
     L.sgc_plan_create_items.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.sgc_plan_create_bc_zero_gradient.argtypes = [C.c_void_p, _i3, _i3, C.POINTER(C.c_void_p)]
     for f in ("sgc_plan_destroy", "sgc_plan_num_items", "sgc_plan_num_remote_items"):
@@ -481,15 +484,27 @@ class Copier:
     def __init__(self):
         self.h = None
 
-    def defineExchangeLD(self, level, periodic=0, trim=0, comp_begin=0, ncomp=None):
+    def defineExchangeLD(self, level, periodic=0, trim=0, comp_begin=0, ncomp=None, nghost=0, item_flags=None):
+        """nghost: ghost width to fill (0 = the level's); item_flags: one component mask per motion item
+        (Motion2Way::setCompRecvFlags), local or remote"""
         self._release()
         dbl = level.dbl
         h = C.c_void_p()
-        check(lib().sgc_plan_create_exchange(level.h, _v3(dbl.domain.lo), _v3(dbl.domain.hi), _v3(dbl.maxbox), periodic,
-                                             trim, comp_begin, level.ncomp if ncomp is None else ncomp, dbl.nproc,
-                                             dbl.rank, C.byref(h)))
+        nc = level.ncomp if ncomp is None else ncomp
+        if nghost == 0 and item_flags is None:
+            check(lib().sgc_plan_create_exchange(level.h, _v3(dbl.domain.lo), _v3(dbl.domain.hi), _v3(dbl.maxbox), periodic,
+                                                 trim, comp_begin, nc, dbl.nproc, dbl.rank, C.byref(h)))
+        else:
+            fl = None if item_flags is None else np.ascontiguousarray(item_flags, np.uint32)
+            check(lib().sgc_plan_create_exchange_ex(level.h, _v3(dbl.domain.lo), _v3(dbl.domain.hi), _v3(dbl.maxbox), nghost,
+                                                    periodic, trim, comp_begin, nc, dbl.nproc, dbl.rank,
+                                                    None if fl is None else fl.ctypes.data, 0 if fl is None else len(fl),
+                                                    C.byref(h)))
         self.h = h
         return self
+
+    def matches(self, level):
+        return bool(lib().sgc_plan_matches_level(self.h, level.h))
 
     def defineItems(self, level, items, comp_begin=0, ncomp=None):
         self._release()

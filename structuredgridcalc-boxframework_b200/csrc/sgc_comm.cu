@@ -119,7 +119,7 @@ int comm_plan_setup(sgc_plan_s* p, sgc_level_s* l, const Grid& g, unsigned perio
     return fail(SGC_ERR_COMM, "plan has remote motion items but sgc_comm_init(nproc, rank, id) has not been called "
                               "with the same nproc/rank");
   std::vector<HaloList> lists;
-  int st = build_halo_lists(g, l->ng, periodic, trim, p->rank, p->items, lists);
+  int st = build_halo_lists(g, p->ng_exchange > 0 ? p->ng_exchange : l->ng, periodic, trim, p->rank, p->items, lists);
   if (st) return st;
   for (const HaloList& h : lists) {
     sgc_plan_s::Peer peer;
@@ -212,11 +212,24 @@ int comm_exchange_end(sgc_level_s* l, sgc_plan_s* p) {
 // there is no cycle; the planes a neighbour reads are exactly those whose computation needed the
 // remote plane, so they are never overwritten too early.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_signal(unsigned long long* flag, unsigned long long value) {
+__global__ void k_signal(unsigned long long* flag, unsigned long long value, const unsigned int* err) {
+  // after a timed-out wait the phase is dead: do not tell the neighbours that data they cannot trust is ready
+  if (*reinterpret_cast<const volatile unsigned int*>(err)) return;
   __threadfence_system();
   *reinterpret_cast<volatile unsigned long long*>(flag) = value;
   __threadfence_system();
 }
+
+// plans that hold a peer-memory session (so that destroying a level can invalidate the sessions that name it)
+static std::vector<sgc_plan_s*>& p2p_plans() {
+  static std::vector<sgc_plan_s*> v;
+  return v;
+}
+
+struct DevTmp {              // device scratch freed on every path out of a function
+  void* p = nullptr;
+  ~DevTmp() { if (p) cudaFree(p); }
+};
 
 struct P2PMsg {
   cudaIpcMemHandle_t lev[2];
@@ -226,19 +239,48 @@ struct P2PMsg {
 
 void comm_p2p_release(sgc_plan_s* p) {
   sgc_plan_s::P2P& S = p->p2p;
+  if (S.tried && rt().ready) { cudaStreamSynchronize(rt().compute); cudaStreamSynchronize(rt().comm); }
+  // closing OUR mappings of the neighbours' memory is always legal
   for (int k = 0; k < 2; ++k) {
     for (int l = 0; l < 2; ++l)
       if (S.peer_base[k][l]) { cudaIpcCloseMemHandle(S.peer_base[k][l]); S.peer_base[k][l] = nullptr; }
     if (S.peer_flag_base[k]) { cudaIpcCloseMemHandle(S.peer_flag_base[k]); S.peer_flag_base[k] = nullptr; }
   }
-  if (S.d_flag) cudaFree(S.d_flag);
+  // our counter may still be mapped by the neighbours: its memory waits for a point every rank passes
+  if (S.d_flag) rt().deferred_free.push_back(S.d_flag);
   if (S.d_err) cudaFree(S.d_err);
   if (S.d_rz) cudaFree(S.d_rz);
   S = sgc_plan_s::P2P();
+  std::vector<sgc_plan_s*>& reg = p2p_plans();
+  reg.erase(std::remove(reg.begin(), reg.end(), p), reg.end());
+}
+
+// sgc_level_destroy: sessions that name the level are over (a later level at the same address is NOT the same level)
+void comm_level_destroyed(sgc_level_s* l) {
+  const std::vector<sgc_plan_s*> reg = p2p_plans();      // copy: release edits the registry
+  for (sgc_plan_s* p : reg)
+    for (int k = 0; k < 2; ++k)
+      if (p->p2p.lev[k] == l && p->p2p.gen[k] == l->generation) { comm_p2p_release(p); break; }
+}
+
+void comm_drain_deferred_frees() {
+  for (void* q : rt().deferred_free) cudaFree(q);
+  rt().deferred_free.clear();
+}
+
+// All ranks meet on stream `s` (a one-int all-reduce, no host synchronisation): no kernel a rank enqueues behind
+// it starts before every rank has enqueued its own, which bounds the skew the peer-counter waits ever see
+int comm_stream_barrier(cudaStream_t s) {
+  Comm& c = cm();
+  if (!c.ready || c.nproc < 2) return 0;
+  static int* d_one = nullptr;
+  if (!d_one) { SGC_CUDA(cudaMalloc(&d_one, 256)); SGC_CUDA(cudaMemset(d_one, 0, 256)); }
+  SGC_NCCL(c.api.AllReduce(d_one, d_one, 1, ncclInt, ncclMax, c.comm, s));
+  return 0;
 }
 
 int comm_p2p_signal(sgc_plan_s* p, unsigned long long value, cudaStream_t s) {
-  k_signal<<<1, 1, 0, s>>>(p->p2p.d_flag, value);
+  k_signal<<<1, 1, 0, s>>>(p->p2p.d_flag, value, p->p2p.d_err);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
@@ -258,13 +300,13 @@ int comm_all_min(int v, int* out) {
   *out = v;
   if (!c.ready || c.nproc < 2) return 0;
   Runtime& r = rt();
-  int* d = nullptr;
-  SGC_CUDA(cudaMalloc(&d, 256));
+  DevTmp buf;
+  SGC_CUDA(cudaMalloc(&buf.p, 256));
+  int* d = (int*)buf.p;
   SGC_CUDA(cudaMemcpy(d, &v, sizeof v, cudaMemcpyHostToDevice));
   SGC_NCCL(c.api.AllReduce(d, d, 1, ncclInt, ncclMin, c.comm, r.comm));
   SGC_CUDA(cudaStreamSynchronize(r.comm));
   SGC_CUDA(cudaMemcpy(out, d, sizeof v, cudaMemcpyDeviceToHost));
-  cudaFree(d);
   return 0;
 }
 
@@ -272,13 +314,17 @@ int comm_all_min(int v, int* out) {
 // rank — decided by an all-reduce, so all ranks take the same path); < 0 on hard errors.
 int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {
   sgc_plan_s::P2P& S = p->p2p;
-  if (S.tried && ((S.lev[0] == a && S.lev[1] == b) || (S.lev[0] == b && S.lev[1] == a))) return 0;
+  // the session is tied to the two LEVELS (generation ids), not to their addresses
+  if (S.tried && ((S.lev[0] == a && S.gen[0] == a->generation && S.lev[1] == b && S.gen[1] == b->generation) ||
+                  (S.lev[0] == b && S.gen[0] == b->generation && S.lev[1] == a && S.gen[1] == a->generation)))
+    return 0;
   Comm& c = cm();
   if (!c.ready || c.nproc < 2) return 0;
   comm_p2p_release(p);
   S.tried = true;
-  S.lev[0] = a;
-  S.lev[1] = b;
+  S.lev[0] = a; S.gen[0] = a->generation;
+  S.lev[1] = b; S.gen[1] = b->generation;
+  p2p_plans().push_back(p);
   Runtime& r = rt();
   // 1. which boxes have a z neighbour on another rank, and is every remote FACE a z face?
   int ok = 1;
@@ -312,20 +358,22 @@ int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {
       ok = cudaIpcGetMemHandle(&mine.lev[0], a->d_base) == cudaSuccess &&
            cudaIpcGetMemHandle(&mine.lev[1], b->d_base) == cudaSuccess &&
            cudaIpcGetMemHandle(&mine.flag, S.d_flag) == cudaSuccess;
+      if (ok) a->exported = b->exported = true;
     }
     cudaGetLastError();
   }
   // 3. agree globally before anything rank-to-rank happens
-  int* d_ok = nullptr;
-  SGC_CUDA(cudaMalloc(&d_ok, 256));
+  DevTmp ok_buf, msg_buf;
+  SGC_CUDA(cudaMalloc(&ok_buf.p, 256));
+  int* d_ok = (int*)ok_buf.p;
   SGC_CUDA(cudaMemcpy(d_ok, &ok, sizeof ok, cudaMemcpyHostToDevice));
   SGC_NCCL(c.api.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c.comm, r.comm));
   SGC_CUDA(cudaStreamSynchronize(r.comm));
   SGC_CUDA(cudaMemcpy(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost));
   if (ok) {
     // 4. swap handles with the z neighbours and map their memory
-    P2PMsg* d_msg = nullptr;
-    SGC_CUDA(cudaMalloc(&d_msg, sizeof(P2PMsg) * 3));
+    SGC_CUDA(cudaMalloc(&msg_buf.p, sizeof(P2PMsg) * 3));
+    P2PMsg* d_msg = (P2PMsg*)msg_buf.p;
     SGC_CUDA(cudaMemcpy(d_msg, &mine, sizeof mine, cudaMemcpyHostToDevice));
     SGC_NCCL(c.api.GroupStart());
     for (int k = 0; k < S.npeer; ++k) {
@@ -335,7 +383,6 @@ int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {
     SGC_NCCL(c.api.GroupEnd());
     SGC_CUDA(cudaStreamSynchronize(r.comm));
     SGC_CUDA(cudaMemcpy(theirs, d_msg + 1, sizeof(P2PMsg) * 2, cudaMemcpyDeviceToHost));
-    cudaFree(d_msg);
     for (int k = 0; k < S.npeer && ok; ++k) {
       for (int l = 0; l < 2 && ok; ++l)
         ok = cudaIpcOpenMemHandle(&S.peer_base[k][l], theirs[k].lev[l], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
@@ -348,7 +395,6 @@ int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {
     SGC_CUDA(cudaStreamSynchronize(r.comm));
     SGC_CUDA(cudaMemcpy(&ok, d_ok, sizeof ok, cudaMemcpyDeviceToHost));
   }
-  cudaFree(d_ok);
   S.ready = ok != 0;
   S.counter = 0;
   return 0;
@@ -394,6 +440,13 @@ int sgc_comm_finalize(void) {
   Comm& c = cm();
   if (!c.ready) return 0;
   if (rt().ready) cudaDeviceSynchronize();
+  if (c.comm && rt().ready) {
+    // every rank is here: sessions are over, nobody launches kernels that read a neighbour any more, and the
+    // allocations neighbours had mapped can go (their mappings were closed with their plans, or die with them)
+    int all = 0;
+    comm_all_min(1, &all);
+    comm_drain_deferred_frees();
+  }
   if (c.comm) c.api.CommDestroy(c.comm);
   c.comm = nullptr;
   c.ready = false;

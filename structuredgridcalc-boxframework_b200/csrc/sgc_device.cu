@@ -35,6 +35,9 @@ void comm_p2p_release(sgc_plan_s* plan);
 int comm_p2p_signal(sgc_plan_s* plan, unsigned long long value, cudaStream_t s);
 int comm_p2p_check(sgc_plan_s* plan);
 int comm_all_min(int v, int* out);
+int comm_stream_barrier(cudaStream_t s);
+void comm_level_destroyed(sgc_level_s* l);
+void comm_drain_deferred_frees();
 bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u);
 bool heat_t2_covers(const sgc_level_s* unew, const sgc_level_s* u);
 int launch_build_xe(sgc_level_s* l, cudaStream_t s);
@@ -322,6 +325,7 @@ int sgc_shutdown(void) {
   if (r.compute) cudaStreamDestroy(r.compute);
   if (r.comm) cudaStreamDestroy(r.comm);
   if (r.d_stage) cudaFree(r.d_stage);
+  comm_drain_deferred_frees();
   for (ProfLog& L : r.prof)
     for (size_t i = 0; i < L.a.size(); ++i) { cudaEventDestroy(L.a[i]); cudaEventDestroy(L.b[i]); }
   r = Runtime();
@@ -503,10 +507,12 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
 int sgc_level_destroy(sgc_level_t l) {
   if (!l) return 0;
   if (rt().ready) cudaStreamSynchronize(rt().compute);
+  comm_level_destroyed(l);             // peer-memory sessions that name this level end here
   l->conv_in.release();
   l->conv_out.release();
   l->conv_valid.release();
-  if (l->d_base) cudaFree(l->d_base);
+  // an arena other GPUs may still have mapped is freed at the next point every rank passes (sgc_comm_finalize)
+  if (l->d_base) { if (l->exported && rt().ready) rt().deferred_free.push_back(l->d_base); else cudaFree(l->d_base); }
   if (l->d_geom) cudaFree(l->d_geom);
   if (l->d_work) cudaFree(l->d_work);
   if (l->d_scratch) cudaFree(l->d_scratch);
@@ -956,8 +962,16 @@ static int upload_local_items(sgc_plan_s* p, sgc_level_s* l) {
 
 int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], const int maxbox[3], unsigned periodic,
                              unsigned trim, int comp_begin, int ncomp, int nproc, int rank, sgc_plan_t* plan) {
+  return sgc_plan_create_exchange_ex(l, dlo, dhi, maxbox, 0, periodic, trim, comp_begin, ncomp, nproc, rank, nullptr, 0, plan);
+}
+
+int sgc_plan_create_exchange_ex(sgc_level_t l, const int dlo[3], const int dhi[3], const int maxbox[3], int nghost_exchange,
+                                unsigned periodic, unsigned trim, int comp_begin, int ncomp, int nproc, int rank,
+                                const unsigned* item_flags, int nitem, sgc_plan_t* plan) {
   SGC_REQUIRE_RT();
   if (!l || !dlo || !dhi || !maxbox || !plan) return fail(SGC_ERR_ARG, "sgc_plan_create_exchange: null argument");
+  const int ngx = nghost_exchange > 0 ? nghost_exchange : l->ng;
+  if (ngx > l->ng) return fail(SGC_ERR_ARG, "sgc_plan_create_exchange: exchange width exceeds the level's ghost width");
   if (comp_begin < 0 || ncomp < 1 || comp_begin + ncomp > l->ncomp)
     return fail(SGC_ERR_ARG, "sgc_plan_create_exchange: component range");
   Grid g(dlo, dhi, maxbox, nproc);
@@ -975,10 +989,16 @@ int sgc_plan_create_exchange(sgc_level_t l, const int dlo[3], const int dhi[3], 
   p->has_grid = true;
   for (int d = 0; d < 3; ++d) { p->dlo[d] = dlo[d]; p->dhi[d] = dhi[d]; p->maxbox[d] = maxbox[d]; }
   p->periodic = periodic; p->trim = trim;
-  int st = build_exchange_items(g, l->ng, periodic, trim, rank, p->items);
+  p->ng_exchange = ngx;
+  int st = build_exchange_items(g, ngx, periodic, trim, rank, p->items);
+  if (!st && item_flags) {
+    // Motion2Way::setCompRecvFlags (Copier.H:430-444) on some items, local or remote: same items, edited masks
+    if (nitem != (int)p->items.size()) st = fail(SGC_ERR_ARG, "sgc_plan_create_exchange_ex: one flag word per motion item expected");
+    else for (int i = 0; i < nitem; ++i) p->items[i].comp_flags = item_flags[i];
+  }
   if (!st) st = upload_local_items(p, l);
   if (!st && p->nremote > 0) st = comm_plan_setup(p, l, g, periodic, trim);
-  if (!st && l->ng == 1 && l->ncomp == 1 && comp_begin == 0 && ncomp == 1 && l->uniform && l->esz == 8) {
+  if (!st && ngx == 1 && !item_flags && l->ng == 1 && l->ncomp == 1 && comp_begin == 0 && ncomp == 1 && l->uniform && l->esz == 8) {
     // neighbour table of the fused / two-step sweeps and the step loops the plan admits (sgc_plan.cpp)
     std::vector<int> nbr;
     const int loops = classify_step_loops(p->items, l->nbox, l->gidx0, nbr);
@@ -1063,6 +1083,7 @@ int sgc_plan_destroy(sgc_plan_t p) {
 }
 
 int sgc_plan_num_items(sgc_plan_t p) { return p ? (int)p->items.size() : -1; }
+int sgc_plan_matches_level(sgc_plan_t p, sgc_level_t l) { return (p && l && plan_matches(p, l)) ? 1 : 0; }
 int sgc_plan_num_remote_items(sgc_plan_t p) { return p ? p->nremote : -1; }
 long long sgc_plan_num_cells(sgc_plan_t p) {
   if (!p) return -1;
@@ -1237,6 +1258,13 @@ static int fused_sweep(sgc_level_t nxt, sgc_level_t cur, double f, unsigned flag
   return st > 0 ? fail(SGC_ERR_UNSUPPORTED, "fused sweep: no streaming kernel for this geometry") : st;
 }
 
+// how long a kernel may wait for a neighbouring GPU's progress counter before it reports a time-out
+static unsigned long long p2p_wait_budget_ns() {
+  static const char* e = getenv("SGC_P2P_TIMEOUT_MS");
+  const double ms = e ? atof(e) : 30000.0;
+  return (unsigned long long)((ms > 1.0 ? ms : 1.0) * 1e6);
+}
+
 // `npass` two-step passes (sgc_stream2.cu) starting from level `cur` of the pair (a, b); a is the level whose
 // physical-boundary ghost cells belong to the even steps.  p2p: z tiles come out of the neighbouring GPUs' memory.
 static int run_t2_passes(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags, int npass, bool p2p,
@@ -1257,6 +1285,7 @@ static int run_t2_passes(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f
       }
       ra.wait_value = S.counter;
       ra.err = S.d_err;
+      ra.wait_budget_ns = p2p_wait_budget_ns();
     }
     if (plan->t2_bnd) {
       // faces without a neighbour: step t of the run reads level a's ghost cells, step t+1 level b's —
@@ -1436,6 +1465,8 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
     // ONE launch per step.  SGC_P2P=0 keeps the NCCL schedule below.
     const char* pe = getenv("SGC_P2P");
     const bool p2p = plan->nremote > 0 && !(pe && pe[0] == '0') && comm_p2p_setup(plan, a, b) == 0 && plan->p2p.ready;
+    // every rank has reached this run before any kernel that waits on a neighbour's counter starts
+    if (p2p) { st = comm_stream_barrier(rt().compute); if (st) return st; }
 
     // ---- two steps per pass (sgc_stream2.cu): level t is read once and level t+2 written once, the
     // intermediate level stays on the SM.  It reads VALID cells only (the neighbours' rows, planes and
@@ -1476,6 +1507,7 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
         }
         ra.wait_value = S.counter;                              // peers have finished their previous sweep
         ra.err = S.d_err;
+        ra.wait_budget_ns = p2p_wait_budget_ns();
         st = fused_sweep(nxt, cur, f, flags, 0, cur->nbox, cur->nbox, cur->nbox, plan->d_push, fmask, &ra);
         if (!st) st = comm_p2p_signal(plan, ++S.counter, rt().compute);
         std::swap(cur, nxt);

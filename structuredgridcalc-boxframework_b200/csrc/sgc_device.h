@@ -114,6 +114,10 @@ struct Runtime {
   int prio_hi = 0;
   long long launches = 0;
   int sweep_grid_cap = 0;               // > 0: persistent sweeps use at most this many CTAs (leaves SMs to NCCL)
+  // allocations other GPUs may still have mapped (exported level arenas, progress counters): freeing them
+  // before every importer has closed its mapping is undefined, so they wait for sgc_comm_finalize /
+  // sgc_shutdown, the points every rank passes
+  std::vector<void*> deferred_free;
 };
 Runtime& rt();
 
@@ -159,7 +163,8 @@ struct PushArgs {
   const double* peer_in[2];                  // the peers' input-level arenas (cudaIpc-mapped)
   const unsigned long long* peer_flag[2];    // the peers' progress counters (cudaIpc-mapped)
   unsigned long long wait_value;             // counter value that makes the peers' input level readable
-  unsigned int* err;                         // set to 1 when a wait timed out
+  unsigned int* err;                         // set to 1 when a wait timed out; a launch that finds it set does nothing
+  unsigned long long wait_budget_ns;         // how long a wait may take (SGC_P2P_TIMEOUT_MS, default 30 s)
   // edge strips of the OUTPUT level (sgc_level_s::xe_base), or null: the threads that compute the first /
   // last cell of a row also store it there, so that the next exchange reads its x faces densely
   double* xe_out;
@@ -186,7 +191,8 @@ struct T2Args {
   const double* peer_in[2];
   const unsigned long long* peer_flag[2];
   unsigned long long wait_value;
-  unsigned int* err;
+  unsigned int* err;                         // as PushArgs::err
+  unsigned long long wait_budget_ns;
 };
 
 // launchers implemented in sgc_kernels.cu
@@ -220,6 +226,7 @@ struct sgc_level_s {
   // pointer (sgc_level_device_ptr) turns the mechanism off for the level for good.
   int xe_valid = 0;
   bool xe_extern = false;
+  bool exported = false;                // the arena has been exported with cudaIpcGetMemHandle (peer GPUs may map it)
   unsigned long long generation = 0;    // unique per created level (peer-memory sessions are keyed on it)
   sgc::CopyTable conv_in, conv_out;     // reference-order staging <-> split-x arena, whole level
   sgc::CopyTable conv_valid;            // arena -> [box][comp] valid cells only (plot output), built on first use
@@ -245,6 +252,7 @@ struct sgc_plan_s {
   int nbox = 0, ncomp = 0, ng = 0, esz = 0, gidx0 = 0;
   std::vector<sgc::IBox> boxes;
   int c0 = 0, nc = 0;
+  int ng_exchange = 0;                  // ghost width the items fill (<= ng: Copier::defineExchangeDBL's a_numGhost)
   int nproc = 1, rank = 0;
   std::vector<sgc_motion_item> items;   // this rank's items, reference order
   int nremote = 0;

@@ -67,4 +67,23 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t byte
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// Peer-memory halo: wait until the neighbouring GPU's progress counter reaches `value` (volatile system-scope
+// loads), timed with %globaltimer against a budget in nanoseconds.  false = timed out: the caller reports it
+// through the session's error word, which turns every later launch of the phase into a no-op.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ bool wait_peer_counter(const volatile unsigned long long* fl, unsigned long long value,
+                                                  unsigned long long budget_ns) {
+  if (*fl >= value) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  while (*fl < value) {
+    if (globaltimer_ns() - t0 > budget_ns) return false;
+    __nanosleep(128);
+  }
+  return true;
+}
+
 }  // namespace sgc

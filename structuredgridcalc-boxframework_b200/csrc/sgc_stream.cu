@@ -119,6 +119,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   const int s_begin = (int)((long long)blockIdx.x * nstages / gridDim.x);
   const int s_end = (int)((long long)(blockIdx.x + 1) * nstages / gridDim.x);
   if (s_begin >= s_end) return;
+  if (push.err && *reinterpret_cast<const volatile unsigned int*>(push.err)) return;   // an earlier wait of this phase timed out
   // stages to load: one before and one after the range (z halo of the first / last output plane)
   const int l_begin = s_begin > 0 ? s_begin - 1 : 0;
   const int l_end = s_end < nstages ? s_end + 1 : nstages;
@@ -151,12 +152,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
         if (rr >= 0) {
           const int ps = rr >> 28;
           if (!waited[ps]) {           // the peer must have finished writing the level we read
-            const volatile unsigned long long* fl = push.peer_flag[ps];
-            long long spins = 0;
-            while (*fl < push.wait_value) {
-              if (++spins > (1LL << 20)) { *push.err = 1u; break; }    // ~3 s: report, never hang
-              __nanosleep(64);
-            }
+            if (!wait_peer_counter(push.peer_flag[ps], push.wait_value, push.wait_budget_ns)) *push.err = 1u;   // report, never hang
             __threadfence_system();
             asm volatile("fence.proxy.async;" ::: "memory");
             waited[ps] = true;

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   const int s_begin = 2 * (int)((long long)blockIdx.x * (a.nplanes / 2) / gridDim.x);
   const int s_end = 2 * (int)((long long)(blockIdx.x + 1) * (a.nplanes / 2) / gridDim.x);
   if (s_begin >= s_end) return;
+  if (a.err && *reinterpret_cast<const volatile unsigned int*>(a.err)) return;   // an earlier wait of this phase timed out
   const int l_begin = s_begin >= 4 ? s_begin - 4 : 0;     // 4 tiles prime the two stages
 
   if (tid == 0) {
@@ -155,12 +156,7 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
             S = (rr & 0x0fffffff) | (ps ? 0x60000000 : 0x40000000);     // bit 30: remote, bit 29: peer slot
             if (!(waited >> ps & 1u)) {          // the peer must have finished writing the level we read
               if (lane == 0) {
-                const volatile unsigned long long* fl = ps ? a.peer_flag[1] : a.peer_flag[0];
-                long long spins = 0;
-                while (*fl < a.wait_value) {
-                  if (++spins > (1LL << 20)) { *a.err = 1u; break; }    // ~3 s: report, never hang
-                  __nanosleep(64);
-                }
+                if (!wait_peer_counter(ps ? a.peer_flag[1] : a.peer_flag[0], a.wait_value, a.wait_budget_ns)) *a.err = 1u;
               }
               __syncwarp();
               __threadfence_system();

@@ -275,6 +275,38 @@ def test_exchange_component_range_and_flags(g, oracle):
     want = u.copy()
     oracle.level_exchange(dbl.boxes, 1, 4, items, want, c0=1, nc=2)
     assert np.array_equal(lev.download(), want)
+    # the same edited masks through the exchange plan itself (sgc_plan_create_exchange_ex: what the facade's
+    # Copier does after setCompRecvFlags, and the form that also carries remote items)
+    lev.upload(u)
+    cp3 = g.Copier().defineExchangeLD(lev, 7, 0, comp_begin=1, ncomp=2, item_flags=it["comp_flags"])
+    lev.exchange(cp3)
+    assert np.array_equal(lev.download(), want)
+    with pytest.raises(g.SgcError):
+        g.Copier().defineExchangeLD(lev, 7, 0, comp_begin=1, ncomp=2, item_flags=it["comp_flags"][:-1])
+
+
+def test_copier_narrower_than_the_levels_ghost_width(g, oracle):
+    """Copier::defineExchangeDBL(dbl, numGhost, ...) (Copier.H:521-528) with numGhost smaller than the level's
+    ghost width: only the inner ghost layer is filled; and one plan per level geometry (a Copier serves every
+    LevelData on its layout)."""
+    rng = np.random.default_rng(15)
+    dlo, dhi, mb = (0, 0, 0), (11, 7, 7), (4, 4, 4)
+    dbl, lev = make_level(g, dlo, dhi, mb, 2, 2)
+    u = rng.standard_normal(lev.elems)
+    lev.upload(u)
+    cp = g.Copier().defineExchangeLD(lev, 5, 0, nghost=1)
+    lev.exchange(cp)
+    want = u.copy()
+    oracle.level_exchange(dbl.boxes, 2, 2, oracle.copier_items(dlo, dhi, mb, 1, 5, 0), want)
+    assert np.array_equal(lev.download(), want)
+    full = g.Copier().defineExchangeLD(lev, 5, 0)
+    lev.exchange(full)
+    oracle.level_exchange(dbl.boxes, 2, 2, oracle.copier_items(dlo, dhi, mb, 2, 5, 0), want)
+    assert np.array_equal(lev.download(), want)
+    with pytest.raises(g.SgcError):
+        g.Copier().defineExchangeLD(lev, 5, 0, nghost=3)
+    _, other = make_level(g, dlo, dhi, mb, 1, 2)
+    assert cp.matches(lev) and not cp.matches(other)
 
 
 def test_plan_geometry_mismatch_is_an_error(g):
