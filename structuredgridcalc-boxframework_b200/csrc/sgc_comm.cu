@@ -15,6 +15,7 @@
 #include <nccl.h>   // types only; no link-time dependency
 
 #include <algorithm>
+#include <tuple>
 #include <cstdlib>
 #include <cstring>
 
@@ -149,6 +150,15 @@ int comm_plan_setup(sgc_plan_s* p, sgc_level_s* l, const Grid& g, unsigned perio
     SGC_CUDA(cudaMalloc(&peer.d_recv, (size_t)std::max<long long>(peer.recv_elems, 1) * l->esz));
     p->peers.push_back(peer);
   }
+  // Message order: the same TOTAL order of rank pairs on every rank (colour of the pair, then the pair), so
+  // that the per-peer send/recv groups below can never wait for each other in a cycle; the colour (parity of
+  // the lower rank) lets a ring of slabs finish in two or three rounds instead of a chain through all ranks.
+  const int me = p->rank;
+  std::sort(p->peers.begin(), p->peers.end(), [me](const sgc_plan_s::Peer& x, const sgc_plan_s::Peer& y) {
+    auto key = [me](int q) { const int lo = std::min(me, q), hi = std::max(me, q); return std::make_tuple(lo & 1, lo, hi); };
+    return key(x.rank) < key(y.rank);
+  });
+  for (sgc_plan_s::Peer& q : p->peers) SGC_CUDA(cudaEventCreateWithFlags(&q.ev_arrived, cudaEventDisableTiming));
   SGC_CUDA(cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));
   SGC_CUDA(cudaEventCreateWithFlags(&p->ev_halo, cudaEventDisableTiming));
   return 0;
@@ -160,6 +170,7 @@ void comm_plan_release(sgc_plan_s* p) {
     q.unpack.release();
     if (q.d_send) cudaFree(q.d_send);
     if (q.d_recv) cudaFree(q.d_recv);
+    if (q.ev_arrived) cudaEventDestroy(q.ev_arrived);
   }
   p->peers.clear();
   if (p->ev_ready) cudaEventDestroy(p->ev_ready);
@@ -167,6 +178,10 @@ void comm_plan_release(sgc_plan_s* p) {
   p->ev_ready = p->ev_halo = nullptr;
 }
 
+// LevelData::exchangeBegin's remote half (LevelData.H:577-626): pack every peer's message, then ONE send/recv
+// pair per peer, each followed by its own event — the device-side form of the reference's MPI_Waitany loop
+// (LevelData.H:507-536): comm_exchange_end unpacks a peer's message as soon as THAT message has arrived, while
+// later peers' transfers are still in flight.  SGC_COMM_ONE_GROUP=1 restores the single group for all peers.
 int comm_exchange_begin(sgc_level_s* l, sgc_plan_s* p) {
   Runtime& r = rt();
   Comm& c = cm();
@@ -178,20 +193,30 @@ int comm_exchange_begin(sgc_level_s* l, sgc_plan_s* p) {
     const int st = launch_copy(q.pack, q.d_send, l->d_arena, l->esz, r.comm);
     if (st) return st;
   }
-  SGC_NCCL(c.api.GroupStart());
+  static const char* og = getenv("SGC_COMM_ONE_GROUP");
+  const bool one_group = og && og[0] == '1';
+  if (one_group) SGC_NCCL(c.api.GroupStart());
   for (sgc_plan_s::Peer& q : p->peers) {
+    if (!one_group) SGC_NCCL(c.api.GroupStart());
     if (q.send_elems) SGC_NCCL(c.api.Send(q.d_send, (size_t)q.send_elems * l->esz, ncclChar, q.rank, c.comm, r.comm));
     if (q.recv_elems) SGC_NCCL(c.api.Recv(q.d_recv, (size_t)q.recv_elems * l->esz, ncclChar, q.rank, c.comm, r.comm));
+    if (!one_group) {
+      SGC_NCCL(c.api.GroupEnd());
+      SGC_CUDA(cudaEventRecord(q.ev_arrived, r.comm));
+    }
   }
-  SGC_NCCL(c.api.GroupEnd());
+  if (one_group) {
+    SGC_NCCL(c.api.GroupEnd());
+    for (sgc_plan_s::Peer& q : p->peers) SGC_CUDA(cudaEventRecord(q.ev_arrived, r.comm));
+  }
   SGC_CUDA(cudaEventRecord(p->ev_halo, r.comm));
   return 0;
 }
 
 int comm_exchange_end(sgc_level_s* l, sgc_plan_s* p) {
   Runtime& r = rt();
-  SGC_CUDA(cudaStreamWaitEvent(r.compute, p->ev_halo, 0));
   for (sgc_plan_s::Peer& q : p->peers) {
+    SGC_CUDA(cudaStreamWaitEvent(r.compute, q.ev_arrived, 0));       // this peer's message only
     const int st = launch_copy(q.unpack, l->d_arena, q.d_recv, l->esz, r.compute);
     if (st) return st;
   }

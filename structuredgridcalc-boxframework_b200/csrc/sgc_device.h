@@ -273,6 +273,7 @@ struct sgc_plan_s {
     void* d_send = nullptr;
     void* d_recv = nullptr;
     long long send_elems = 0, recv_elems = 0;
+    cudaEvent_t ev_arrived = nullptr;   // this peer's message has landed in d_recv (recorded on the comm stream)
   };
   std::vector<Peer> peers;
   int n_boundary_boxes = 0;               // boxes with at least one remote item

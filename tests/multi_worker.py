@@ -87,14 +87,21 @@ def run_gpu(rank, world, local_rank):
     ids = [sgc.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     sgc.comm_init(world, rank, ids[0])
-    for dlo, dhi, mb, per, f, nstep in (((0, 0, 0), (31, 31, 32 * world - 1), (16, 16, 16), 7, 0.125, 12),
-                                        ((0, 0, 0), (63, 63, 64 * world - 1), (64, 64, 64), 7, 1.0 / 6.0, 6),
-                                        ((0, 0, 0), (127, 63, 128 * world - 1), (64, 64, 64), 7, 0.2, 11),
-                                        ((0, 0, 0), (127, 63, 128 * world - 1), (64, 64, 64), 3, 0.2, 10),   # z ends: physical
-                                        ((0, 0, 0), (63, 127, 64 * world - 1), (64, 64, 64), 0, 0.125, 9),    # no periodicity
-                                        ((0, 0, 0), (63, 31, 64 * world - 1), (32, 32, 32), 3, 0.125, 9),
-                                        ((0, 0, 0), (15, 15, 8 * world - 1), (8, 8, 8), 0, 0.125, 5),
-                                        ((0, 0, 0), (11, 7, 10 * world - 1), (6, 4, 5), 3, 0.2, 4)):
+    cases = (((0, 0, 0), (31, 31, 32 * world - 1), (16, 16, 16), 7, 0.125, 12),
+             ((0, 0, 0), (63, 63, 64 * world - 1), (64, 64, 64), 7, 1.0 / 6.0, 6),
+             ((0, 0, 0), (127, 63, 128 * world - 1), (64, 64, 64), 7, 0.2, 11),
+             ((0, 0, 0), (127, 63, 128 * world - 1), (64, 64, 64), 3, 0.2, 10),   # z ends: physical
+             ((0, 0, 0), (63, 127, 64 * world - 1), (64, 64, 64), 0, 0.125, 9),    # no periodicity
+             ((0, 0, 0), (63, 31, 64 * world - 1), (32, 32, 32), 3, 0.125, 9),
+             ((0, 0, 0), (15, 15, 8 * world - 1), (8, 8, 8), 0, 0.125, 5),
+             ((0, 0, 0), (11, 7, 10 * world - 1), (6, 4, 5), 3, 0.2, 4))
+    # every case twice: z halo read out of the neighbour's memory (default), and the NCCL schedule (SGC_P2P=0:
+    # pack, one send/recv pair per peer, each peer's message unpacked as it arrives — LevelData.H:507-536)
+    for p2p_env, (dlo, dhi, mb, per, f, nstep) in [(e, c) for e in (None, "0") for c in cases]:
+        if p2p_env is None:
+            os.environ.pop("SGC_P2P", None)
+        else:
+            os.environ["SGC_P2P"] = p2p_env
         dbl = sgc.DisjointBoxLayout(sgc.Box(dlo, dhi), mb, world, rank)
         allboxes, _, _ = O.layout(dlo, dhi, mb)
         u0 = O.fill_hash(allboxes, 1, 0.0)
@@ -126,6 +133,7 @@ def run_gpu(rank, world, local_rank):
             assert n2 == ((nstep - 2) // 2) & ~1, ("two-step passes", n2, nstep)
         if world > 1:
             assert cp.numRemoteItem() > 0
+    os.environ.pop("SGC_P2P", None)
     sgc.sync()
     dist.barrier()
     sgc.comm_finalize()

@@ -41,6 +41,9 @@ def test_multirank_nccl_halo_parity():
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     out = _launch("gpu", 2)
     assert out.count("gpu multi-rank parity ok") == 2
+    if n >= 4:          # several peers per rank: per-peer message order and unpack-as-arrived
+        out = _launch("gpu", 4)
+        assert out.count("gpu multi-rank parity ok") == 4
 
 
 @pytest.mark.gpu
