@@ -21,6 +21,8 @@ if [ -d "$REF_DIR/lib/test/BoxFramework" ]; then
   for t in testIntVect testBox testBoxIterator testBaseFab testDisjointBoxLayout testLayoutIterator testLevelData; do
     $CXX $FL -o "$OUT/ref_$t" "$REF_DIR/lib/test/BoxFramework/$t.cpp" $LD
   done
-  echo "[apps] built the reference's 7 serial tests against the B200 facade"
+  # the reference's VLA / MD_ARRAY address-identity program (application/vlaloops/vlaloops.cpp:30-95), unmodified
+  $CXX $FL -o "$OUT/ref_vlaloops" "$REF_DIR/application/vlaloops/vlaloops.cpp" $LD
+  echo "[apps] built the reference's 7 serial tests and vlaloops against the B200 facade"
 fi
 echo "[apps] done"

@@ -295,6 +295,14 @@ long long sgc_copyset_num_cells(sgc_copyset_t set);
  *   unew = u + f*( ((u[i+1]-2u)+u[i-1]) + ((u[j+1]-2u)+u[j-1]) + ((u[k+1]-2u)+u[k-1]) )
  * on the valid cells of each box; u needs nghost >= 1, filled by sgc_exchange.              */
 int sgc_heat_sweep(sgc_level_t unew, sgc_level_t u, double f, unsigned flags);
+/* All sweeps take levels of double or of float (the reference's USE_SINGLE_PRECISION build,
+ * Parameters.H:17-23) and update every component.                                            */
+/* General weighted 7-point stencil on every component:
+ *   out = w[0]*u; out += w[1]*u[i-1]; out += w[2]*u[i+1]; out += w[3]*u[j-1]; out += w[4]*u[j+1];
+ *   out += w[5]*u[k-1]; out += w[6]*u[k+1]          (in this order; fused multiply-adds with SGC_FMA)
+ * — the loop form of the reference's device stencil test (gpuSandbox.cpp:120-151: B = A[-e_z] + A + A[+e_z]
+ * per component, on the moving SlabFab window of CudaFab.H:539-905).                          */
+int sgc_stencil7_apply(sgc_level_t out, sgc_level_t in, const double weights[7], unsigned flags);
 /* Only boxes [box_begin, box_end) — used to overlap interior boxes with the halo transfer.   */
 int sgc_heat_sweep_range(sgc_level_t unew, sgc_level_t u, double f, unsigned flags,
                          int box_begin, int box_end);

@@ -41,6 +41,9 @@ $CXX $COMMON $REL                   -shared -o "$OUT/libsgcref.so"       $LIBSRC
 $CXX $COMMON $REL -ffp-contract=off -shared -o "$OUT/libsgcref_nofma.so" $LIBSRC "$HERE/ref_shim.cpp"
 $CXX $COMMON $REL -fopenmp          -shared -o "$OUT/libsgcref_omp.so"   $LIBSRC "$HERE/ref_shim.cpp"
 $CXX $COMMON -O1 -g                 -shared -o "$OUT/libsgcref_dbg.so"   $LIBSRC "$HERE/ref_shim.cpp"
+# the reference's single-precision build (Real = float, Parameters.H:17-23,197): same shim, float buffers
+$CXX $COMMON $REL -DUSE_SINGLE_PRECISION                   -shared -o "$OUT/libsgcref_sp.so"       $LIBSRC "$HERE/ref_shim.cpp"
+$CXX $COMMON $REL -DUSE_SINGLE_PRECISION -ffp-contract=off -shared -o "$OUT/libsgcref_sp_nofma.so" $LIBSRC "$HERE/ref_shim.cpp"
 # the shipped wave time stepper (WavePatch, USE_VEX pencil path); cgnslib.h is included
 # unconditionally by WavePatch.cpp:15 -> an empty stub on the include path
 mkdir -p "$OUT/stub"
@@ -54,7 +57,7 @@ LBFL="-std=c++14 -Wno-vla -Wno-unknown-pragmas -w -I$S -fPIC -I$HERE/cgns_record
 $CXX $LBFL $REL                   -shared -o "$OUT/libsgcref_lb.so"       $LIBSRC "$LB/LBLevel.cpp" "$HERE/ref_lb_shim.cpp"
 $CXX $LBFL $REL -ffp-contract=off -shared -o "$OUT/libsgcref_lb_nofma.so" $LIBSRC "$LB/LBLevel.cpp" "$HERE/ref_lb_shim.cpp"
 $CXX $LBFL $REL -fopenmp          -shared -o "$OUT/libsgcref_lb_omp.so"   $LIBSRC "$LB/LBLevel.cpp" "$HERE/ref_lb_shim.cpp"
-echo "[oracle] built _ref/libsgcref{,_nofma,_omp,_dbg,_wave,_lb,_lb_nofma,_lb_omp}.so from $REF_DIR"
+echo "[oracle] built _ref/libsgcref{,_nofma,_omp,_dbg,_sp,_sp_nofma,_wave,_lb,_lb_nofma,_lb_omp}.so from $REF_DIR"
 
 # the reference's own serial tests, asserts live (no -DRELEASE)
 T="$REF_DIR/lib/test/BoxFramework"

@@ -227,23 +227,28 @@ class Reference:
     def __init__(self, variant=""):
         self.variant = variant
         self.lib = L = C.CDLL(ref_path(variant))
+        # "_sp", "_sp_nofma": the reference built with -DUSE_SINGLE_PRECISION (Real = float): float32 buffers
+        self.dtype = np.float32 if variant.startswith("_sp") else np.float64
+        _dp = _P(dtype=self.dtype, flags="C_CONTIGUOUS")
+        _real = C.c_float if self.dtype == np.float32 else C.c_double
         L.sgcref_openmp_threads.restype = C.c_int
         L.sgcref_layout.argtypes = [_i3, _i3, _i3, C.c_int, _ip, _ip, C.c_int]
         L.sgcref_copier_items.argtypes = [_i3, _i3, _i3, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int,
                                           C.c_int, C.c_void_p, C.c_int]
         L.sgcref_level_exchange.argtypes = [_i3, _i3, _i3, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, _dp]
-        L.sgcref_level_heat.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_double, C.c_int, _dp, _dp]
+        L.sgcref_level_heat.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, _real, C.c_int, _dp,
+                                        _P(dtype=np.float64, flags="C_CONTIGUOUS")]
         L.sgcref_laplacian.argtypes = [C.c_int, C.c_int, _dp, _dp]
         L.sgcref_laplacian.restype = C.c_double
         L.sgcref_laplacian_boxiter.argtypes = [C.c_int, C.c_int, _dp, _dp]
         L.sgcref_laplacian_boxiter.restype = C.c_double
-        L.sgcref_wave.argtypes = [_i3, _i3, C.c_double, C.c_int, _dp, _dp]
+        L.sgcref_wave.argtypes = [_i3, _i3, _real, C.c_int, _dp, _dp]
         fabargs = [_i3, _i3, C.c_int, _dp]
         L.sgcref_fab_copy.argtypes = fabargs + fabargs + [_i3, _i3, C.c_int, _i3, _i3, C.c_int, C.c_int, C.c_uint]
         L.sgcref_fab_copy_same.argtypes = fabargs + [_i3, _i3, _dp, _i3, _i3]
         L.sgcref_fab_linear_out.argtypes = fabargs + [_i3, _i3, C.c_int, C.c_int, C.c_uint, _dp]
         L.sgcref_fab_linear_in.argtypes = fabargs + [_i3, _i3, C.c_int, C.c_int, C.c_uint, _dp]
-        L.sgcref_fab_setval.argtypes = fabargs + [C.c_int, C.c_double]
+        L.sgcref_fab_setval.argtypes = fabargs + [C.c_int, _real]
         L.sgcref_adjbox.argtypes = [_i3, _i3, C.c_int, C.c_int, C.c_int, _ip]
 
     def threads(self):
@@ -282,7 +287,7 @@ class Reference:
         return n, t
 
     def laplacian(self, n, niter, A, boxiter=False):
-        B = np.zeros((n - 2) ** 3)
+        B = np.zeros((n - 2) ** 3, self.dtype)
         fn = self.lib.sgcref_laplacian_boxiter if boxiter else self.lib.sgcref_laplacian
         ms = fn(n, niter, A, B)
         return B, ms

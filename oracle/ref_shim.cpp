@@ -60,22 +60,22 @@ inline void putbox(int* out, const Box& b)
 
 /* Concatenated level storage used across the shim boundary: fabs in local box order,
  * each ncomp*(box grown by ng).size() doubles, reference memory order.              */
-void levelIn(LevelData<FArrayBox>& ld, const DisjointBoxLayout& dbl, const double* src)
+void levelIn(LevelData<FArrayBox>& ld, const DisjointBoxLayout& dbl, const Real* src)
 {
   for (DataIterator dit(dbl); dit.ok(); ++dit)
     {
       FArrayBox& fab = ld[dit];
-      std::memcpy(fab.dataPtr(), src, sizeof(double)*fab.size());
+      std::memcpy(fab.dataPtr(), src, sizeof(Real)*fab.size());
       src += fab.size();
     }
 }
 
-void levelOut(const LevelData<FArrayBox>& ld, const DisjointBoxLayout& dbl, double* dst)
+void levelOut(const LevelData<FArrayBox>& ld, const DisjointBoxLayout& dbl, Real* dst)
 {
   for (DataIterator dit(dbl); dit.ok(); ++dit)
     {
       const FArrayBox& fab = ld[dit];
-      std::memcpy(dst, fab.dataPtr(), sizeof(double)*fab.size());
+      std::memcpy(dst, fab.dataPtr(), sizeof(Real)*fab.size());
       dst += fab.size();
     }
 }
@@ -84,7 +84,7 @@ void levelOut(const LevelData<FArrayBox>& ld, const DisjointBoxLayout& dbl, doub
  * reference applications use (MD_ARRAY_RESTRICT + MD_BOXLOOP over dbl[dit]).
  * unew = u + f*( (u[i+1]-2u+u[i-1]) + (u[j+1]-2u+u[j-1]) + (u[k+1]-2u+u[k-1]) )     */
 void heatSweep(LevelData<FArrayBox>& unew, LevelData<FArrayBox>& u,
-               const DisjointBoxLayout& dbl, const double f)
+               const DisjointBoxLayout& dbl, const Real f)
 {
   for (DataIterator dit(dbl); dit.ok(); ++dit)
     {
@@ -187,7 +187,7 @@ int sgcref_copier_items(const int* dlo, const int* dhi, const int* maxbox, int n
  * mode 0 = LevelData::exchange, 1 = exchangeBegin + exchangeEnd.                    */
 int sgcref_level_exchange(const int* dlo, const int* dhi, const int* maxbox, int ng,
                           int ncomp, unsigned periodic, unsigned trim, int mode,
-                          double* fabs)
+                          Real* fabs)
 {
   LayoutRanks::set(1, 0);
   DisjointBoxLayout dbl(mkbox(dlo, dhi), IntVect(maxbox[0], maxbox[1], maxbox[2]));
@@ -205,8 +205,8 @@ int sgcref_level_exchange(const int* dlo, const int* dhi, const int* maxbox, int
  * on entry and the last-written level on exit.  times_ms[0..2] = plan build,
  * total exchange, total sweep (Stopwatch, ms).                                      */
 int sgcref_level_heat(const int* dlo, const int* dhi, const int* maxbox, int ng,
-                      unsigned periodic, unsigned trim, double f, int nstep,
-                      double* fabs, double* times_ms)
+                      unsigned periodic, unsigned trim, Real f, int nstep,
+                      Real* fabs, double* times_ms)
 {
   LayoutRanks::set(1, 0);
   DisjointBoxLayout dbl(mkbox(dlo, dhi), IntVect(maxbox[0], maxbox[1], maxbox[2]));
@@ -242,11 +242,11 @@ int sgcref_level_heat(const int* dlo, const int* dhi, const int* maxbox, int ng,
 
 /* The PR1 driver's VLA-macro sweep (laplacian.cpp:90-110) on caller-supplied A.
  * A on (1..n)^3, B on (2..n-1)^3, B zeroed first, `niter` x 3 directional passes.   */
-double sgcref_laplacian(int n, int niter, const double* A, double* B)
+double sgcref_laplacian(int n, int niter, const Real* A, Real* B)
 {
   Box allocBox(IntVect::Unit, n*IntVect::Unit);
   FArrayBox fabA(allocBox, 1);
-  std::memcpy(fabA.dataPtr(), A, sizeof(double)*fabA.size());
+  std::memcpy(fabA.dataPtr(), A, sizeof(Real)*fabA.size());
   Box computeBox(allocBox);
   computeBox.grow(-1);
   FArrayBox fabB(computeBox, 1);
@@ -267,16 +267,16 @@ double sgcref_laplacian(int n, int niter, const double* A, double* B)
           }
       }
   timer.stop();
-  std::memcpy(B, fabB.dataPtr(), sizeof(double)*fabB.size());
+  std::memcpy(B, fabB.dataPtr(), sizeof(Real)*fabB.size());
   return timer.time();
 }
 
 /* Same sweep through BoxIterator + operator() (laplacian.cpp:58-79). */
-double sgcref_laplacian_boxiter(int n, int niter, const double* A, double* B)
+double sgcref_laplacian_boxiter(int n, int niter, const Real* A, Real* B)
 {
   Box allocBox(IntVect::Unit, n*IntVect::Unit);
   FArrayBox fabA(allocBox, 1);
-  std::memcpy(fabA.dataPtr(), A, sizeof(double)*fabA.size());
+  std::memcpy(fabA.dataPtr(), A, sizeof(Real)*fabA.size());
   Box computeBox(allocBox);
   computeBox.grow(-1);
   FArrayBox fabB(computeBox, 1);
@@ -294,22 +294,22 @@ double sgcref_laplacian_boxiter(int n, int niter, const double* A, double* B)
           }
       }
   timer.stop();
-  std::memcpy(B, fabB.dataPtr(), sizeof(double)*fabB.size());
+  std::memcpy(B, fabB.dataPtr(), sizeof(Real)*fabB.size());
   return timer.time();
 }
 
 /* Single-box leap-frog wave step in the reference's scalar form
  * (WavePatch.cpp:156-166 BC by adjBox copies, :226-244 update), nstep steps.
  * u0 = u^n, u1 = u^{n-1}, both on grow(domain,1); on exit u0 = latest, u1 = previous. */
-void sgcref_wave(const int* dlo, const int* dhi, double factor, int nstep,
-                 double* u0, double* u1)
+void sgcref_wave(const int* dlo, const int* dhi, Real factor, int nstep,
+                 Real* u0, Real* u1)
 {
   const Box domain = mkbox(dlo, dhi);
   Box gb(domain);
   gb.grow(1);
   FArrayBox u[3] = { FArrayBox(gb, 1), FArrayBox(gb, 1), FArrayBox(gb, 1) };
-  std::memcpy(u[0].dataPtr(), u0, sizeof(double)*u[0].size());
-  std::memcpy(u[2].dataPtr(), u1, sizeof(double)*u[2].size());
+  std::memcpy(u[0].dataPtr(), u0, sizeof(Real)*u[0].size());
+  std::memcpy(u[2].dataPtr(), u1, sizeof(Real)*u[2].size());
   u[1].setVal(0.);
   int in = 0, inp1 = 1, inm1 = 2;
   for (int s = 0; s != nstep; ++s)
@@ -344,13 +344,13 @@ void sgcref_wave(const int* dlo, const int* dhi, double factor, int nstep,
         }
       const int t = inm1; inm1 = in; in = inp1; inp1 = t;
     }
-  std::memcpy(u0, u[in].dataPtr(), sizeof(double)*u[in].size());
-  std::memcpy(u1, u[inm1].dataPtr(), sizeof(double)*u[inm1].size());
+  std::memcpy(u0, u[in].dataPtr(), sizeof(Real)*u[in].size());
+  std::memcpy(u1, u[inm1].dataPtr(), sizeof(Real)*u[inm1].size());
 }
 
 /* BaseFab primitives on caller memory (alias construction, BaseFab.H:59-76). */
-void sgcref_fab_copy(const int* dfb_lo, const int* dfb_hi, int dncomp, double* ddata,
-                     const int* sfb_lo, const int* sfb_hi, int sncomp, double* sdata,
+void sgcref_fab_copy(const int* dfb_lo, const int* dfb_hi, int dncomp, Real* ddata,
+                     const int* sfb_lo, const int* sfb_hi, int sncomp, Real* sdata,
                      const int* dlo, const int* dhi, int dcomp,
                      const int* slo, const int* shi, int scomp, int ncomp,
                      unsigned flags)
@@ -360,8 +360,8 @@ void sgcref_fab_copy(const int* dfb_lo, const int* dfb_hi, int dncomp, double* d
   dst.copy(mkbox(dlo, dhi), dcomp, src, mkbox(slo, shi), scomp, ncomp, flags);
 }
 
-void sgcref_fab_copy_same(const int* dfb_lo, const int* dfb_hi, int ncomp, double* ddata,
-                          const int* sfb_lo, const int* sfb_hi, double* sdata,
+void sgcref_fab_copy_same(const int* dfb_lo, const int* dfb_hi, int ncomp, Real* ddata,
+                          const int* sfb_lo, const int* sfb_hi, Real* sdata,
                           const int* rlo, const int* rhi)
 {
   FArrayBox dst(mkbox(dfb_lo, dfb_hi), ncomp, ddata);
@@ -369,24 +369,24 @@ void sgcref_fab_copy_same(const int* dfb_lo, const int* dfb_hi, int ncomp, doubl
   dst.copy(mkbox(rlo, rhi), src);
 }
 
-void sgcref_fab_linear_out(const int* fb_lo, const int* fb_hi, int ncomp, double* data,
+void sgcref_fab_linear_out(const int* fb_lo, const int* fb_hi, int ncomp, Real* data,
                            const int* rlo, const int* rhi, int c0, int c1,
-                           unsigned flags, double* buffer)
+                           unsigned flags, Real* buffer)
 {
   FArrayBox fab(mkbox(fb_lo, fb_hi), ncomp, data);
   fab.linearOut(buffer, mkbox(rlo, rhi), c0, c1, flags);
 }
 
-void sgcref_fab_linear_in(const int* fb_lo, const int* fb_hi, int ncomp, double* data,
+void sgcref_fab_linear_in(const int* fb_lo, const int* fb_hi, int ncomp, Real* data,
                           const int* rlo, const int* rhi, int c0, int c1,
-                          unsigned flags, const double* buffer)
+                          unsigned flags, const Real* buffer)
 {
   FArrayBox fab(mkbox(fb_lo, fb_hi), ncomp, data);
   fab.linearIn(buffer, mkbox(rlo, rhi), c0, c1, flags);
 }
 
-void sgcref_fab_setval(const int* fb_lo, const int* fb_hi, int ncomp, double* data,
-                       int comp, double val)
+void sgcref_fab_setval(const int* fb_lo, const int* fb_hi, int ncomp, Real* data,
+                       int comp, Real val)
 {
   FArrayBox fab(mkbox(fb_lo, fb_hi), ncomp, data);
   if (comp < 0) fab.setVal(val); else fab.setVal(comp, val);

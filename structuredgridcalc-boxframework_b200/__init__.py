@@ -34,7 +34,7 @@ SYMBOLS = [
     "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
     "sgc_level_upload_async", "sgc_level_download_async", "sgc_copyset_create", "sgc_copyset_run", "sgc_copyset_destroy",
     "sgc_copyset_num_cells", "sgc_level_valid_elems", "sgc_level_download_valid", "sgc_level_download_valid_async", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run", "sgc_lb_selftest_divconst",
-    "sgc_level_edge_strips", "sgc_plan_rebox_factors", "sgc_plan_create_exchange_ex", "sgc_plan_matches_level",
+    "sgc_level_edge_strips", "sgc_plan_rebox_factors", "sgc_plan_create_exchange_ex", "sgc_plan_matches_level", "sgc_stencil7_apply",
 ]
 
 
@@ -124,6 +124,7 @@ def lib():
     L.sgc_heat_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint]
     L.sgc_heat_sweep_range.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint, C.c_int, C.c_int]
     L.sgc_heat_sweep_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.sgc_stencil7_apply.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_uint]
     L.sgc_laplacian_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_uint]
     L.sgc_wave_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint]
     L.sgc_wave_run.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_double, C.c_uint, C.c_int,
@@ -365,9 +366,13 @@ class LevelData:
     on grow(box, nghost), all in one HBM arena.  Host arrays are the fabs concatenated in box order,
     reference memory order."""
 
-    def __init__(self, dbl, ncomp, nghost, elem_bytes=8, boxes=None):
+    def __init__(self, dbl, ncomp, nghost, elem_bytes=8, boxes=None, dtype=None):
+        """dtype: host element type when it is not the default of the size (np.float32: a level of float,
+        the reference's USE_SINGLE_PRECISION Real)"""
+        if dtype is not None:
+            elem_bytes = np.dtype(dtype).itemsize
         self.dbl, self.ncomp, self.nghost, self.elem_bytes = dbl, int(ncomp), int(nghost), int(elem_bytes)
-        self.dtype = _DT[self.elem_bytes]
+        self.dtype = np.dtype(dtype).type if dtype is not None else _DT[self.elem_bytes]
         if boxes is None:
             boxes, gidx0 = dbl.local_boxes(), dbl.localIdxBegin()
         else:
@@ -553,6 +558,12 @@ def heat_sweep(unew, u, f, flags=SGC_FMA, box_range=None):
         check(lib().sgc_heat_sweep_ranges(unew.h, u.h, f, flags, *box_range))
     else:
         check(lib().sgc_heat_sweep_range(unew.h, u.h, f, flags, box_range[0], box_range[1]))
+
+
+def stencil7_apply(out, u, weights, flags=SGC_FMA):
+    """out = w0*u + w1*u[i-1] + w2*u[i+1] + w3*u[j-1] + w4*u[j+1] + w5*u[k-1] + w6*u[k+1] on every component"""
+    w = (C.c_double * 7)(*[float(x) for x in weights])
+    check(lib().sgc_stencil7_apply(out.h, u.h, w, flags))
 
 
 def laplacian_apply(B, A, coef=0.5, niter=16, fuse_iters=0, flags=SGC_FMA):

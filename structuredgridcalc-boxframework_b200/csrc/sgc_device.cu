@@ -16,12 +16,14 @@ Runtime& rt() {
 }
 
 // kernels / launchers (sgc_kernels.cu, sgc_stream.cu)
-int launch_heat_generic(const int*, int, int, const FabGeom*, const FabGeom*, const double*, double*, double, int,
+int launch_heat_generic(const int*, int, int, int ncomp, int esz, const FabGeom*, const FabGeom*, const void*, void*, double, int,
                         cudaStream_t);
-int launch_lap_generic(const int*, int, int, const FabGeom*, const FabGeom*, const double*, double*, double, int, int,
+int launch_lap_generic(const int*, int, int, int ncomp, int esz, const FabGeom*, const FabGeom*, const void*, void*, double, int, int,
                        cudaStream_t);
-int launch_wave_generic(const int*, int, int, const FabGeom*, const FabGeom*, const double*, double*, const double*,
+int launch_wave_generic(const int*, int, int, int ncomp, int esz, const FabGeom*, const FabGeom*, const void*, void*, const void*,
                         double, int, cudaStream_t);
+int launch_weight_generic(const int*, int, int, int ncomp, int esz, const FabGeom*, const FabGeom*, const void*, void*,
+                          const double w[7], int, cudaStream_t);
 int sweep_tile_y();
 int sweep_tile_z();
 // streaming sweep (returns 1 when it does not apply to this geometry, 0 when launched, <0 on error)
@@ -1136,7 +1138,10 @@ int sgc_exchange(sgc_level_t l, sgc_plan_t p) {
 // ------------------------------------------------------------------------------- stencil apply
 static int check_sweep(sgc_level_s* out, sgc_level_s* in, const char* who) {
   if (!out || !in) return fail(SGC_ERR_ARG, std::string(who) + ": null level");
-  if (out->esz != 8 || in->esz != 8) return fail(SGC_ERR_UNSUPPORTED, std::string(who) + ": needs 8-byte Real");
+  // Real is double, or float as in the reference's USE_SINGLE_PRECISION build (Parameters.H:17-23)
+  if ((out->esz != 8 && out->esz != 4) || in->esz != out->esz)
+    return fail(SGC_ERR_UNSUPPORTED, std::string(who) + ": levels must both hold double or both hold float");
+  if (out->ncomp != in->ncomp) return fail(SGC_ERR_GEOMETRY, std::string(who) + ": levels have different component counts");
   if (out == in) return fail(SGC_ERR_ARG, std::string(who) + ": in-place sweep is not defined");
   // The swept region of box b is out's valid box; the two levels need not share a layout (the PR1
   // driver sweeps B on (2..n-1)^3 from A on (1..n)^3, laplacian.cpp:13-33) but must pair up box by box.
@@ -1159,8 +1164,8 @@ int sgc_heat_sweep_range(sgc_level_t unew, sgc_level_t u, double f, unsigned fla
   if (st <= 0) return st;
   const int w0 = unew->work_begin[box_begin], w1 = unew->work_begin[box_end];
   level_written(unew);
-  return launch_heat_generic(unew->d_work, w0, w1 - w0, u->d_geom, unew->d_geom, (const double*)u->d_arena,
-                             (double*)unew->d_arena, f, fma, rt().compute);
+  return launch_heat_generic(unew->d_work, w0, w1 - w0, unew->ncomp, unew->esz, u->d_geom, unew->d_geom, u->d_arena,
+                             unew->d_arena, f, fma, rt().compute);
 }
 
 int sgc_heat_sweep(sgc_level_t unew, sgc_level_t u, double f, unsigned flags) {
@@ -1178,8 +1183,8 @@ int sgc_laplacian_apply(sgc_level_t B, sgc_level_t A, double coef, int niter, in
   const int per = fuse_iters ? niter : 1;
   level_written(B);
   for (int i = 0; i < launches && !st; ++i)
-    st = launch_lap_generic(B->d_work, 0, B->nwork, A->d_geom, B->d_geom, (const double*)A->d_arena,
-                            (double*)B->d_arena, coef, (flags & SGC_FMA) ? 1 : 0, per, rt().compute);
+    st = launch_lap_generic(B->d_work, 0, B->nwork, B->ncomp, B->esz, A->d_geom, B->d_geom, A->d_arena,
+                            B->d_arena, coef, (flags & SGC_FMA) ? 1 : 0, per, rt().compute);
   return st;
 }
 
@@ -1188,14 +1193,26 @@ int sgc_wave_step(sgc_level_t unp1, sgc_level_t un, sgc_level_t unm1, double fac
   int st = check_sweep(unp1, un, "sgc_wave_step");
   if (st) return st;
   if (!unm1 || !same_geometry(un, unm1)) return fail(SGC_ERR_GEOMETRY, "sgc_wave_step: un and unm1 must share geometry");
+  if (unm1->esz != un->esz) return fail(SGC_ERR_UNSUPPORTED, "sgc_wave_step: element types differ");
   if (unm1 == unp1) return fail(SGC_ERR_ARG, "sgc_wave_step: unp1 must not alias unm1");
   ProfScope prof(0, rt().compute);
   level_written(unp1);
   const int wf = (int)(flags & (SGC_FMA | SGC_WAVE_DIRSUM));      // bit 0 fma, bit 1 dirsum form
   st = launch_wave_stream(unp1, un, unm1, factor, wf, rt().compute);
   if (st <= 0) return st;
-  return launch_wave_generic(unp1->d_work, 0, unp1->nwork, un->d_geom, unp1->d_geom, (const double*)un->d_arena,
-                             (double*)unp1->d_arena, (const double*)unm1->d_arena, factor, wf, rt().compute);
+  return launch_wave_generic(unp1->d_work, 0, unp1->nwork, unp1->ncomp, unp1->esz, un->d_geom, unp1->d_geom, un->d_arena,
+                             unp1->d_arena, unm1->d_arena, factor, wf, rt().compute);
+}
+
+int sgc_stencil7_apply(sgc_level_t out, sgc_level_t in, const double weights[7], unsigned flags) {
+  SGC_REQUIRE_RT();
+  int st = check_sweep(out, in, "sgc_stencil7_apply");
+  if (st) return st;
+  if (!weights) return fail(SGC_ERR_ARG, "sgc_stencil7_apply: null weights");
+  ProfScope prof(0, rt().compute);
+  level_written(out);
+  return launch_weight_generic(out->d_work, 0, out->nwork, out->ncomp, out->esz, in->d_geom, out->d_geom, in->d_arena,
+                               out->d_arena, weights, (flags & SGC_FMA) ? 1 : 0, rt().compute);
 }
 
 int sgc_heat_sweep_ranges(sgc_level_t nxt, sgc_level_t cur, double f, unsigned flags, int a0, int a1, int b0, int b1) {

@@ -249,54 +249,94 @@ int launch_fill(void* p, long long n, int esz, const void* value, cudaStream_t s
 // ---------------------------------------------------------------------------------------------
 constexpr int kTileX = 64, kTileY = 4, kTileZ = 16;
 
+// Correctly rounded arithmetic of the element type, spelled out so that nvcc can neither contract nor
+// re-associate: double (the reference's default Real) and float (its USE_SINGLE_PRECISION build,
+// Parameters.H:17-23,197).
+template <typename T> struct Ar;
+template <> struct Ar<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+};
+template <> struct Ar<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+};
+
+// second difference in the reference's association: (u[+e] - 2u) + u[-e]; 2u is exact.
+template <typename T>
+__device__ __forceinline__ T d2(T p, T c, T m) {
+  return Ar<T>::add(Ar<T>::sub(p, Ar<T>::mul((T)2, c)), m);
+}
+
+// The ops see the centre value and its six neighbours (xm, xp, ym, yp, zm, zp) and the auxiliary value.
+template <typename T>
 struct HeatOp {                       // unew = u + f*S
-  double f; int fma;
-  __device__ __forceinline__ double operator()(double c, double tx, double ty, double tz, double) const {
-    const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
-    return fma ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+  T f; int fma;
+  __device__ __forceinline__ T operator()(T c, T xm, T xp, T ym, T yp, T zm, T zp, T) const {
+    const T S = Ar<T>::add(Ar<T>::add(d2(xp, c, xm), d2(yp, c, ym)), d2(zp, c, zm));
+    return fma ? Ar<T>::fma(f, S, c) : Ar<T>::add(c, Ar<T>::mul(f, S));
   }
 };
+template <typename T>
 struct LapOp {                        // niter x { b -= coef*Tx; b -= coef*Ty; b -= coef*Tz }
-  double coef; int fma; int niter;
-  __device__ __forceinline__ double operator()(double, double tx, double ty, double tz, double b) const {
-    const double mc = -coef;
+  T coef; int fma; int niter;
+  __device__ __forceinline__ T operator()(T c, T xm, T xp, T ym, T yp, T zm, T zp, T b) const {
+    const T tx = d2(xp, c, xm), ty = d2(yp, c, ym), tz = d2(zp, c, zm);
+    const T mc = -coef;
     for (int it = 0; it < niter; ++it) {
-      if (fma) { b = __fma_rn(mc, tx, b); b = __fma_rn(mc, ty, b); b = __fma_rn(mc, tz, b); }
+      if (fma) { b = Ar<T>::fma(mc, tx, b); b = Ar<T>::fma(mc, ty, b); b = Ar<T>::fma(mc, tz, b); }
       else {
-        b = __dsub_rn(b, __dmul_rn(coef, tx)); b = __dsub_rn(b, __dmul_rn(coef, ty));
-        b = __dsub_rn(b, __dmul_rn(coef, tz));
+        b = Ar<T>::sub(b, Ar<T>::mul(coef, tx)); b = Ar<T>::sub(b, Ar<T>::mul(coef, ty));
+        b = Ar<T>::sub(b, Ar<T>::mul(coef, tz));
       }
     }
     return b;
   }
 };
+template <typename T>
 struct WaveOp {                       // r = 2u - um1; r += f*Tx; r += f*Ty; r += f*Tz   (or the MD_DIRSUM form)
-  double f; int fma;                  // fma: bit 0 = fused multiply-add, bit 1 = SGC_WAVE_DIRSUM
-  __device__ __forceinline__ double operator()(double c, double tx, double ty, double tz, double um1) const {
-    double r = __dsub_rn(__dmul_rn(2.0, c), um1);       // 2*c is exact: contraction-invariant
+  T f; int fma;                       // fma: bit 0 = fused multiply-add, bit 1 = SGC_WAVE_DIRSUM
+  __device__ __forceinline__ T operator()(T c, T xm, T xp, T ym, T yp, T zm, T zp, T um1) const {
+    const T tx = d2(xp, c, xm), ty = d2(yp, c, ym), tz = d2(zp, c, zm);
+    T r = Ar<T>::sub(Ar<T>::mul((T)2, c), um1);         // 2*c is exact: contraction-invariant
     if (fma & 2) {                                      // shipped pencil form: (2u - um1) + f*(Tz + (Ty + Tx))
-      const double sum = __dadd_rn(tz, __dadd_rn(ty, tx));
-      return (fma & 1) ? __fma_rn(f, sum, r) : __dadd_rn(r, __dmul_rn(f, sum));
+      const T sum = Ar<T>::add(tz, Ar<T>::add(ty, tx));
+      return (fma & 1) ? Ar<T>::fma(f, sum, r) : Ar<T>::add(r, Ar<T>::mul(f, sum));
     }
-    if (fma & 1) { r = __fma_rn(f, tx, r); r = __fma_rn(f, ty, r); r = __fma_rn(f, tz, r); return r; }
-    r = __dadd_rn(r, __dmul_rn(f, tx)); r = __dadd_rn(r, __dmul_rn(f, ty)); r = __dadd_rn(r, __dmul_rn(f, tz));
+    if (fma & 1) { r = Ar<T>::fma(f, tx, r); r = Ar<T>::fma(f, ty, r); r = Ar<T>::fma(f, tz, r); return r; }
+    r = Ar<T>::add(r, Ar<T>::mul(f, tx)); r = Ar<T>::add(r, Ar<T>::mul(f, ty)); r = Ar<T>::add(r, Ar<T>::mul(f, tz));
+    return r;
+  }
+};
+// General weighted 7-point stencil: r = w0*c; r += w1*u[x-1]; r += w2*u[x+1]; r += w3*u[y-1]; r += w4*u[y+1];
+// r += w5*u[z-1]; r += w6*u[z+1], in that order (each multiply-add fused when fma).  The loop form of the
+// reference's device stencil test (gpuSandbox.cpp:120-151: B = A[-e_z] + A + A[+e_z] on every component).
+template <typename T>
+struct WeightOp {
+  T w[7]; int fma;
+  __device__ __forceinline__ T operator()(T c, T xm, T xp, T ym, T yp, T zm, T zp, T) const {
+    const T v[6] = {xm, xp, ym, yp, zm, zp};
+    T r = Ar<T>::mul(w[0], c);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r = fma ? Ar<T>::fma(w[k + 1], v[k], r) : Ar<T>::add(r, Ar<T>::mul(w[k + 1], v[k]));
     return r;
   }
 };
 
-// second difference in the reference's association: (u[+e] - 2u) + u[-e]; 2u is exact.
-__device__ __forceinline__ double d2(double p, double c, double m) {
-  return __dadd_rn(__dsub_rn(p, __dmul_rn(2.0, c)), m);
-}
-
 // AUX: 0 none, 1 = read old value of out (read-modify-write), 2 = third level with in geometry.
 // Fabs are in the split-x device layout: x neighbours of the first / last valid column of the
 // input fab come from its xg block, everything else from the main block (fab_index()).
-template <class Op, int AUX>
+// blockIdx.y = component (the same component of the in, out and aux fabs).
+template <typename T, class Op, int AUX>
 __global__ void __launch_bounds__(kTileX * kTileY)
 k_sweep7(const int* __restrict__ work, const FabGeom* __restrict__ gin, const FabGeom* __restrict__ gout,
-         const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ aux, Op op) {
+         const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ aux, Op op) {
   const int b = work[3 * blockIdx.x], y0 = work[3 * blockIdx.x + 1], z0 = work[3 * blockIdx.x + 2];
+  const int comp = blockIdx.y;
   const FabGeom GI = gin[b], GO = gout[b];
   const int y = y0 + threadIdx.y;
   if (y >= GO.vn[1]) return;
@@ -309,52 +349,67 @@ k_sweep7(const int* __restrict__ work, const FabGeom* __restrict__ gin, const Fa
     // the centre column and its y / z neighbours live in one block of the in fab; strides there:
     const bool cmain = (ix >= GI.ngx) && (ix < GI.ngx + GI.mx);
     const long long sy = cmain ? GI.mx : 1, sz = cmain ? (long long)GI.mx * GI.n[1] : GI.n[1];
-    const double* __restrict__ p = in + fab_index(GI, ix, iy, iz0, 0);
-    const double* __restrict__ pxm = in + fab_index(GI, ix - 1, iy, iz0, 0);
-    const double* __restrict__ pxp = in + fab_index(GI, ix + 1, iy, iz0, 0);
+    const T* __restrict__ p = in + fab_index(GI, ix, iy, iz0, comp);
+    const T* __restrict__ pxm = in + fab_index(GI, ix - 1, iy, iz0, comp);
+    const T* __restrict__ pxp = in + fab_index(GI, ix + 1, iy, iz0, comp);
     const bool mmain = (ix - 1 >= GI.ngx) && (ix - 1 < GI.ngx + GI.mx), pmain = (ix + 1 >= GI.ngx) && (ix + 1 < GI.ngx + GI.mx);
     const long long szm = mmain ? (long long)GI.mx * GI.n[1] : GI.n[1], szp = pmain ? (long long)GI.mx * GI.n[1] : GI.n[1];
-    double* __restrict__ q = out + fab_index(GO, ox0 + x, oy, oz0, 0);
+    T* __restrict__ q = out + fab_index(GO, ox0 + x, oy, oz0, comp);
     const bool omain = (ox0 + x >= GO.ngx) && (ox0 + x < GO.ngx + GO.mx);
     const long long osz = omain ? (long long)GO.mx * GO.n[1] : GO.n[1];
-    const double* __restrict__ a = (AUX == 2) ? aux + fab_index(GI, ix, iy, iz0, 0) : nullptr;
-    double zm = __ldg(p - sz), c = __ldg(p);
+    const T* __restrict__ a = (AUX == 2) ? aux + fab_index(GI, ix, iy, iz0, comp) : nullptr;
+    T zm = __ldg(p - sz), c = __ldg(p);
     for (int z = z0; z < zend; ++z) {
-      const double zp = __ldg(p + sz);
-      const double tx = d2(__ldg(pxp), c, __ldg(pxm));
-      const double ty = d2(__ldg(p + sy), c, __ldg(p - sy));
-      const double tz = d2(zp, c, zm);
-      double av = 0.0;
+      const T zp = __ldg(p + sz);
+      T av = (T)0;
       if (AUX == 1) av = *q;
       if (AUX == 2) { av = __ldg(a); a += sz; }
-      *q = op(c, tx, ty, tz, av);
+      *q = op(c, __ldg(pxm), __ldg(pxp), __ldg(p - sy), __ldg(p + sy), zm, zp, av);
       zm = c; c = zp;
       p += sz; pxm += szm; pxp += szp; q += osz;
     }
   }
 }
 
-template <class Op, int AUX>
-static int launch_sweep(const int* d_work, int w0, int nwork, const FabGeom* gin, const FabGeom* gout,
-                        const double* in, double* out, const double* aux, Op op, cudaStream_t s) {
+template <typename T, class Op, int AUX>
+static int launch_sweep(const int* d_work, int w0, int nwork, int ncomp, const FabGeom* gin, const FabGeom* gout,
+                        const void* in, void* out, const void* aux, Op op, cudaStream_t s) {
   if (nwork <= 0) return 0;
-  k_sweep7<Op, AUX><<<nwork, dim3(kTileX, kTileY), 0, s>>>(d_work + 3 * (size_t)w0, gin, gout, in, out, aux, op);
+  k_sweep7<T, Op, AUX><<<dim3(nwork, ncomp), dim3(kTileX, kTileY), 0, s>>>(d_work + 3 * (size_t)w0, gin, gout, (const T*)in,
+                                                                           (T*)out, (const T*)aux, op);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_heat_generic(const int* d_work, int w0, int nwork, const FabGeom* gin, const FabGeom* gout,
-                        const double* in, double* out, double f, int fma, cudaStream_t s) {
-  return launch_sweep<HeatOp, 0>(d_work, w0, nwork, gin, gout, in, out, nullptr, HeatOp{f, fma}, s);
+// esz 8: double, 4: float.  Every component of the levels is swept.
+int launch_heat_generic(const int* d_work, int w0, int nwork, int ncomp, int esz, const FabGeom* gin, const FabGeom* gout,
+                        const void* in, void* out, double f, int fma, cudaStream_t s) {
+  if (esz == 4) return launch_sweep<float, HeatOp<float>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, HeatOp<float>{(float)f, fma}, s);
+  return launch_sweep<double, HeatOp<double>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, HeatOp<double>{f, fma}, s);
 }
-int launch_lap_generic(const int* d_work, int w0, int nwork, const FabGeom* gin, const FabGeom* gout,
-                       const double* in, double* out, double coef, int fma, int niter, cudaStream_t s) {
-  return launch_sweep<LapOp, 1>(d_work, w0, nwork, gin, gout, in, out, nullptr, LapOp{coef, fma, niter}, s);
+int launch_lap_generic(const int* d_work, int w0, int nwork, int ncomp, int esz, const FabGeom* gin, const FabGeom* gout,
+                       const void* in, void* out, double coef, int fma, int niter, cudaStream_t s) {
+  if (esz == 4) return launch_sweep<float, LapOp<float>, 1>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, LapOp<float>{(float)coef, fma, niter}, s);
+  return launch_sweep<double, LapOp<double>, 1>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, LapOp<double>{coef, fma, niter}, s);
 }
-int launch_wave_generic(const int* d_work, int w0, int nwork, const FabGeom* gin, const FabGeom* gout,
-                        const double* in, double* out, const double* um1, double f, int fma, cudaStream_t s) {
-  return launch_sweep<WaveOp, 2>(d_work, w0, nwork, gin, gout, in, out, um1, WaveOp{f, fma}, s);
+int launch_wave_generic(const int* d_work, int w0, int nwork, int ncomp, int esz, const FabGeom* gin, const FabGeom* gout,
+                        const void* in, void* out, const void* um1, double f, int fma, cudaStream_t s) {
+  if (esz == 4) return launch_sweep<float, WaveOp<float>, 2>(d_work, w0, nwork, ncomp, gin, gout, in, out, um1, WaveOp<float>{(float)f, fma}, s);
+  return launch_sweep<double, WaveOp<double>, 2>(d_work, w0, nwork, ncomp, gin, gout, in, out, um1, WaveOp<double>{f, fma}, s);
+}
+int launch_weight_generic(const int* d_work, int w0, int nwork, int ncomp, int esz, const FabGeom* gin, const FabGeom* gout,
+                          const void* in, void* out, const double w[7], int fma, cudaStream_t s) {
+  if (esz == 4) {
+    WeightOp<float> op;
+    for (int k = 0; k < 7; ++k) op.w[k] = (float)w[k];
+    op.fma = fma;
+    return launch_sweep<float, WeightOp<float>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, op, s);
+  }
+  WeightOp<double> op;
+  for (int k = 0; k < 7; ++k) op.w[k] = w[k];
+  op.fma = fma;
+  return launch_sweep<double, WeightOp<double>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, op, s);
 }
 
 int sweep_tile_y() { return kTileY; }

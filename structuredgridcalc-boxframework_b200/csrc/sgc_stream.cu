@@ -458,6 +458,7 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
                         cudaStream_t s, const PushArgs* fuse) {
   if (!u->uniform || !unew->uniform || u->ncomp != 1 || unew->ncomp != 1 || u->ng != unew->ng || u->ng != 1) return 1;
+  if (u->esz != 8 || unew->esz != 8) return 1;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0) return 1;
   if (a1 == a0) { a0 = b0; a1 = b1; b0 = b1 = a1; }
@@ -519,7 +520,7 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
 // Leap-frog wave step over all boxes with the streaming pipeline; 1 when the geometry is not covered.
 int launch_wave_stream(sgc_level_s* unp1, sgc_level_s* un, sgc_level_s* unm1, double f, int fma, cudaStream_t s) {
   if (!un->uniform || un->ncomp != 1 || unp1->ncomp != 1 || unm1->ncomp != 1 || un->ng != 1 || unp1->ng != 1 ||
-      unm1->ng != 1 || getenv("SGC_NO_STREAM"))
+      unm1->ng != 1 || un->esz != 8 || unp1->esz != 8 || unm1->esz != 8 || getenv("SGC_NO_STREAM"))
     return 1;
   const FabGeom& g = un->geom[0];
   if (memcmp(g.n, unp1->geom[0].n, sizeof g.n) != 0 || memcmp(g.n, unm1->geom[0].n, sizeof g.n) != 0 || !unp1->uniform ||
@@ -548,6 +549,7 @@ int launch_wave_stream(sgc_level_s* unp1, sgc_level_s* un, sgc_level_s* unm1, do
 // does a streaming instance exist for this pair of levels?
 bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u) {
   if (!u->uniform || !unew->uniform || u->ncomp != 1 || unew->ncomp != 1 || u->ng != 1 || unew->ng != 1) return false;
+  if (u->esz != 8 || unew->esz != 8) return false;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0 || getenv("SGC_NO_STREAM")) return false;
   const int vx = g.vn[0], vy = g.vn[1], n2 = g.n[2];

@@ -42,6 +42,14 @@ def test_reference_device_tests_against_facade(name):
 
 
 @pytest.mark.gpu
+def test_reference_vlaloops_address_identities_against_facade():
+    """application/vlaloops/vlaloops.cpp, compiled unmodified: &vla[MD_IX(i, 0)] == &fab(IntVect(i0,i1,i2), 0) for
+    the plain VLA view, the offset-subtracted view and the MD_ARRAY / MD_BOXLOOP macros (asserts live)."""
+    r = _run("ref_vlaloops")
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
 def test_laplacian_driver_facade():
     for n in ("64", "128"):                       # as shipped / BASELINE config 1
         r = _run("laplacian", n, "16")

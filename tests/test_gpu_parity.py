@@ -635,6 +635,108 @@ def test_single_sweep_leaves_ghosts_and_input_untouched(g, oracle):
         assert np.array_equal(got[s], want[s] if 2 <= k < 5 else v[s])
 
 
+def test_single_precision_and_multicomponent_sweeps(g, oracle):
+    """Real = float (the reference's USE_SINGLE_PRECISION build, Parameters.H:17-23,197): nstep x {exchange; sweep}
+    on float levels against the reference library itself compiled that way (oracle/_ref/libsgcref_sp*.so),
+    both FMA modes; and multi-component levels: every component is swept (double, against the oracle per
+    component)."""
+    import pyoracle
+    rng = np.random.default_rng(41)
+    for variant, flags in (("_sp", g.SGC_FMA), ("_sp_nofma", 0)):
+        if not pyoracle.have_reference(variant):
+            pytest.skip("oracle/_ref/libsgcref%s.so not built" % variant)
+        R = pyoracle.Reference(variant)
+        for (dlo, dhi, mb, per, f, nstep) in (((0, 0, 0), (23, 15, 15), (8, 8, 8), 7, 0.2, 6),
+                                              ((0, 0, 0), (127, 63, 63), (64, 64, 64), 3, 1.0 / 6.0, 5),
+                                              ((0, 0, 0), (11, 9, 8), (6, 5, 3), 0, 0.31, 4)):
+            dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
+            a, b = g.LevelData(dbl, 1, 1, dtype=np.float32), g.LevelData(dbl, 1, 1, dtype=np.float32)
+            u0 = rng.standard_normal(a.elems).astype(np.float32)
+            a.upload(u0); b.upload(u0)
+            cp = g.Copier().defineExchangeLD(a, per, 0)
+            res = g.heat_run(a, b, cp, f, nstep, flags)
+            want = u0.copy()
+            R.level_heat(dlo, dhi, mb, 1, per, 0, np.float32(f), nstep, want)
+            got = res.download()
+            assert got.dtype == np.float32 and np.array_equal(got, want), (variant, mb)
+    # double and float levels do not mix
+    dbl = g.DisjointBoxLayout(g.Box((0, 0, 0), (7, 7, 7)), 4)
+    with pytest.raises(g.SgcError):
+        g.heat_sweep(g.LevelData(dbl, 1, 1), g.LevelData(dbl, 1, 1, dtype=np.float32), 0.1)
+    # three components, double: each is an independent field
+    dlo, dhi, mb = (0, 0, 0), (15, 11, 7), (8, 4, 4)
+    dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
+    a, b = g.LevelData(dbl, 3, 1), g.LevelData(dbl, 3, 1)
+    u, v = rng.standard_normal(a.elems), rng.standard_normal(a.elems)
+    a.upload(u); b.upload(v)
+    g.heat_sweep(b, a, 0.2)
+    got = b.download()
+    n = [int(np.prod(bx[3:] - bx[:3] + 3)) for bx in dbl.boxes]
+    for c in range(3):
+        uc = np.concatenate([u[a.fab_offset(k) + c * n[k]:a.fab_offset(k) + (c + 1) * n[k]] for k in range(a.size())])
+        vc = np.concatenate([v[a.fab_offset(k) + c * n[k]:a.fab_offset(k) + (c + 1) * n[k]] for k in range(a.size())])
+        gc = np.concatenate([got[a.fab_offset(k) + c * n[k]:a.fab_offset(k) + (c + 1) * n[k]] for k in range(a.size())])
+        oracle.level_heat_sweep(dbl.boxes, 1, uc, vc, 0.2, 1)
+        assert np.array_equal(gc, vc), c
+
+
+def test_reference_device_kats_gpuSandbox(g):
+    """The reference's device-side known-answer tests restated through this library (gpuSandbox.cpp:66-151;
+    its own kernels live in the application's sandbox_Cuda.cu on CudaFab / SlabFab): fab on grow((-1..2)^3, 1)
+    with 2 components — test 3 set every value, tests 4/5 set the core cells only, test 6 the two-component
+    3-point z stencil B = A[-e_z] + A + A[+e_z] on the core box, everything else of B untouched."""
+    core_lo, core_hi = (-1, -1, -1), (2, 2, 2)
+    A = g.LevelData(None, 2, 1, boxes=[list(core_lo) + list(core_hi)])
+    n = 6
+    # test 3: all values of comp 0 / 1
+    A.setVal(-1.0, comp=0); A.setVal(-2.0, comp=1)
+    f = A.download().reshape(2, n, n, n)
+    assert (f[0] == -1.0).all() and (f[1] == -2.0).all()
+    # tests 4 and 5: core cells only (BaseFab::copy(box, src) from a constant fab, BaseFab.cpp:254-271)
+    for vals in ((1.0, 2.0), (3.0, 4.0)):
+        K = g.LevelData(None, 2, 1, boxes=[list(core_lo) + list(core_hi)])
+        K.setVal(vals[0], comp=0); K.setVal(vals[1], comp=1)
+        A.copy(0, core_lo, core_hi, 0, K, 0, core_lo, core_hi, 0, 2)
+        f = A.download().reshape(2, n, n, n)
+        core = np.zeros((n, n, n), bool); core[1:-1, 1:-1, 1:-1] = True
+        assert (f[0][core] == vals[0]).all() and (f[1][core] == vals[1]).all()
+        assert (f[0][~core] == -1.0).all() and (f[1][~core] == -2.0).all()
+    # test 6: A[c0] = i0, A[c1] = i0 + 1 on the ghost box, B preset to 1.234567E89
+    i0 = np.arange(-2, 4, dtype=np.float64)[None, None, :] + np.zeros((n, n, n))
+    hostA = np.stack([i0, i0 + 1.0])
+    A.upload(hostA.ravel())
+    B = g.LevelData(None, 2, 1, boxes=[list(core_lo) + list(core_hi)])
+    B.setVal(1.234567e89)
+    g.stencil7_apply(B, A, (1, 0, 0, 0, 0, 1, 1))
+    fb = B.download().reshape(2, n, n, n)
+    for c in range(2):
+        want = hostA[c][:-2, 1:-1, 1:-1] + hostA[c][1:-1, 1:-1, 1:-1] + hostA[c][2:, 1:-1, 1:-1]
+        assert np.array_equal(fb[c][1:-1, 1:-1, 1:-1], want)
+        ghost = np.ones((n, n, n), bool); ghost[1:-1, 1:-1, 1:-1] = False
+        assert (fb[c][ghost] == 1.234567e89).all()
+    # and a general weighted stencil on random data, double and float, without contraction (numpy has no fma)
+    rng = np.random.default_rng(43)
+    w = rng.standard_normal(7)
+    for dt in (np.float64, np.float32):
+        dbl = g.DisjointBoxLayout(g.Box((0, 0, 0), (9, 7, 5)), (5, 4, 3))
+        a, b = g.LevelData(dbl, 2, 1, dtype=dt), g.LevelData(dbl, 2, 1, dtype=dt)
+        u = rng.standard_normal(a.elems).astype(dt)
+        a.upload(u); b.setVal(0.0)
+        g.stencil7_apply(b, a, w, flags=0)
+        got = b.download()
+        wt = w.astype(dt)
+        for k, bx in enumerate(dbl.boxes):
+            m = bx[3:] - bx[:3] + 3
+            fu = u[a.fab_offset(k):a.fab_offset(k) + a.fab_elems(k)].reshape(2, m[2], m[1], m[0])
+            fg = got[a.fab_offset(k):a.fab_offset(k) + a.fab_elems(k)].reshape(2, m[2], m[1], m[0])
+            c = fu[:, 1:-1, 1:-1, 1:-1]
+            r = wt[0] * c
+            for wk, nb in zip(wt[1:], (fu[:, 1:-1, 1:-1, :-2], fu[:, 1:-1, 1:-1, 2:], fu[:, 1:-1, :-2, 1:-1],
+                                        fu[:, 1:-1, 2:, 1:-1], fu[:, :-2, 1:-1, 1:-1], fu[:, 2:, 1:-1, 1:-1])):
+                r = r + wk * nb
+            assert r.dtype == dt and np.array_equal(fg[:, 1:-1, 1:-1, 1:-1], r), dt
+
+
 def test_laplacian_driver_C1(g, golden, oracle):
     # application/laplacian/laplacian.cpp: A on (1..n)^3, B on (2..n-1)^3, 16 iterations
     meta, arr = golden
