@@ -205,6 +205,11 @@ int sgc_level_download_async(sgc_level_t level, void* host, sgc_stream_t stream,
 long long sgc_level_valid_elems(sgc_level_t level);
 int sgc_level_download_valid(sgc_level_t level, void* host);
 int sgc_level_download_valid_async(sgc_level_t level, void* host, sgc_stream_t stream, sgc_event_t gathered);
+/* The reverse: the valid cells of every fab from a dense buffer [box][comp][k][j][i]; ghost cells keep their
+ * contents (the next exchange / BC fill writes them).  Moves (n/(n+2g))^3 of the bytes of the whole-fab
+ * copyToDevice (BaseFab.cpp:427-483, LevelData.H:711-765).                                              */
+int sgc_level_upload_valid(sgc_level_t level, const void* host);
+int sgc_level_upload_valid_async(sgc_level_t level, const void* host, sgc_stream_t stream);
 /* LevelData::setVal / BaseFab::setVal (LevelData.H:352-383, BaseFab.cpp:219-246);
  * comp = -1: all components.  `value` points at one element of elem_bytes bytes.           */
 int sgc_level_setval(sgc_level_t level, int box, int comp, const void* value);

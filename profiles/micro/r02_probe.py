@@ -90,3 +90,26 @@ if __name__ == "__main__":
         res["rebox_32"] = rebox_probe(512, 32)
         res["rebox_8"] = rebox_probe(256, 8)
     print(json.dumps(res, indent=1))
+
+
+def float_probe(n=512, box=64):
+    """one-step sweep on float levels (streaming float instance) against the double one"""
+    out = {}
+    for tag, dt in (("f64", np.float64), ("f32", np.float32)):
+        dbl = sgc.DisjointBoxLayout(sgc.Box((0, 0, 0), (n - 1,) * 3), box)
+        a, b = sgc.LevelData(dbl, 1, 1, dtype=dt), sgc.LevelData(dbl, 1, 1, dtype=dt)
+        u = np.random.default_rng(1).standard_normal(a.elems).astype(dt)
+        a.upload(u)
+        b.upload(u)
+
+        def two():
+            sgc.heat_sweep(b, a, 0.125)
+            sgc.heat_sweep(a, b, 0.125)
+        two()
+        t = timed(two, 10) / 2
+        out[tag] = {"sweep_ms": t, "gcells": n ** 3 / (t * 1e-3) / 1e9, "algorithmic_GBs": 2 * np.dtype(dt).itemsize * n ** 3 / (t * 1e-3) / 1e9}
+    return out
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "float":
+    print(json.dumps({"float_C2": float_probe(512, 64), "float_32": float_probe(512, 32)}, indent=1))

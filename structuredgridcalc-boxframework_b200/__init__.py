@@ -34,7 +34,7 @@ SYMBOLS = [
     "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
     "sgc_level_upload_async", "sgc_level_download_async", "sgc_copyset_create", "sgc_copyset_run", "sgc_copyset_destroy",
     "sgc_copyset_num_cells", "sgc_level_valid_elems", "sgc_level_download_valid", "sgc_level_download_valid_async", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run", "sgc_lb_selftest_divconst",
-    "sgc_level_edge_strips", "sgc_plan_rebox_factors", "sgc_plan_create_exchange_ex", "sgc_plan_matches_level", "sgc_stencil7_apply",
+    "sgc_level_edge_strips", "sgc_plan_rebox_factors", "sgc_plan_create_exchange_ex", "sgc_plan_matches_level", "sgc_stencil7_apply", "sgc_level_upload_valid", "sgc_level_upload_valid_async",
 ]
 
 
@@ -147,6 +147,8 @@ def lib():
     L.sgc_level_valid_elems.argtypes = [C.c_void_p]
     L.sgc_level_valid_elems.restype = C.c_longlong
     L.sgc_level_download_valid.argtypes = [C.c_void_p, C.c_void_p]
+    L.sgc_level_upload_valid.argtypes = [C.c_void_p, C.c_void_p]
+    L.sgc_level_upload_valid_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sgc_level_download_valid_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sgc_copyset_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
     L.sgc_copyset_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -436,6 +438,19 @@ class LevelData:
             out = np.empty(self.validElems(), self.dtype)
         check(lib().sgc_level_download_valid(self.h, out.ctypes.data))
         return out
+
+    def uploadValid(self, host, stream=None):
+        """valid cells only, dense [box][comp][k][j][i]; ghost cells keep their contents.  With `stream`, `host` is a
+        PinnedBuffer and the copy runs on that transfer stream."""
+        if stream is not None:
+            assert host.array.size == self.validElems()
+            check(lib().sgc_level_upload_valid_async(self.h, host.ptr, stream.h))
+            return self
+        host = np.ascontiguousarray(host, self.dtype)
+        assert host.size == self.validElems()
+        check(lib().sgc_level_upload_valid(self.h, host.ctypes.data))
+        sync()
+        return self
 
     def edgeStrips(self):
         """-1 none, 0 stale, 1 outer columns current, 2 all four (sgc_level_edge_strips)"""

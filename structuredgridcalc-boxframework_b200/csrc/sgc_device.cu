@@ -17,13 +17,13 @@ Runtime& rt() {
 
 // kernels / launchers (sgc_kernels.cu, sgc_stream.cu)
 int launch_heat_generic(const int*, int, int, int ncomp, int esz, const FabGeom*, const FabGeom*, const void*, void*, double, int,
-                        cudaStream_t);
+                        int tile_z, cudaStream_t);
 int launch_lap_generic(const int*, int, int, int ncomp, int esz, const FabGeom*, const FabGeom*, const void*, void*, double, int, int,
-                       cudaStream_t);
+                       int tile_z, cudaStream_t);
 int launch_wave_generic(const int*, int, int, int ncomp, int esz, const FabGeom*, const FabGeom*, const void*, void*, const void*,
-                        double, int, cudaStream_t);
+                        double, int, int tile_z, cudaStream_t);
 int launch_weight_generic(const int*, int, int, int ncomp, int esz, const FabGeom*, const FabGeom*, const void*, void*,
-                          const double w[7], int, cudaStream_t);
+                          const double w[7], int, int tile_z, cudaStream_t);
 int sweep_tile_y();
 int sweep_tile_z();
 // streaming sweep (returns 1 when it does not apply to this geometry, 0 when launched, <0 on error)
@@ -488,7 +488,15 @@ int sgc_level_create(const int* boxes6, int nbox, int ncomp, int nghost, int ele
   // sweep work table for the generic kernel: (box, y0, z0) tiles of the valid region
   std::vector<int> work;
   l->work_begin.resize(nbox + 1);
-  const int ty = sweep_tile_y(), tz = sweep_tile_z();
+  // z extent of a work tile: 16 planes, halved while the level would give the table-driven kernel fewer than four
+  // CTAs per SM (the reference driver's single 128^3 box: 256 tiles of 16 planes leave 40 SMs half idle)
+  const int ty = sweep_tile_y();
+  int tz = sweep_tile_z();
+  {
+    auto count = [&](int z) { long long n = 0; for (int b = 0; b < nbox; ++b) n += (long long)((l->geom[b].vn[2] + z - 1) / z) * ((l->geom[b].vn[1] + ty - 1) / ty); return n * ncomp; };
+    while (tz > 2 && count(tz) < 4LL * rt().sm_count) tz /= 2;
+  }
+  l->tile_z = tz;
   for (int b = 0; b < nbox; ++b) {
     l->work_begin[b] = (int)(work.size() / 3);
     for (int z = 0; z < l->geom[b].vn[2]; z += tz)
@@ -513,6 +521,7 @@ int sgc_level_destroy(sgc_level_t l) {
   l->conv_in.release();
   l->conv_out.release();
   l->conv_valid.release();
+  l->conv_valid_in.release();
   // an arena other GPUs may still have mapped is freed at the next point every rank passes (sgc_comm_finalize)
   if (l->d_base) { if (l->exported && rt().ready) rt().deferred_free.push_back(l->d_base); else cudaFree(l->d_base); }
   if (l->d_geom) cudaFree(l->d_geom);
@@ -687,15 +696,44 @@ long long sgc_level_valid_elems(sgc_level_t l) {
 
 static int ensure_valid_table(sgc_level_s* l) {
   if (l->conv_valid.d_items || l->nbox == 0) return 0;
-  std::vector<CopyItem> v;
+  std::vector<CopyItem> v, w;
   long long off = 0;
   for (int b = 0; b < l->nbox; ++b) {
     const IBox& vb = l->boxes[b];
     make_items(v, dense_geom(vb, off), vb, 0, l->geom[b], vb, 0, l->ncomp, ~0u);
+    make_items(w, l->geom[b], vb, 0, dense_geom(vb, off), vb, 0, l->ncomp, ~0u);
     off += vb.size() * l->ncomp;
   }
   l->valid_elems = off;
-  return l->conv_valid.upload(v, l->esz);
+  const int st = l->conv_valid.upload(v, l->esz);
+  return st ? st : l->conv_valid_in.upload(w, l->esz);
+}
+
+// The reverse of the plot gather: the valid cells of every fab from a dense host buffer [box][comp][k][j][i];
+// ghost cells keep their contents (the next exchange / BC fill writes them).  9-27 % fewer bytes over PCIe than
+// the whole-fab copyToDevice of BaseFab.cpp:427-483 (66^3 -> 64^3: 8.8 %; 18^3 -> 16^3: 30 %).
+int sgc_level_upload_valid(sgc_level_t l, const void* host) {
+  SGC_REQUIRE_RT();
+  if (!l || !host) return fail(SGC_ERR_ARG, "sgc_level_upload_valid: bad argument");
+  const size_t bytes = (size_t)sgc_level_valid_elems(l) * l->esz;
+  int st = ensure_valid_table(l);
+  if (!st) st = ensure_stage(bytes);
+  if (st) return st;
+  SGC_CUDA(cudaMemcpyAsync(rt().d_stage, host, bytes, cudaMemcpyHostToDevice, rt().compute));
+  level_written(l);
+  return launch_copy(l->conv_valid_in, l->d_arena, rt().d_stage, l->esz, rt().compute);
+}
+
+int sgc_level_upload_valid_async(sgc_level_t l, const void* host, sgc_stream_t x) {
+  SGC_REQUIRE_RT();
+  if (!l || !host || !x) return fail(SGC_ERR_ARG, "sgc_level_upload_valid_async: bad argument");
+  const size_t bytes = (size_t)sgc_level_valid_elems(l) * l->esz;
+  int st = ensure_valid_table(l);
+  if (!st) st = stream_stage(x, bytes);
+  if (st) return st;
+  SGC_CUDA(cudaMemcpyAsync(x->d_stage, host, bytes, cudaMemcpyHostToDevice, x->s));
+  level_written(l);
+  return launch_copy(l->conv_valid_in, l->d_arena, x->d_stage, l->esz, x->s);
 }
 
 int sgc_level_download_valid(sgc_level_t l, void* host) {
@@ -1165,7 +1203,7 @@ int sgc_heat_sweep_range(sgc_level_t unew, sgc_level_t u, double f, unsigned fla
   const int w0 = unew->work_begin[box_begin], w1 = unew->work_begin[box_end];
   level_written(unew);
   return launch_heat_generic(unew->d_work, w0, w1 - w0, unew->ncomp, unew->esz, u->d_geom, unew->d_geom, u->d_arena,
-                             unew->d_arena, f, fma, rt().compute);
+                             unew->d_arena, f, fma, unew->tile_z, rt().compute);
 }
 
 int sgc_heat_sweep(sgc_level_t unew, sgc_level_t u, double f, unsigned flags) {
@@ -1184,7 +1222,7 @@ int sgc_laplacian_apply(sgc_level_t B, sgc_level_t A, double coef, int niter, in
   level_written(B);
   for (int i = 0; i < launches && !st; ++i)
     st = launch_lap_generic(B->d_work, 0, B->nwork, B->ncomp, B->esz, A->d_geom, B->d_geom, A->d_arena,
-                            B->d_arena, coef, (flags & SGC_FMA) ? 1 : 0, per, rt().compute);
+                            B->d_arena, coef, (flags & SGC_FMA) ? 1 : 0, per, B->tile_z, rt().compute);
   return st;
 }
 
@@ -1201,7 +1239,7 @@ int sgc_wave_step(sgc_level_t unp1, sgc_level_t un, sgc_level_t unm1, double fac
   st = launch_wave_stream(unp1, un, unm1, factor, wf, rt().compute);
   if (st <= 0) return st;
   return launch_wave_generic(unp1->d_work, 0, unp1->nwork, unp1->ncomp, unp1->esz, un->d_geom, unp1->d_geom, un->d_arena,
-                             unp1->d_arena, unm1->d_arena, factor, wf, rt().compute);
+                             unp1->d_arena, unm1->d_arena, factor, wf, unp1->tile_z, rt().compute);
 }
 
 int sgc_stencil7_apply(sgc_level_t out, sgc_level_t in, const double weights[7], unsigned flags) {
@@ -1212,7 +1250,7 @@ int sgc_stencil7_apply(sgc_level_t out, sgc_level_t in, const double weights[7],
   ProfScope prof(0, rt().compute);
   level_written(out);
   return launch_weight_generic(out->d_work, 0, out->nwork, out->ncomp, out->esz, in->d_geom, out->d_geom, in->d_arena,
-                               out->d_arena, weights, (flags & SGC_FMA) ? 1 : 0, rt().compute);
+                               out->d_arena, weights, (flags & SGC_FMA) ? 1 : 0, out->tile_z, rt().compute);
 }
 
 int sgc_heat_sweep_ranges(sgc_level_t nxt, sgc_level_t cur, double f, unsigned flags, int a0, int a1, int b0, int b1) {

@@ -230,6 +230,7 @@ struct sgc_level_s {
   unsigned long long generation = 0;    // unique per created level (peer-memory sessions are keyed on it)
   sgc::CopyTable conv_in, conv_out;     // reference-order staging <-> split-x arena, whole level
   sgc::CopyTable conv_valid;            // arena -> [box][comp] valid cells only (plot output), built on first use
+  sgc::CopyTable conv_valid_in;         // the reverse: dense valid cells -> arena (ghost cells untouched)
   long long valid_elems = 0;
   sgc::FabGeom* d_geom = nullptr;
   std::vector<sgc::FabGeom> geom;
@@ -237,6 +238,7 @@ struct sgc_level_s {
   // sweep work table (box, y0, z0) for the generic kernel, built at creation
   int* d_work = nullptr;
   int nwork = 0;
+  int tile_z = 16;                      // planes per work tile
   std::vector<int> work_begin;          // first work item of box b (nbox+1 entries)
   // scratch device buffer for linearOut/In
   void* d_scratch = nullptr;

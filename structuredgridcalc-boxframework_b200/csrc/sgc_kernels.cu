@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "sgc_device.h"
+#include "sgc_pipe.cuh"
 
 namespace sgc {
 
@@ -249,23 +250,6 @@ int launch_fill(void* p, long long n, int esz, const void* value, cudaStream_t s
 // ---------------------------------------------------------------------------------------------
 constexpr int kTileX = 64, kTileY = 4, kTileZ = 16;
 
-// Correctly rounded arithmetic of the element type, spelled out so that nvcc can neither contract nor
-// re-associate: double (the reference's default Real) and float (its USE_SINGLE_PRECISION build,
-// Parameters.H:17-23,197).
-template <typename T> struct Ar;
-template <> struct Ar<double> {
-  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
-};
-template <> struct Ar<float> {
-  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-};
-
 // second difference in the reference's association: (u[+e] - 2u) + u[-e]; 2u is exact.
 template <typename T>
 __device__ __forceinline__ T d2(T p, T c, T m) {
@@ -334,13 +318,13 @@ struct WeightOp {
 template <typename T, class Op, int AUX>
 __global__ void __launch_bounds__(kTileX * kTileY)
 k_sweep7(const int* __restrict__ work, const FabGeom* __restrict__ gin, const FabGeom* __restrict__ gout,
-         const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ aux, Op op) {
+         const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ aux, Op op, int tile_z) {
   const int b = work[3 * blockIdx.x], y0 = work[3 * blockIdx.x + 1], z0 = work[3 * blockIdx.x + 2];
   const int comp = blockIdx.y;
   const FabGeom GI = gin[b], GO = gout[b];
   const int y = y0 + threadIdx.y;
   if (y >= GO.vn[1]) return;
-  const int zend = min(z0 + kTileZ, GO.vn[2]);
+  const int zend = min(z0 + tile_z, GO.vn[2]);
   // fab-relative coordinates of valid cell (0, y, z0) of this box in the in / out fabs
   const int ix0 = GO.vlo[0] - GI.lo[0], iy = GO.vlo[1] + y - GI.lo[1], iz0 = GO.vlo[2] + z0 - GI.lo[2];
   const int ox0 = GO.vlo[0] - GO.lo[0], oy = GO.vlo[1] + y - GO.lo[1], oz0 = GO.vlo[2] + z0 - GO.lo[2];
@@ -373,10 +357,10 @@ k_sweep7(const int* __restrict__ work, const FabGeom* __restrict__ gin, const Fa
 
 template <typename T, class Op, int AUX>
 static int launch_sweep(const int* d_work, int w0, int nwork, int ncomp, const FabGeom* gin, const FabGeom* gout,
-                        const void* in, void* out, const void* aux, Op op, cudaStream_t s) {
+                        const void* in, void* out, const void* aux, Op op, int tile_z, cudaStream_t s) {
   if (nwork <= 0) return 0;
   k_sweep7<T, Op, AUX><<<dim3(nwork, ncomp), dim3(kTileX, kTileY), 0, s>>>(d_work + 3 * (size_t)w0, gin, gout, (const T*)in,
-                                                                           (T*)out, (const T*)aux, op);
+                                                                           (T*)out, (const T*)aux, op, tile_z);
   rt().launches++;
   SGC_CUDA(cudaGetLastError());
   return 0;
@@ -384,32 +368,32 @@ static int launch_sweep(const int* d_work, int w0, int nwork, int ncomp, const F
 
 // esz 8: double, 4: float.  Every component of the levels is swept.
 int launch_heat_generic(const int* d_work, int w0, int nwork, int ncomp, int esz, const FabGeom* gin, const FabGeom* gout,
-                        const void* in, void* out, double f, int fma, cudaStream_t s) {
-  if (esz == 4) return launch_sweep<float, HeatOp<float>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, HeatOp<float>{(float)f, fma}, s);
-  return launch_sweep<double, HeatOp<double>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, HeatOp<double>{f, fma}, s);
+                        const void* in, void* out, double f, int fma, int tile_z, cudaStream_t s) {
+  if (esz == 4) return launch_sweep<float, HeatOp<float>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, HeatOp<float>{(float)f, fma}, tile_z, s);
+  return launch_sweep<double, HeatOp<double>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, HeatOp<double>{f, fma}, tile_z, s);
 }
 int launch_lap_generic(const int* d_work, int w0, int nwork, int ncomp, int esz, const FabGeom* gin, const FabGeom* gout,
-                       const void* in, void* out, double coef, int fma, int niter, cudaStream_t s) {
-  if (esz == 4) return launch_sweep<float, LapOp<float>, 1>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, LapOp<float>{(float)coef, fma, niter}, s);
-  return launch_sweep<double, LapOp<double>, 1>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, LapOp<double>{coef, fma, niter}, s);
+                       const void* in, void* out, double coef, int fma, int niter, int tile_z, cudaStream_t s) {
+  if (esz == 4) return launch_sweep<float, LapOp<float>, 1>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, LapOp<float>{(float)coef, fma, niter}, tile_z, s);
+  return launch_sweep<double, LapOp<double>, 1>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, LapOp<double>{coef, fma, niter}, tile_z, s);
 }
 int launch_wave_generic(const int* d_work, int w0, int nwork, int ncomp, int esz, const FabGeom* gin, const FabGeom* gout,
-                        const void* in, void* out, const void* um1, double f, int fma, cudaStream_t s) {
-  if (esz == 4) return launch_sweep<float, WaveOp<float>, 2>(d_work, w0, nwork, ncomp, gin, gout, in, out, um1, WaveOp<float>{(float)f, fma}, s);
-  return launch_sweep<double, WaveOp<double>, 2>(d_work, w0, nwork, ncomp, gin, gout, in, out, um1, WaveOp<double>{f, fma}, s);
+                        const void* in, void* out, const void* um1, double f, int fma, int tile_z, cudaStream_t s) {
+  if (esz == 4) return launch_sweep<float, WaveOp<float>, 2>(d_work, w0, nwork, ncomp, gin, gout, in, out, um1, WaveOp<float>{(float)f, fma}, tile_z, s);
+  return launch_sweep<double, WaveOp<double>, 2>(d_work, w0, nwork, ncomp, gin, gout, in, out, um1, WaveOp<double>{f, fma}, tile_z, s);
 }
 int launch_weight_generic(const int* d_work, int w0, int nwork, int ncomp, int esz, const FabGeom* gin, const FabGeom* gout,
-                          const void* in, void* out, const double w[7], int fma, cudaStream_t s) {
+                          const void* in, void* out, const double w[7], int fma, int tile_z, cudaStream_t s) {
   if (esz == 4) {
     WeightOp<float> op;
     for (int k = 0; k < 7; ++k) op.w[k] = (float)w[k];
     op.fma = fma;
-    return launch_sweep<float, WeightOp<float>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, op, s);
+    return launch_sweep<float, WeightOp<float>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, op, tile_z, s);
   }
   WeightOp<double> op;
   for (int k = 0; k < 7; ++k) op.w[k] = w[k];
   op.fma = fma;
-  return launch_sweep<double, WeightOp<double>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, op, s);
+  return launch_sweep<double, WeightOp<double>, 0>(d_work, w0, nwork, ncomp, gin, gout, in, out, nullptr, op, tile_z, s);
 }
 
 int sweep_tile_y() { return kTileY; }

@@ -47,8 +47,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// Correctly rounded arithmetic of the element type, spelled out so that nvcc can neither contract nor
+// re-associate: double (the reference's default Real) and float (its USE_SINGLE_PRECISION build,
+// Parameters.H:17-23,197).
+template <typename T> struct Ar;
+template <> struct Ar<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+};
+template <> struct Ar<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+};
+
 __device__ __forceinline__ double sd2(double p, double twoc, double m) {   // (p - 2c) + m
   return __dadd_rn(__dsub_rn(p, twoc), m);
+}
+__device__ __forceinline__ float sd2(float p, float twoc, float m) {
+  return __fadd_rn(__fsub_rn(p, twoc), m);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

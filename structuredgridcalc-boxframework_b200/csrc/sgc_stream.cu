@@ -42,12 +42,12 @@ constexpr int kGatherWarps = 4;   // helper warps of the narrow-box fused mode (
 
 // Narrow-box instances have few consumer warps per CTA (one or four columns per thread): when the ring
 // is small enough two CTAs share an SM, which doubles the warps that hide shared-memory / FP64 latency.
-__host__ __device__ constexpr size_t stream_smem_bytes(int vnx, int vny, int ng, int ps, int ns, int op) {
-  return (size_t)ns * ps * ((size_t)vnx * (vny + 2 * ng) + 2 * ng * (vny + 2 * ng) + (op == 1 ? (size_t)vnx * vny : 0)) * 8 +
+__host__ __device__ constexpr size_t stream_smem_bytes(int vnx, int vny, int ng, int ps, int ns, int op, int esz = 8) {
+  return (size_t)ns * ps * ((size_t)vnx * (vny + 2 * ng) + 2 * ng * (vny + 2 * ng) + (op == 1 ? (size_t)vnx * vny : 0)) * esz +
          2 * (size_t)ns * 8;
 }
-__host__ __device__ constexpr int stream_ctas_per_sm(int vnx, int vny, int ng, int ps, int ns, int op) {
-  const size_t per_cta = stream_smem_bytes(vnx, vny, ng, ps, ns, op) + 1024;     // + the per-CTA reservation
+__host__ __device__ constexpr int stream_ctas_per_sm(int vnx, int vny, int ng, int ps, int ns, int op, int esz = 8) {
+  const size_t per_cta = stream_smem_bytes(vnx, vny, ng, ps, ns, op, esz) + 1024;     // + the per-CTA reservation
   return per_cta <= 74 * 1024 ? 3 : (per_cta <= 112 * 1024 ? 2 : 1);
 }
 
@@ -86,12 +86,20 @@ __host__ __device__ constexpr int stream_ctas_per_sm(int vnx, int vny, int ng, i
 // `full` barrier next to the TMA transaction count.  With
 // 16^3 boxes a CTA walks the boxes of an x row back to back, so those lines are in L2 (they were, or
 // are about to be, streamed by the same CTA) and cost no extra DRAM traffic.
+// T: double, or float (the reference's USE_SINGLE_PRECISION Real; plain sweep only: the fused ghost fill, the
+// peer-memory halo and the edge strips are double-only).
 template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0,
-          bool GATHER = false>
-__global__ void __launch_bounds__((NCW + 1 + (GATHER ? kGatherWarps : 0)) * 32, stream_ctas_per_sm(VNX, VNY, NG, PS, NS, OP))
-k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_xg, double* __restrict__ out_main,
-              int nstages, int n2, double f, int fma, int seam, int jump, PushArgs push,
-              const double* __restrict__ aux_main) {
+          bool GATHER = false, typename T = double>
+__global__ void __launch_bounds__((NCW + 1 + (GATHER ? kGatherWarps : 0)) * 32, stream_ctas_per_sm(VNX, VNY, NG, PS, NS, OP, (int)sizeof(T)))
+k_heat_stream(const T* __restrict__ in_main, const T* __restrict__ in_xg, T* __restrict__ out_main,
+              int nstages, int n2, double f_, int fma, int seam, int jump, PushArgs push,
+              const T* __restrict__ aux_main) {
+  static_assert(sizeof(T) == 8 || (!PUSH && !GATHER && OP == 0 && MODE == 0), "float: the plain heat sweep only");
+  constexpr uint32_t ESZ = (uint32_t)sizeof(T);
+  const T f = (T)f_;
+  // the level-wide pointers of the fused modes, in the element type (never dereferenced when T is float)
+  const T* const lvl_in = reinterpret_cast<const T*>(push.in_level);
+  T* const lvl_out = reinterpret_cast<T*>(push.out_level);
   // The launch covers the box range as a virtual stage sequence [0, nstages); stages >= seam live
   // `jump` stages further on in memory (a second box range, e.g. the two boundary box layers of a
   // z-slab).  Both ranges start and end on fab boundaries, so the seam sits between two ghost planes.
@@ -102,7 +110,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   constexpr int AUXP = (OP == 1) ? VNX * VNY : 0;   // elements of the third level carried per plane (valid rows)
   constexpr int STAGE = PS * (PLANE + 2 * STRIP + AUXP);   // ring slot: planes | low strips | high strips | aux rows
   constexpr int AUX_OFF = PS * (PLANE + 2 * STRIP);
-  constexpr uint32_t MAIN_BYTES = PS * PLANE * 8u, STRIP_BYTES = PS * STRIP * 8u, AUX_BYTES = PS * AUXP * 8u;
+  constexpr uint32_t MAIN_BYTES = PS * PLANE * ESZ, STRIP_BYTES = PS * STRIP * ESZ, AUX_BYTES = PS * AUXP * ESZ;
   constexpr int COLS = VNX * VNY;
   constexpr int CPT = (COLS + NT - 1) / NT;      // columns per consumer thread
   static_assert(NG == 1, "one ghost layer");
@@ -111,8 +119,8 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   static_assert(NS >= 3, "two stages are being read while at least one is in flight");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* ring = reinterpret_cast<double*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE * 8);
+  T* ring = reinterpret_cast<T*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE * ESZ);
   uint64_t* empty = full + NS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -142,13 +150,13 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
       bool waited[2] = {false, false};
       // where ghost plane kz of box b comes from: the z neighbour's last (low side) / first (high side)
       // valid plane — a local fab, a fab in the neighbouring GPU's memory, or (no neighbour) the own ghosts
-      auto zsource = [&](int b, int kz) -> const double* {
+      auto zsource = [&](int b, int kz) -> const T* {
         const long long fabm = (long long)PLANE * n2;
         const int vnz_ = n2 - 2 * NG;
         const bool low = kz < NG;
         const int dl = low ? dzm : dzp, rr = low ? rzm : rzp;
         const long long skz = low ? kz + vnz_ : kz - vnz_;
-        if (dl >= 0) return push.in_level + dl * fabm + skz * PLANE;
+        if (dl >= 0) return lvl_in + dl * fabm + skz * PLANE;
         if (rr >= 0) {
           const int ps = rr >> 28;
           if (!waited[ps]) {           // the peer must have finished writing the level we read
@@ -157,9 +165,9 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
             asm volatile("fence.proxy.async;" ::: "memory");
             waited[ps] = true;
           }
-          return push.peer_in[ps] + (long long)(rr & 0x0fffffff) * fabm + skz * PLANE;
+          return reinterpret_cast<const T*>(push.peer_in[ps]) + (long long)(rr & 0x0fffffff) * fabm + skz * PLANE;
         }
-        return push.in_level + b * fabm + (long long)kz * PLANE;
+        return lvl_in + b * fabm + (long long)kz * PLANE;
       };
       for (int t = l_begin; t < l_end; ++t, ++tr) {
         if (t == seam && t != l_begin) tr += jump;
@@ -170,8 +178,8 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
           const long long pl = tr * PS;                        // first plane of the stage
           const long long box = pl / n2;
           const int kz0 = (int)(pl - box * n2);
-          double* dst = ring + (size_t)slot * STAGE;
-          const double* xg = in_xg + box * xfab + (long long)kz0 * STRIP;
+          T* dst = ring + (size_t)slot * STAGE;
+          const T* xg = in_xg + box * xfab + (long long)kz0 * STRIP;
           if (GATHER) {
             // planes only: a ghost plane whole (from its z source), an interior plane's valid rows;
             // the gather warp fills the y-ghost rows and the x strips
@@ -186,15 +194,15 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
             const long long fabm = (long long)PLANE * n2;
             uint32_t bytes = 0;
 #pragma unroll
-            for (int p = 0; p < PS; ++p) bytes += (kz0 + p < NG || kz0 + p >= n2 - NG) ? PLANE * 8u : VNY * VNX * 8u;
+            for (int p = 0; p < PS; ++p) bytes += (kz0 + p < NG || kz0 + p >= n2 - NG) ? PLANE * ESZ : VNY * VNX * ESZ;
             mbar_expect_tx(full + slot, bytes);
 #pragma unroll
             for (int p = 0; p < PS; ++p) {
               const int kz = kz0 + p;
-              double* d = dst + p * PLANE;
-              const double* own = push.in_level + b * fabm + (long long)kz * PLANE;
-              if (kz < NG || kz >= n2 - NG) bulk_g2s(d, zsource(b, kz), PLANE * 8u, full + slot);
-              else bulk_g2s(d + NG * VNX, own + NG * VNX, VNY * VNX * 8u, full + slot);
+              T* d = dst + p * PLANE;
+              const T* own = lvl_in + b * fabm + (long long)kz * PLANE;
+              if (kz < NG || kz >= n2 - NG) bulk_g2s(d, zsource(b, kz), PLANE * ESZ, full + slot);
+              else bulk_g2s(d + NG * VNX, own + NG * VNX, VNY * VNX * ESZ, full + slot);
             }
             if (++slot == NS) { slot = 0; ++round; }
             continue;
@@ -206,7 +214,7 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
 #pragma unroll
             for (int p = 0; p < PS; ++p) {
               const long long ap = (pl + p > 0) ? pl + p - 1 : 0;
-              bulk_g2s(dst + AUX_OFF + p * AUXP, aux_main + ap * PLANE + NG * VNX, AUXP * 8u, full + slot);
+              bulk_g2s(dst + AUX_OFF + p * AUXP, aux_main + ap * PLANE + NG * VNX, AUXP * ESZ, full + slot);
             }
           }
           if (!PUSH || !(push.mask & 6)) {
@@ -227,16 +235,16 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
 #pragma unroll
             for (int p = 0; p < PS; ++p) {
               const int kz = kz0 + p;
-              double* d = dst + p * PLANE;
-              const double* own = push.in_level + b * fabm + (long long)kz * PLANE;
+              T* d = dst + p * PLANE;
+              const T* own = lvl_in + b * fabm + (long long)kz * PLANE;
               if (kz < NG || kz >= n2 - NG) {
-                bulk_g2s(d, zsource(b, kz), PLANE * 8u, full + slot);
+                bulk_g2s(d, zsource(b, kz), PLANE * ESZ, full + slot);
               } else if (dym < 0 && dyp < 0) {
-                bulk_g2s(d, own, PLANE * 8u, full + slot);
+                bulk_g2s(d, own, PLANE * ESZ, full + slot);
               } else {
-                constexpr uint32_t YG = NG * VNX * 8u, YV = VNY * VNX * 8u;
-                const double* lo = dym >= 0 ? push.in_level + dym * fabm + (long long)kz * PLANE + VNY * VNX : own;
-                const double* hi = dyp >= 0 ? push.in_level + dyp * fabm + (long long)kz * PLANE + NG * VNX
+                constexpr uint32_t YG = NG * VNX * ESZ, YV = VNY * VNX * ESZ;
+                const T* lo = dym >= 0 ? lvl_in + dym * fabm + (long long)kz * PLANE + VNY * VNX : own;
+                const T* hi = dyp >= 0 ? lvl_in + dyp * fabm + (long long)kz * PLANE + NG * VNX
                                             : own + (VNY + NG) * VNX;
                 bulk_g2s(d, lo, YG, full + slot);                              // ghost rows 0..NG-1
                 bulk_g2s(d + NG * VNX, own + NG * VNX, YV, full + slot);      // valid rows
@@ -276,10 +284,10 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
         const int* __restrict__ nb = push.nbr + (size_t)b * 27;
         dxm = __ldg(nb + 12); dxp = __ldg(nb + 14); dym = __ldg(nb + 10); dyp = __ldg(nb + 16);
       }
-      double* dst = ring + (size_t)slot * STAGE;
-      const double* ownmain = push.in_level + b * fabm;
-      const double* ownxg = push.in_level + push.xg_base + b * xfab;
-      double vx[IX], vy[IY];
+      T* dst = ring + (size_t)slot * STAGE;
+      const T* ownmain = lvl_in + b * fabm;
+      const T* ownxg = lvl_in + push.xg_base + b * xfab;
+      T vx[IX], vy[IY];
       int ox[IX], oy[IY];                          // destination offsets in the slot, -1 = nothing to do
 #pragma unroll
       for (int it = 0; it < IX; ++it) {
@@ -288,10 +296,10 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
         const int kz = kz0 + p;
         const bool live = idx < NXH && kz >= NG && kz < n2 - NG;   // edge ghosts are not needed by the stencil
         const int D = side ? dxp : dxm;
-        const double* src = D >= 0 ? push.in_level + D * fabm + ((long long)kz * N1 + r) * VNX + (side ? 0 : VNX - 1)
+        const T* src = D >= 0 ? lvl_in + D * fabm + ((long long)kz * N1 + r) * VNX + (side ? 0 : VNX - 1)
                                    : ownxg + ((long long)side * n2 + kz) * N1 + r;
         ox[it] = live ? PS * PLANE + side * PS * STRIP + p * STRIP + r : -1;
-        vx[it] = live ? *src : 0.0;
+        vx[it] = live ? *src : (T)0;
       }
 #pragma unroll
       for (int it = 0; it < IY; ++it) {
@@ -301,10 +309,10 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
         const bool live = idx < NYH && kz >= NG && kz < n2 - NG;   // ghost planes are copied whole by the producer
         const int D = side ? dyp : dym;
         const int grow = side ? VNY + NG : 0;      // ghost row being filled (NG == 1)
-        const double* src = D >= 0 ? push.in_level + D * fabm + ((long long)kz * N1 + (side ? NG : VNY)) * VNX + x
+        const T* src = D >= 0 ? lvl_in + D * fabm + ((long long)kz * N1 + (side ? NG : VNY)) * VNX + x
                                    : ownmain + ((long long)kz * N1 + grow) * VNX + x;
         oy[it] = live ? p * PLANE + grow * VNX + x : -1;
-        vy[it] = live ? *src : 0.0;
+        vy[it] = live ? *src : (T)0;
       }
 #pragma unroll
       for (int it = 0; it < IX; ++it) if (ox[it] >= 0) dst[ox[it]] = vx[it];
@@ -329,10 +337,10 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   // fused ghost fill: which faces of the box this thread's cells lie on
   const int fx = at_lo ? -1 : (at_hi ? 1 : 0);
   const long long fab_xg = (long long)2 * STRIP * n2;
-  double* xdst = nullptr;      // x-face destination strip of the current fab (threads on an x face only)
+  T* xdst = nullptr;      // x-face destination strip of the current fab (threads on an x face only)
   // edge strips of the output level ([box][valid plane][4][VNY], columns 0 and VNX-1 = strips 0 and 3)
-  constexpr bool XE = (VNX >= 32 && OP == 0 && MODE == 0);
-  double* const xe_col = (XE && (at_lo || at_hi) && push.xe_out) ? push.xe_out + (at_lo ? 0 : 3 * VNY) + j0 : nullptr;
+  constexpr bool XE = (VNX >= 32 && OP == 0 && MODE == 0 && sizeof(T) == 8);
+  T* const xe_col = (XE && (at_lo || at_hi) && push.xe_out) ? reinterpret_cast<T*>(push.xe_out) + (at_lo ? 0 : 3 * VNY) + j0 : nullptr;
   int pbox = -1;               // box whose destination is cached
   int bcur = 0;                // box of plane q (tracked incrementally)
 
@@ -344,10 +352,10 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   int bprev = bcur;                                    // box of plane q-1
   int slot = 0, prev_slot = 0;
   uint32_t phase = 0;
-  double cc[CPT], zm[CPT];                             // column values at planes q-1 and q-2
-  const double* prev = ring;                           // plane q-1 and its two x-ghost strips
-  const double* prev_lo = ring;
-  const double* prev_hi = ring;
+  T cc[CPT], zm[CPT];                             // column values at planes q-1 and q-2
+  const T* prev = ring;                           // plane q-1 and its two x-ghost strips
+  const T* prev_lo = ring;
+  const T* prev_hi = ring;
   bool prev_out = false;
   int kz_prev = 0;                                     // fab plane index of plane q-1
 
@@ -355,59 +363,59 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
     if (t == seam && t != l_begin) { qr += (long long)jump * PS; bcur = push.box0 + (int)(qr / n2); }
     mbar_wait(full + slot, (phase >> slot) & 1u);
     phase ^= 1u << slot;
-    const double* __restrict__ sbase = ring + (size_t)slot * STAGE;
+    const T* __restrict__ sbase = ring + (size_t)slot * STAGE;
 #pragma unroll
     for (int p = 0; p < PS; ++p) {
-      const double* __restrict__ cur = sbase + p * PLANE + so0;      // column 0 of plane q
+      const T* __restrict__ cur = sbase + p * PLANE + so0;      // column 0 of plane q
       const bool emit = prev_out && (q - 1 >= p_lo) && (q - 1 < p_hi);
       if (!emit) {
 #pragma unroll
         for (int m = 0; m < CPT; ++m) { zm[m] = cc[m]; cc[m] = cur[m * NT]; }
       } else {
-        double* __restrict__ po = out_main + (size_t)(qr - 1) * PLANE + so0;
-        const double* __restrict__ pc = prev + so0;
-        const double* __restrict__ pa = sbase + AUX_OFF + p * AUXP + (so0 - NG * VNX);   // OP 1: unm1 of plane q-1
+        T* __restrict__ po = out_main + (size_t)(qr - 1) * PLANE + so0;
+        const T* __restrict__ pc = prev + so0;
+        const T* __restrict__ pa = sbase + AUX_OFF + p * AUXP + (so0 - NG * VNX);   // OP 1: unm1 of plane q-1
         // x neighbours: from the plane, or from the strip for the first / last column
-        const double* __restrict__ pxm = at_lo ? prev_lo + sr0 : pc - 1;
-        const double* __restrict__ pxp = at_hi ? prev_hi + sr0 : pc + 1;
+        const T* __restrict__ pxm = at_lo ? prev_lo + sr0 : pc - 1;
+        const T* __restrict__ pxp = at_hi ? prev_hi + sr0 : pc + 1;
         const int xmstep = at_lo ? ROWS : NT, xpstep = at_hi ? ROWS : NT;   // strips advance by rows, planes by NT
-        double* __restrict__ xrow = nullptr;
+        T* __restrict__ xrow = nullptr;
         if (PUSH && !GATHER) {
           if (bprev != pbox) {           // new fab: look up the x neighbour this thread pushes into
             pbox = bprev;
             const int Dx = (fx && (push.mask & 1)) ? __ldg(push.nbr + (size_t)pbox * 27 + 13 + fx) : -1;
             // a +x push lands in the neighbour's LOW strip, a -x push in its HIGH strip
-            xdst = Dx >= 0 ? push.out_level + push.xg_base + Dx * fab_xg + (fx > 0 ? 0 : (long long)n2 * N1) + sr0 : nullptr;
+            xdst = Dx >= 0 ? lvl_out + push.xg_base + Dx * fab_xg + (fx > 0 ? 0 : (long long)n2 * N1) + sr0 : nullptr;
           }
           if (xdst) xrow = xdst + (long long)kz_prev * N1;
         }
-        double* __restrict__ erow = nullptr;
+        T* __restrict__ erow = nullptr;
         if (XE) { if (xe_col) erow = xe_col + ((long long)bprev * (n2 - 2 * NG) + (kz_prev - NG)) * (4 * VNY); }
 #pragma unroll
         for (int m = 0; m < CPT; ++m) {
-          const double zp = cur[m * NT];
-          const double c = cc[m];
-          double r;
+          const T zp = cur[m * NT];
+          const T c = cc[m];
+          T r;
           if (MODE == 1 || MODE == 3) r = c;
           else if (MODE == 2) r = zp;
           else {
-            const double twoc = __dmul_rn(2.0, c);
-            const double tx = sd2(pxp[m * xpstep], twoc, pxm[m * xmstep]);
-            const double ty = sd2(pc[m * NT + VNX], twoc, pc[m * NT - VNX]);
-            const double tz = sd2(zp, twoc, zm[m]);
+            const T twoc = Ar<T>::mul((T)2, c);
+            const T tx = sd2(pxp[m * xpstep], twoc, pxm[m * xmstep]);
+            const T ty = sd2(pc[m * NT + VNX], twoc, pc[m * NT - VNX]);
+            const T tz = sd2(zp, twoc, zm[m]);
             if (OP == 0) {
-              const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
-              r = (fma & 1) ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
+              const T S = Ar<T>::add(Ar<T>::add(tx, ty), tz);
+              r = (fma & 1) ? Ar<T>::fma(f, S, c) : Ar<T>::add(c, Ar<T>::mul(f, S));
             } else {
-              r = __dsub_rn(twoc, pa[m * NT]);
+              r = Ar<T>::sub(twoc, pa[m * NT]);
               if (fma & 2) {               // SGC_WAVE_DIRSUM: (2u - um1) + f*(Tz + (Ty + Tx))
-                const double sum = __dadd_rn(tz, __dadd_rn(ty, tx));
-                r = (fma & 1) ? __fma_rn(f, sum, r) : __dadd_rn(r, __dmul_rn(f, sum));
-              } else if (fma & 1) { r = __fma_rn(f, tx, r); r = __fma_rn(f, ty, r); r = __fma_rn(f, tz, r); }
-              else { r = __dadd_rn(r, __dmul_rn(f, tx)); r = __dadd_rn(r, __dmul_rn(f, ty)); r = __dadd_rn(r, __dmul_rn(f, tz)); }
+                const T sum = Ar<T>::add(tz, Ar<T>::add(ty, tx));
+                r = (fma & 1) ? Ar<T>::fma(f, sum, r) : Ar<T>::add(r, Ar<T>::mul(f, sum));
+              } else if (fma & 1) { r = Ar<T>::fma(f, tx, r); r = Ar<T>::fma(f, ty, r); r = Ar<T>::fma(f, tz, r); }
+              else { r = Ar<T>::add(r, Ar<T>::mul(f, tx)); r = Ar<T>::add(r, Ar<T>::mul(f, ty)); r = Ar<T>::add(r, Ar<T>::mul(f, tz)); }
             }
           }
-          if (MODE != 2 || zp == 1.2345e300) po[m * NT] = r;
+          if (MODE != 2 || zp == (T)1.2345e30) po[m * NT] = r;
           if (PUSH && !GATHER) { if (xrow) xrow[m * ROWS] = r; }
           if (XE) { if (erow) erow[m * ROWS] = r; }
           zm[m] = c;
@@ -432,20 +440,23 @@ k_heat_stream(const double* __restrict__ in_main, const double* __restrict__ in_
   }
 }
 
-template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0, bool GATHER = false>
-static int launch_cfg(const double* in_main, const double* in_xg, double* out_main, int nstages, int n2, double f,
+template <int VNX, int VNY, int NG, int PS, int NS, int NCW, int MODE = 0, bool PUSH = false, int OP = 0, bool GATHER = false,
+          typename T = double>
+static int launch_cfg(const T* in_main, const T* in_xg, T* out_main, int nstages, int n2, double f,
                       int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs(),
-                      const double* aux_main = nullptr) {
-  constexpr size_t smem = stream_smem_bytes(VNX, VNY, NG, PS, NS, OP);
+                      const T* aux_main = nullptr) {
+  constexpr int E = (int)sizeof(T);
+  static_assert((PS * VNX * (VNY + 2 * NG) * E) % 16 == 0 && (PS * NG * (VNY + 2 * NG) * E) % 16 == 0, "bulk copies move multiples of 16 bytes");
+  constexpr size_t smem = stream_smem_bytes(VNX, VNY, NG, PS, NS, OP, E);
   static_assert(smem <= 232448, "ring exceeds the 227 KB of shared memory a CTA can have");
   static bool configured = false;
-  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE, PUSH, OP, GATHER>;
+  auto kern = k_heat_stream<VNX, VNY, NG, PS, NS, NCW, MODE, PUSH, OP, GATHER, T>;
   if (!configured) {
     SGC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  int grid = rt().sm_count * stream_ctas_per_sm(VNX, VNY, NG, PS, NS, OP);
-  if (rt().sweep_grid_cap > 0 && rt().sweep_grid_cap < rt().sm_count) grid = rt().sweep_grid_cap * stream_ctas_per_sm(VNX, VNY, NG, PS, NS, OP);
+  int grid = rt().sm_count * stream_ctas_per_sm(VNX, VNY, NG, PS, NS, OP, E);
+  if (rt().sweep_grid_cap > 0 && rt().sweep_grid_cap < rt().sm_count) grid = rt().sweep_grid_cap * stream_ctas_per_sm(VNX, VNY, NG, PS, NS, OP, E);
   if (grid > nstages) grid = nstages;
   kern<<<grid, (NCW + 1 + (GATHER ? kGatherWarps : 0)) * 32, smem, s>>>(in_main, in_xg, out_main, nstages, n2, f, fma, seam, jump, push, aux_main);
   rt().launches++;
@@ -457,21 +468,42 @@ static int launch_cfg(const double* in_main, const double* in_xg, double* out_ma
 // Returns 1 when the geometry is not covered (caller falls back to the table-driven kernel).
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
                         cudaStream_t s, const PushArgs* fuse) {
-  if (!u->uniform || !unew->uniform || u->ncomp != 1 || unew->ncomp != 1 || u->ng != unew->ng || u->ng != 1) return 1;
-  if (u->esz != 8 || unew->esz != 8) return 1;
+  if (!u->uniform || !unew->uniform || u->ncomp != unew->ncomp || u->ng != unew->ng || u->ng != 1) return 1;
+  if (u->esz != unew->esz || (u->esz != 8 && u->esz != 4)) return 1;
+  // Several components: component c of fab b is the virtual fab b*ncomp + c of the plane sequence (the main
+  // blocks [comp][k][j][i] and xg blocks [comp][side][k][j] of a fab follow each other).  The fused modes and
+  // float levels take the plain sweep only.
+  const int nc = u->ncomp;
+  if (fuse && (nc != 1 || u->esz != 8)) return 1;
   const FabGeom& g = u->geom[0];
   if (memcmp(g.n, unew->geom[0].n, sizeof g.n) != 0) return 1;
   if (a1 == a0) { a0 = b0; a1 = b1; b0 = b1 = a1; }
   if (b1 == b0) b0 = b1 = a1;
   const int vnx = g.vn[0], vny = g.vn[1], n2 = g.n[2];
-  const double* in_main = (const double*)u->d_arena + (long long)a0 * g.cs;
-  const double* in_xg = (const double*)u->d_arena + u->xg_base + (long long)a0 * g.xcs;
-  double* out = (double*)unew->d_arena + (long long)a0 * g.cs;
-  const long long planesA = (long long)(a1 - a0) * n2, planesB = (long long)(b1 - b0) * n2;
-  const long long planes = planesA + planesB, gap = (long long)(b0 - a1) * n2;
+  const long long planesA = (long long)(a1 - a0) * nc * n2, planesB = (long long)(b1 - b0) * nc * n2;
+  const long long planes = planesA + planesB, gap = (long long)(b0 - a1) * nc * n2;
   if (planes <= 0) return 0;
   if (planes + gap > 0x7fffffffLL) return 1;
   if (getenv("SGC_NO_STREAM")) return 1;
+  if (u->esz == 4) {
+    const float* in_main = (const float*)u->d_arena + (long long)a0 * nc * g.cs;
+    const float* in_xg = (const float*)u->d_arena + u->xg_base + (long long)a0 * nc * g.xcs;
+    float* out = (float*)unew->d_arena + (long long)a0 * nc * g.cs;
+    unew->xe_valid = 0;
+    // stages of an even number of planes keep every bulk copy a multiple of 16 bytes (a strip of 66 floats is 264)
+#define SGC_STREAM_CASE_F(VX, VY, PS_, NS_, NCW_)                                                                        \
+  if (vnx == VX && vny == VY && n2 % PS_ == 0)                                                                           \
+    return launch_cfg<VX, VY, 1, PS_, NS_, NCW_, 0, false, 0, false, float>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
+                                                                          (int)(planesA / PS_), (int)(gap / PS_), s)
+    SGC_STREAM_CASE_F(64, 64, 2, 6, 16);
+    SGC_STREAM_CASE_F(32, 32, 2, 10, 8);
+    SGC_STREAM_CASE_F(16, 16, 6, 6, 8);
+#undef SGC_STREAM_CASE_F
+    return 1;
+  }
+  const double* in_main = (const double*)u->d_arena + (long long)a0 * nc * g.cs;
+  const double* in_xg = (const double*)u->d_arena + u->xg_base + (long long)a0 * nc * g.xcs;
+  double* out = (double*)unew->d_arena + (long long)a0 * nc * g.cs;
   PushArgs pa;
   memset(&pa, 0, sizeof pa);
   if (fuse) pa = *fuse;

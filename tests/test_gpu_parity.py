@@ -57,6 +57,43 @@ def test_upload_download_roundtrip_and_setval(g, oracle):
     assert (got[0] == 7.0).all() and (got[1] == -1.25).all()
 
 
+def test_valid_only_upload_and_download(g, oracle):
+    """sgc_level_upload_valid / download_valid: the valid cells of every fab as one dense buffer
+    [box][comp][k][j][i] (what LevelData.cpp:150-193 hands to the plot writer, and its reverse); ghost cells keep
+    their contents on upload.  Blocking and transfer-stream forms, double and float, uniform and ragged boxes."""
+    rng = np.random.default_rng(3)
+    for dlo, dhi, mb, nc, dt in (((0, 0, 0), (127, 63, 63), (64, 64, 64), 1, np.float64),
+                                 ((1, -1, 1), (12, 10, 12), (4, 4, 4), 2, np.float64),
+                                 ((0, 0, 0), (31, 31, 15), (16, 16, 16), 1, np.float32)):
+        dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
+        lev = g.LevelData(dbl, nc, 1, dtype=dt)
+        full = rng.standard_normal(lev.elems).astype(dt)
+        lev.upload(full)
+        nv = lev.validElems()
+        assert nv == nc * int(np.prod(np.array(dhi) - np.array(dlo) + 1))
+        vals = rng.standard_normal(nv).astype(dt)
+        lev.uploadValid(vals)
+        want = full.copy()
+        pos = 0
+        for k, bx in enumerate(dbl.boxes):
+            n = bx[3:] - bx[:3] + 1
+            f = want[lev.fab_offset(k):lev.fab_offset(k) + lev.fab_elems(k)].reshape(nc, n[2] + 2, n[1] + 2, n[0] + 2)
+            cnt = nc * int(np.prod(n))
+            f[:, 1:-1, 1:-1, 1:-1] = vals[pos:pos + cnt].reshape(nc, n[2], n[1], n[0])
+            pos += cnt
+        assert np.array_equal(lev.download(), want)              # valid cells replaced, ghost cells untouched
+        assert np.array_equal(lev.downloadValid(), vals)
+        # transfer-stream forms
+        pin_in, pin_out = g.PinnedBuffer(nv, dt), g.PinnedBuffer(nv, dt)
+        pin_in.array[:] = -vals
+        st = g.Stream()
+        lev.uploadValid(pin_in, st)
+        st.sync()
+        lev.downloadValid(pin_out, st)
+        st.sync()
+        assert np.array_equal(pin_out.array, -vals)
+
+
 def test_async_transfer_streams_pipeline(g, oracle):
     """LevelData::copyToDeviceAsync / copyToHostAsync (LevelData.H:734-765): batches streamed through
     two transfer streams and the compute stream, ordered by events, give the same bits as the blocking
@@ -648,6 +685,8 @@ def test_single_precision_and_multicomponent_sweeps(g, oracle):
         R = pyoracle.Reference(variant)
         for (dlo, dhi, mb, per, f, nstep) in (((0, 0, 0), (23, 15, 15), (8, 8, 8), 7, 0.2, 6),
                                               ((0, 0, 0), (127, 63, 63), (64, 64, 64), 3, 1.0 / 6.0, 5),
+                                              ((0, 0, 0), (63, 31, 31), (32, 32, 32), 7, 0.2, 4),
+                                              ((0, 0, 0), (31, 31, 15), (16, 16, 16), 5, 0.3, 5),
                                               ((0, 0, 0), (11, 9, 8), (6, 5, 3), 0, 0.31, 4)):
             dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
             a, b = g.LevelData(dbl, 1, 1, dtype=np.float32), g.LevelData(dbl, 1, 1, dtype=np.float32)
@@ -663,21 +702,23 @@ def test_single_precision_and_multicomponent_sweeps(g, oracle):
     dbl = g.DisjointBoxLayout(g.Box((0, 0, 0), (7, 7, 7)), 4)
     with pytest.raises(g.SgcError):
         g.heat_sweep(g.LevelData(dbl, 1, 1), g.LevelData(dbl, 1, 1, dtype=np.float32), 0.1)
-    # three components, double: each is an independent field
-    dlo, dhi, mb = (0, 0, 0), (15, 11, 7), (8, 4, 4)
-    dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
-    a, b = g.LevelData(dbl, 3, 1), g.LevelData(dbl, 3, 1)
-    u, v = rng.standard_normal(a.elems), rng.standard_normal(a.elems)
-    a.upload(u); b.upload(v)
-    g.heat_sweep(b, a, 0.2)
-    got = b.download()
-    n = [int(np.prod(bx[3:] - bx[:3] + 3)) for bx in dbl.boxes]
-    for c in range(3):
-        uc = np.concatenate([u[a.fab_offset(k) + c * n[k]:a.fab_offset(k) + (c + 1) * n[k]] for k in range(a.size())])
-        vc = np.concatenate([v[a.fab_offset(k) + c * n[k]:a.fab_offset(k) + (c + 1) * n[k]] for k in range(a.size())])
-        gc = np.concatenate([got[a.fab_offset(k) + c * n[k]:a.fab_offset(k) + (c + 1) * n[k]] for k in range(a.size())])
-        oracle.level_heat_sweep(dbl.boxes, 1, uc, vc, 0.2, 1)
-        assert np.array_equal(gc, vc), c
+    # three components, double: each is an independent field (table-driven kernel, and the streaming kernel,
+    # which walks component c of fab b as virtual fab 3 b + c)
+    for dlo, dhi, mb in (((0, 0, 0), (15, 11, 7), (8, 4, 4)), ((0, 0, 0), (63, 31, 15), (32, 32, 8)),
+                         ((0, 0, 0), (63, 127, 11), (64, 64, 6))):
+        dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
+        a, b = g.LevelData(dbl, 3, 1), g.LevelData(dbl, 3, 1)
+        u, v = rng.standard_normal(a.elems), rng.standard_normal(a.elems)
+        a.upload(u); b.upload(v)
+        g.heat_sweep(b, a, 0.2)
+        got = b.download()
+        n = [int(np.prod(bx[3:] - bx[:3] + 3)) for bx in dbl.boxes]
+        for c in range(3):
+            uc = np.concatenate([u[a.fab_offset(k) + c * n[k]:a.fab_offset(k) + (c + 1) * n[k]] for k in range(a.size())])
+            vc = np.concatenate([v[a.fab_offset(k) + c * n[k]:a.fab_offset(k) + (c + 1) * n[k]] for k in range(a.size())])
+            gc = np.concatenate([got[a.fab_offset(k) + c * n[k]:a.fab_offset(k) + (c + 1) * n[k]] for k in range(a.size())])
+            oracle.level_heat_sweep(dbl.boxes, 1, uc, vc, 0.2, 1)
+            assert np.array_equal(gc, vc), (mb, c)
 
 
 def test_reference_device_kats_gpuSandbox(g):
