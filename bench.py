@@ -307,6 +307,43 @@ def run_reference_arm_c1(a):
 
 # ------------------------------------------------------------------------------ our arm
 _REAL_STDOUT = None
+_FULL_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank (and therefore the pinned host buffers it allocates, first touch) to the CPUs of the NUMA node
+    its GPU hangs off — what `numactl --cpunodebind --membind` does for a production launch.  Returns a description
+    for the JSON line; silently does nothing where sysfs / nvidia-smi do not tell (single-node hosts)."""
+    global _FULL_AFFINITY
+    try:
+        _FULL_AFFINITY = os.sched_getaffinity(0)
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "platform reports no NUMA affinity for the GPU"}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= _FULL_AFFINITY
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus_bound": len(cpus), "pci_bus_id": bus}
+    except Exception as ex:
+        return {"numa_node": None, "note": repr(ex)}
+
+
+def restore_full_affinity():
+    if _FULL_AFFINITY:
+        try:
+            os.sched_setaffinity(0, _FULL_AFFINITY)
+        except OSError:
+            pass
 
 
 def emit(line):
@@ -605,6 +642,7 @@ def main():
         dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world)
     n_gpus = world
 
+    numa = bind_to_gpu_numa_node(local_rank)
     from _loadpkg import load_package
     sgc = load_package()
     sgc.init(local_rank)
@@ -615,6 +653,7 @@ def main():
             sampler = ClockSampler(local_rank)
             sampler.start()
             tw0 = time.time()
+            restore_full_affinity()
             c1 = run_c1(sgc, a, peak, peak_src, max(a.steps, 5), max(a.warmup, 3), with_cpu=not a.no_cpu_baseline)
             clocks = sampler.stop(tw0, time.time())
             name, sms, _ = sgc.device_info()
@@ -858,7 +897,7 @@ def main():
                "host_bw_ceiling_gbs": (A.validElems() * 8 / (copy_t * 1e-3) / 1e9) if copy_t == copy_t else None,
                "host_bw_ceiling": "per GPU and direction: the leg's H2D and D2H streams running concurrently with no compute, "
                                   "all ranks at once, slowest rank; ceiling_value = the metric if a step cost only that",
-               "ceiling_value": gc(copy_t) if copy_t == copy_t else None,
+               "ceiling_value": gc(copy_t) if copy_t == copy_t else None, "numa_binding": numa,
                "ms_per_step": pipe_t if piped else serial_t, "pipelined": bool(piped), "batches_timed": nbatch if piped else len(serial_ms),
                "single_batch": {"value": gc(serial_t), "ms_per_step": serial_t,
                                 "call": "sgc_level_upload_valid + sgc_heat_run(%d sweeps) + sgc_level_download_valid" % a.sweeps},
@@ -870,6 +909,7 @@ def main():
     # Full-size parity + CPU baseline (rank 0, N = 1): the reference's own CPU run of `cpu_sweeps` sweeps of the
     # SAME level is both the checker of the device result and the timed baseline.
     cpu, parity = None, None
+    restore_full_affinity()               # the CPU baseline gets every host core
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             gdom = global_domain(a, 1)

@@ -40,7 +40,7 @@ def exchange_probe(n=512, box=64):
     dbl, a, b, cp = level(n, box)
     out = {"level": "%d^3 in %d^3 boxes" % (n, box), "ghost_cells": cp.numCells(), "algorithmic_MB": 16e-6 * cp.numCells()}
     sgc.heat_sweep(b, a, 0.125)                   # b's outer strips are current now
-    assert b.edgeStrips() == 1
+    assert b.edgeStrips() == 2
     out["exchange_strips_ms"] = timed(lambda: b.exchange(cp), 20)
     os.environ["SGC_NO_XE"] = "1"
     out["exchange_plain_ms"] = timed(lambda: b.exchange(cp), 20)

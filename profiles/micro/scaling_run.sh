@@ -1,15 +1,26 @@
 #!/bin/bash
-# weak scaling on ONE 8-GPU box (all N on the same GPUs), then the C4 shape (1024^3 over 8 GPUs)
-for n in 1 2 4 8; do
-  if [ $n = 1 ]; then
-    timeout 300 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/scale_n$n.log 2>&1
-  else
-    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2961$n \
-      bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/scale_n$n.log 2>&1
-  fi
-  tail -1 gpurun_out/scale_n$n.log > gpurun_out/scale_n$n.json
+# All N back to back on ONE 8xB200 box (B200s of the pool differ by a few per cent: never compare across boxes).
+# Usage (on the GPU box): bash profiles/micro/scaling_run.sh [tag]   -> gpurun_out/<tag>_n{1,2,4,8}.json
+tag=${1:-scale}
+python bench.py --no-configs > gpurun_out/${tag}_n1.json 2> gpurun_out/${tag}_n1.err
+port=29600
+for n in 2 4 8; do
+  port=$((port+1))
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port \
+      bench.py --gpus $n > gpurun_out/${tag}_n$n.json 2> gpurun_out/${tag}_n$n.err
 done
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29631 \
-  bench.py --gpus 8 --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 0 --domain 1024 --domain-z 128 > gpurun_out/scale_c4.log 2>&1
-tail -1 gpurun_out/scale_c4.log > gpurun_out/scale_c4.json
-for f in gpurun_out/scale_n1.json gpurun_out/scale_n2.json gpurun_out/scale_n4.json gpurun_out/scale_n8.json gpurun_out/scale_c4.json; do cut -c1-130 $f; done
+port=$((port+1))
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $port \
+    bench.py --gpus 8 --config C4 --e2e-steps 0 > gpurun_out/${tag}_c4.json 2> gpurun_out/${tag}_c4.err
+for f in gpurun_out/${tag}_n*.json gpurun_out/${tag}_c4.json; do python - "$f" <<'PY'
+import json, sys
+try:
+    j = json.load(open(sys.argv[1]))
+    e = j.get("e2e") or {}
+    print(sys.argv[1], "N=%d value=%.1f ms/step=%.3f e2e=%s ceiling=%s bw=%s parity=%s" % (
+        j["n_gpus"], j["value"], j["ms_per_step"], e.get("value"), e.get("ceiling_value"), e.get("host_bw_ceiling_gbs"),
+        (j.get("parity_nranks") or j.get("parity") or {}).get("ok")))
+except Exception as ex:
+    print(sys.argv[1], "unreadable:", ex)
+PY
+done

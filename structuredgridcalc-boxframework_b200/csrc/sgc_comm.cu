@@ -20,6 +20,7 @@
 #include <cstring>
 
 #include "sgc_device.h"
+#include "sgc_pipe.cuh"
 
 namespace sgc {
 
@@ -134,6 +135,21 @@ int comm_plan_setup(sgc_plan_s* p, sgc_level_s* l, const Grid& g, unsigned perio
       pos += r.size() * p->nc;
     }
     peer.recv_elems = pos;
+    if (l->uniform) {
+      // pull table: every rank holds the same sequence of fab shapes, so box `send_box` sits in its owner's arena
+      // where our own box of the same local index sits in ours
+      std::vector<CopyItem> pull;
+      const FabGeom& g0 = l->geom[0];
+      for (const sgc_motion_item& it : h.recv) {
+        const IBox r = box_of(it.recv_lo, it.recv_hi), sr = box_of(it.src_lo, it.src_hi);
+        const int ld = it.recv_box - l->gidx0, rb = it.send_box - it.send_proc * g.bpp;
+        const FabGeom gp = level_fab_geom(g.box(it.send_box), l->ng, (long long)rb * g0.cs * l->ncomp,
+                                          l->xg_base + (long long)rb * g0.xcs * l->ncomp);
+        make_items(pull, l->geom[ld], r, p->c0, gp, sr, p->c0, p->nc, it.comp_flags);
+      }
+      st = peer.pull.upload(pull, l->esz);
+      if (st) return st;
+    }
     pos = 0;
     for (const sgc_motion_item& it : h.send) {
       const IBox r = box_of(it.src_lo, it.src_hi);
@@ -168,6 +184,7 @@ void comm_plan_release(sgc_plan_s* p) {
   for (sgc_plan_s::Peer& q : p->peers) {
     q.pack.release();
     q.unpack.release();
+    q.pull.release();
     if (q.d_send) cudaFree(q.d_send);
     if (q.d_recv) cudaFree(q.d_recv);
     if (q.ev_arrived) cudaEventDestroy(q.ev_arrived);
@@ -301,6 +318,46 @@ int comm_stream_barrier(cudaStream_t s) {
   static int* d_one = nullptr;
   if (!d_one) { SGC_CUDA(cudaMalloc(&d_one, 256)); SGC_CUDA(cudaMemset(d_one, 0, 256)); }
   SGC_NCCL(c.api.AllReduce(d_one, d_one, 1, ncclInt, ncclMax, c.comm, s));
+  return 0;
+}
+
+__global__ void k_wait_peer(const unsigned long long* flag, unsigned long long value, unsigned long long budget_ns,
+                            unsigned int* err) {
+  if (*reinterpret_cast<const volatile unsigned int*>(err)) return;
+  if (!wait_peer_counter(flag, value, budget_ns)) *err = 1u;
+  __threadfence_system();
+}
+
+// can the remote half of an exchange of `l` be done by reading the neighbours' arenas? (session up, l is one of its two
+// levels, every peer of the plan is a session peer and has a pull table)
+bool comm_p2p_can_pull(sgc_plan_s* p, sgc_level_s* l) {
+  const sgc_plan_s::P2P& S = p->p2p;
+  if (!S.ready || (l != S.lev[0] && l != S.lev[1])) return false;
+  for (const sgc_plan_s::Peer& q : p->peers) {
+    bool found = false;
+    for (int k = 0; k < S.npeer; ++k) found = found || S.peer_rank[k] == q.rank;
+    if (!found || q.pull.nitem == 0) return false;
+  }
+  return true;
+}
+
+// The remote half of LevelData::exchange inside a step loop on a slab partition, without a message: wait (on the
+// device) until the neighbour's progress counter says its level holds the step being exchanged, then ONE batched copy
+// per neighbour reads the regions out of its arena over NVLink straight into our ghost cells.  No pack, no NCCL, no
+// unpack, no host synchronisation.  Ordering against the neighbour's later writes: see DESIGN.md §5.
+int comm_p2p_pull(sgc_plan_s* p, sgc_level_s* l, unsigned long long budget_ns, cudaStream_t s) {
+  sgc_plan_s::P2P& S = p->p2p;
+  const int li = (l == S.lev[0]) ? 0 : 1;
+  for (sgc_plan_s::Peer& q : p->peers) {
+    int slot = 0;
+    for (int k = 0; k < S.npeer; ++k) if (S.peer_rank[k] == q.rank) slot = k;
+    k_wait_peer<<<1, 1, 0, s>>>((const unsigned long long*)S.peer_flag_base[slot], S.counter, budget_ns, S.d_err);
+    rt().launches++;
+    SGC_CUDA(cudaGetLastError());
+    const void* peer_arena = (const char*)S.peer_base[slot][li] + l->lead * l->esz;
+    const int st = launch_copy(q.pull, l->d_arena, peer_arena, l->esz, s);
+    if (st) return st;
+  }
   return 0;
 }
 

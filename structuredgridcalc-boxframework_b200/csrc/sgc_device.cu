@@ -38,6 +38,8 @@ int comm_p2p_signal(sgc_plan_s* plan, unsigned long long value, cudaStream_t s);
 int comm_p2p_check(sgc_plan_s* plan);
 int comm_all_min(int v, int* out);
 int comm_stream_barrier(cudaStream_t s);
+bool comm_p2p_can_pull(sgc_plan_s* p, sgc_level_s* l);
+int comm_p2p_pull(sgc_plan_s* p, sgc_level_s* l, unsigned long long budget_ns, cudaStream_t s);
 void comm_level_destroyed(sgc_level_s* l);
 void comm_drain_deferred_frees();
 bool heat_stream_covers(const sgc_level_s* unew, const sgc_level_s* u);
@@ -101,7 +103,7 @@ void CopyTable::release() {
   if (d_cell_start) cudaFree(d_cell_start);
   if (d_chunk_first) cudaFree(d_chunk_first);
   d_items = nullptr; d_cell_start = nullptr; d_chunk_first = nullptr;
-  nitem = nchunk = nwitem = nwchunk = 0; ncell = nwcell = 0; strided_reads = false;
+  nitem = nchunk = nwitem = nwchunk = 0; ncell = nwcell = 0; strided_reads = false; mostly_big = false;
 }
 
 // can the item run with 16-byte accesses?  (8-byte elements; every base pointer the tables are used with
@@ -129,6 +131,7 @@ int CopyTable::upload(const std::vector<CopyItem>& in, int esz) {
   static const bool no_sort = ns_env && ns_env[0] == '1';
   std::vector<CopyItem> items;
   items.reserve(in.size() + 2);
+  long long big_units = 0, all_units = 0;
   for (int wide = 1; wide >= 0; --wide) {
     std::vector<CopyItem> small, big;
     for (const CopyItem& c : in) {
@@ -140,6 +143,8 @@ int CopyTable::upload(const std::vector<CopyItem>& in, int esz) {
     }
     long long n = 0;
     for (const CopyItem& c : small) n += units(c);
+    all_units += n;
+    for (const CopyItem& c : big) { big_units += units(c); all_units += units(c); }
     if (!big.empty() && n % kCopyChunk) {
       CopyItem pad;
       memset(&pad, 0, sizeof pad);       // flags = 0, c0 = 0: every unit is masked out, nothing is touched
@@ -151,6 +156,7 @@ int CopyTable::upload(const std::vector<CopyItem>& in, int esz) {
     if (wide) nwitem = (int)items.size();
   }
   nitem = (int)items.size();
+  mostly_big = big_units * 2 >= all_units;
   std::vector<long long> start(nitem + 1);
   start[0] = 0;
   for (int i = 0; i < nitem; ++i) start[i + 1] = start[i] + units(items[i]);
@@ -1363,8 +1369,7 @@ static int run_t2_passes(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f
     if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);
     std::swap(cur, nxt);
   }
-  if (!st && p2p) st = comm_p2p_check(plan);
-  return st;
+  return st;           // a timed-out wait turns the later launches into no-ops; the caller checks once, at the end
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1546,9 +1551,22 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
       if (st) return st;
       s0 += 2 * npass;
     }
-    // the exchange below also orders the phases on a multi-GPU run: its receives complete only after
+    // Peer-memory session: the rest of the run needs no message either — every exchange reads its remote regions out
+    // of the neighbours' arenas (comm_p2p_pull), gated by the same progress counters as the sweeps.
+    // Opt-in (SGC_PULL=1): measured at N = 2 on the bench level it is 0.2 ms per 100 steps SLOWER than the NCCL
+    // schedule of the last steps, which hides its 8 MB message behind the interior boxes (26.45 against 26.22 ms).
+    const char* pl = getenv("SGC_PULL");
+    const bool pull = p2p && pl && pl[0] == '1' && comm_p2p_can_pull(plan, a);
+    auto exchange_pull = [&](sgc_level_t lev) -> int {
+      ProfScope prof(1, rt().compute);
+      const bool strips = plan->local_xe.nitem > 0 && lev->xe_valid >= 1 && !getenv("SGC_NO_XE");
+      int e = launch_copy(strips ? plan->local_xe : plan->local, lev->d_arena, lev->d_arena, lev->esz, rt().compute);
+      if (!e) e = comm_p2p_pull(plan, lev, p2p_wait_budget_ns(), rt().compute);
+      return e;
+    };
+    // otherwise the exchange below also orders the phases on a multi-GPU run: its receives complete only after
     // the neighbours have left their last pass, so their reads of our levels are over
-    st = sgc_exchange(cur, plan);
+    st = pull ? exchange_pull(cur) : sgc_exchange(cur, plan);
     if (p2p && !st) {
       sgc_plan_s::P2P& S = plan->p2p;
       for (; s0 < nstep - 2 && !st; ++s0) {
@@ -1566,6 +1584,16 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
         st = fused_sweep(nxt, cur, f, flags, 0, cur->nbox, cur->nbox, cur->nbox, plan->d_push, fmask, &ra);
         if (!st) st = comm_p2p_signal(plan, ++S.counter, rt().compute);
         std::swap(cur, nxt);
+      }
+      if (pull) {
+        // the last two steps { exchange ; sweep } as they are, the exchange's remote half pulled: restores every
+        // ghost cell of both levels exactly as the step-by-step schedule leaves it
+        for (; s0 < nstep && !st; ++s0) {
+          st = exchange_pull(cur);
+          if (!st) st = sgc_heat_sweep(nxt, cur, f, flags);
+          if (!st) st = comm_p2p_signal(plan, ++S.counter, rt().compute);
+          std::swap(cur, nxt);
+        }
       }
       if (!st) st = comm_p2p_check(plan);
       if (st) return st;

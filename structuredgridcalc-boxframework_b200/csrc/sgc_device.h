@@ -75,6 +75,7 @@ struct CopyTable {
   int nwitem = 0, nwchunk = 0;
   long long ncell = 0, nwcell = 0;
   bool strided_reads = false;          // a good share of the cells are single elements of long rows (x faces)
+  bool mostly_big = false;             // most units belong to items of at least a chunk: the single-item kernel variant pays
   void release();
   int upload(const std::vector<CopyItem>& items, int esz = 0);   // esz 8 enables the wide class
 };
@@ -276,6 +277,9 @@ struct sgc_plan_s {
     void* d_recv = nullptr;
     long long send_elems = 0, recv_elems = 0;
     cudaEvent_t ev_arrived = nullptr;   // this peer's message has landed in d_recv (recorded on the comm stream)
+    // the same ghost regions filled by READING the peer's arena where it lies (peer-memory session of a step loop):
+    // dst = offsets in this rank's arena, src = offsets in the peer's arena (uniform levels: same layout everywhere)
+    sgc::CopyTable pull;
   };
   std::vector<Peer> peers;
   int n_boundary_boxes = 0;               // boxes with at least one remote item

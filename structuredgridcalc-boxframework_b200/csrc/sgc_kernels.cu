@@ -164,7 +164,10 @@ int launch_copy(const CopyTable& t, void* dst_arena, const void* src_arena, int 
   if (t.nwchunk > 0 && (esz != 8 || (((uintptr_t)dst_arena | (uintptr_t)src_arena) & 15)))
     return fail(SGC_ERR_ARG, "copy table has 16-byte items but the buffers are not 16-byte aligned 8-byte arrays");
   static const char* var_env = getenv("SGC_COPY_VARIANT");
-  const int variant = var_env ? atoi(var_env) : 1;       // 0: per-unit decode only; 1: + single-item chunks, loads batched; 2: + not batched
+  // 0: per-unit decode only (32 registers, 8 CTAs per SM: best when chunks hold many small items — 16^3 / 32^3 box faces,
+  // edges, corners); 1: + single-item chunks with batched loads (72 registers: best when most units sit in items of at
+  // least a chunk — 64^3 box faces, layout conversions); 2: single-item chunks, loads not batched (A/B only)
+  const int variant = var_env ? atoi(var_env) : (t.mostly_big ? 1 : 0);
 #define SGC_COPY_LAUNCH(T, V, NW, WC)                                                                               \
   k_copy_items<T, V><<<t.nchunk, kCopyThreads, 0, s>>>(t.d_items, t.d_cell_start, t.d_chunk_first, (T*)dst_arena,   \
                                                        (const T*)src_arena, t.ncell, small_fetch, NW, WC)

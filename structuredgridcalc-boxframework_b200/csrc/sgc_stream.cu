@@ -338,9 +338,10 @@ k_heat_stream(const T* __restrict__ in_main, const T* __restrict__ in_xg, T* __r
   const int fx = at_lo ? -1 : (at_hi ? 1 : 0);
   const long long fab_xg = (long long)2 * STRIP * n2;
   T* xdst = nullptr;      // x-face destination strip of the current fab (threads on an x face only)
-  // edge strips of the output level ([box][valid plane][4][VNY], columns 0 and VNX-1 = strips 0 and 3)
+  // edge strips of the output level ([box][valid plane][4][VNY] = copies of columns 0, 1, VNX-2, VNX-1)
   constexpr bool XE = (VNX >= 32 && OP == 0 && MODE == 0 && sizeof(T) == 8);
-  T* const xe_col = (XE && (at_lo || at_hi) && push.xe_out) ? reinterpret_cast<T*>(push.xe_out) + (at_lo ? 0 : 3 * VNY) + j0 : nullptr;
+  const int xe_s = xi == 0 ? 0 : (xi == 1 ? 1 : (xi == VNX - 2 ? 2 : (xi == VNX - 1 ? 3 : -1)));    // strip this column is a copy of
+  T* const xe_col = (XE && xe_s >= 0 && push.xe_out) ? reinterpret_cast<T*>(push.xe_out) + xe_s * VNY + j0 : nullptr;
   int pbox = -1;               // box whose destination is cached
   int bcur = 0;                // box of plane q (tracked incrementally)
 
@@ -511,7 +512,7 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
   pa.in_level = (const double*)u->d_arena;
   pa.xg_base = unew->xg_base;
   pa.box0 = a0;
-  // the sweep keeps the outer edge strips of its output current when it covers the whole level
+  // the sweep keeps the edge strips of its output current when it covers the whole level
   const bool whole = (a0 == 0 && a1 == unew->nbox) || (a0 == 0 && b1 == unew->nbox && a1 == b0);
   static const bool no_xe = getenv("SGC_NO_XE") != nullptr;
   pa.xe_out = (whole && unew->xe_elems && !unew->xe_extern && !no_xe) ? (double*)unew->d_arena + unew->xe_base : nullptr;
@@ -527,7 +528,7 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
     else                                                                                             \
       st_ = launch_cfg<VX, VY, 1, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, \
                                                   (int)(planesA / PS_), (int)(gap / PS_), s, pa);    \
-    if (st_ == 0 && pa.xe_out && VX >= 32) unew->xe_valid = 1;                                       \
+    if (st_ == 0 && pa.xe_out && VX >= 32) unew->xe_valid = 2;                                       \
     return st_;                                                                                      \
   }
   if (const char* m = getenv("SGC_STREAM_MODE")) {      // diagnostics only

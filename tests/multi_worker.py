@@ -95,12 +95,15 @@ def run_gpu(rank, world, local_rank):
              ((0, 0, 0), (63, 31, 64 * world - 1), (32, 32, 32), 3, 0.125, 9),
              ((0, 0, 0), (15, 15, 8 * world - 1), (8, 8, 8), 0, 0.125, 5),
              ((0, 0, 0), (11, 7, 10 * world - 1), (6, 4, 5), 3, 0.2, 4))
-    # every case twice: z halo read out of the neighbour's memory (default), and the NCCL schedule (SGC_P2P=0:
-    # pack, one send/recv pair per peer, each peer's message unpacked as it arrives — LevelData.H:507-536)
-    for p2p_env, (dlo, dhi, mb, per, f, nstep) in [(e, c) for e in (None, "0") for c in cases]:
-        if p2p_env is None:
-            os.environ.pop("SGC_P2P", None)
-        else:
+    # every case three times: z halo read out of the neighbour's memory (default), the NCCL schedule (SGC_P2P=0:
+    # pack, one send/recv pair per peer, each peer's message unpacked as it arrives — LevelData.H:507-536), and
+    # the all-peer-memory schedule (SGC_PULL=1)
+    for p2p_env, (dlo, dhi, mb, per, f, nstep) in [(e, c) for e in (None, "0", "pull") for c in cases]:
+        os.environ.pop("SGC_P2P", None)
+        os.environ.pop("SGC_PULL", None)
+        if p2p_env == "pull":          # the last steps' exchanges read the neighbours' arenas too (comm_p2p_pull)
+            os.environ["SGC_PULL"] = "1"
+        elif p2p_env is not None:
             os.environ["SGC_P2P"] = p2p_env
         dbl = sgc.DisjointBoxLayout(sgc.Box(dlo, dhi), mb, world, rank)
         allboxes, _, _ = O.layout(dlo, dhi, mb)
@@ -134,6 +137,7 @@ def run_gpu(rank, world, local_rank):
         if world > 1:
             assert cp.numRemoteItem() > 0
     os.environ.pop("SGC_P2P", None)
+    os.environ.pop("SGC_PULL", None)
     sgc.sync()
     dist.barrier()
     sgc.comm_finalize()

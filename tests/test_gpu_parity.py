@@ -542,7 +542,7 @@ def test_exchange_after_sweep_reads_edge_strips(g, oracle, monkeypatch):
             assert np.array_equal(cur.download(), hc), (mb, per, step, "exchange")
             g.heat_sweep(nxt, cur, 0.2)
             oracle.level_heat_sweep(dbl.boxes, 1, hc, hn, 0.2, 1)
-            assert nxt.edgeStrips() == 1, "the whole-level streaming sweep keeps the outer strips current"
+            assert nxt.edgeStrips() == 2, "the whole-level streaming sweep keeps the edge strips current"
             assert np.array_equal(nxt.download(), hn), (mb, per, step, "sweep")
             cur, nxt, hc, hn = nxt, cur, hn, hc
         # cur's strips are current; every other writer of valid cells must invalidate them
@@ -558,7 +558,7 @@ def test_exchange_after_sweep_reads_edge_strips(g, oracle, monkeypatch):
             g.heat_sweep(nxt, cur, 0.125)
             oracle.level_heat_sweep(dbl.boxes, 1, hc, hn, 0.125, 1)
             cur, nxt, hc, hn = nxt, cur, hn, hc
-            assert cur.edgeStrips() == 1
+            assert cur.edgeStrips() == 2
             lo = [int(x) for x in dbl.boxes[0][:3]]
             f0 = hc[:n].reshape(mb[2] + 2, mb[1] + 2, mb[0] + 2)
             if writer == "setval":
