@@ -1124,6 +1124,7 @@ int sgc_plan_destroy(sgc_plan_t p) {
   comm_p2p_release(p);
   comm_plan_release(p);
   rebox_release(p);
+  if (p->t2_scratch) sgc_level_destroy(p->t2_scratch);
   delete p;
   return 0;
 }
@@ -1329,9 +1330,10 @@ static unsigned long long p2p_wait_budget_ns() {
 // `npass` two-step passes (sgc_stream2.cu) starting from level `cur` of the pair (a, b); a is the level whose
 // physical-boundary ghost cells belong to the even steps.  p2p: z tiles come out of the neighbouring GPUs' memory.
 static int run_t2_passes(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags, int npass, bool p2p,
-                         sgc_level_t& cur, sgc_level_t& nxt) {
+                         sgc_level_t& cur, sgc_level_t& nxt, sgc_level_t scratch = nullptr) {
   sgc_plan_s::P2P& S = plan->p2p;
   int st = 0;
+  auto other = [&](sgc_level_t x) { return x == a ? b : a; };
   if (cur->xe_valid != 2) st = launch_build_xe(cur, rt().compute);
   if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);     // our strips are readable
   for (int k = 0; k < npass && !st; ++k) {
@@ -1361,13 +1363,18 @@ static int run_t2_passes(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f
         }
       }
     }
+    // an odd number of passes ends a -> b -> scratch -> a instead of ping-ponging
+    const bool via_scratch = scratch && k == npass - 2;
+    sgc_level_t out = via_scratch ? scratch : nxt;
     {
       ProfScope prof(2, rt().compute);
-      st = launch_heat_t2(nxt, cur, f, (flags & SGC_FMA) ? 1 : 0, plan->d_push, &ra, rt().compute);
+      st = launch_heat_t2(out, cur, f, (flags & SGC_FMA) ? 1 : 0, plan->d_push, &ra, rt().compute);
     }
     if (st > 0) st = fail(SGC_ERR_UNSUPPORTED, "two-step sweep: geometry not covered");
     if (!st && p2p) st = comm_p2p_signal(plan, ++S.counter, rt().compute);
-    std::swap(cur, nxt);
+    sgc_level_t prev = cur;
+    cur = out;
+    nxt = via_scratch ? other(prev) : ((scratch && k == npass - 1) ? other(cur) : prev);
   }
   return st;           // a timed-out wait turns the later launches into no-ops; the caller checks once, at the end
 }
@@ -1532,9 +1539,24 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
     // intermediate level stays on the SM.  It reads VALID cells only (the neighbours' rows, planes and
     // edge strips), so no ghost cell is touched until the phase ends; an even number of passes keeps
     // the result in the level the step-by-step schedule would leave it in.
-    const int npass = ((nstep - 2) / 2) & ~1;
+    int npass = (nstep - 2) / 2;
     const bool t2_remote_ok = plan->nremote == 0 || p2p;          // remote z faces need the peer-memory session
     bool t2 = heat_t2_covers(b, a) && (plan->t2_local || ((plan->t2_slab || plan->t2_bnd) && t2_remote_ok));
+    // an odd number of passes needs the library-owned third level (single rank: the neighbours of a peer-memory
+    // session map two arenas only); otherwise one pass fewer
+    sgc_level_t scratch = nullptr;
+    if (npass & 1) {
+      if (t2 && npass >= 3 && plan->nremote == 0 && !getenv("SGC_NO_T2_SCRATCH")) {
+        if (!plan->t2_scratch) {
+          std::vector<int> boxes6((size_t)a->nbox * 6);
+          for (int i = 0; i < a->nbox; ++i)
+            for (int d = 0; d < 3; ++d) { boxes6[6 * i + d] = a->boxes[i].lo[d]; boxes6[6 * i + 3 + d] = a->boxes[i].hi[d]; }
+          if (sgc_level_create(boxes6.data(), a->nbox, 1, 1, 8, a->gidx0, &plan->t2_scratch)) plan->t2_scratch = nullptr;
+        }
+        scratch = plan->t2_scratch;
+      }
+      if (!scratch) npass &= ~1;
+    }
     if (plan->nremote > 0) {
       // ranks may classify differently (the end ranks of a non-periodic slab partition see physical faces,
       // the others do not); the passes signal each other, so all ranks run them or none does
@@ -1547,7 +1569,7 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
       t2 = t2 && plan->t2_agreed == 1;
     }
     if (npass >= 2 && t2) {
-      st = run_t2_passes(a, b, plan, f, flags, npass, p2p, cur, nxt);
+      st = run_t2_passes(a, b, plan, f, flags, npass, p2p, cur, nxt, scratch);
       if (st) return st;
       s0 += 2 * npass;
     }
@@ -1566,7 +1588,8 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
     };
     // otherwise the exchange below also orders the phases on a multi-GPU run: its receives complete only after
     // the neighbours have left their last pass, so their reads of our levels are over
-    st = pull ? exchange_pull(cur) : sgc_exchange(cur, plan);
+    // (single rank with no fused step left: the plain steps below start with this very exchange)
+    if (plan->nremote > 0 || s0 < nstep - 2) st = pull ? exchange_pull(cur) : sgc_exchange(cur, plan);
     if (p2p && !st) {
       sgc_plan_s::P2P& S = plan->p2p;
       for (; s0 < nstep - 2 && !st; ++s0) {

@@ -295,6 +295,10 @@ struct sgc_plan_s {
   bool t2_local = false, t2_slab = false;
   bool t2_bnd = false;                  // as t2_slab, but some faces have no motion item at all (physical boundary)
   int t2_agreed = -1;                   // multi-rank: every rank can run the two-step passes (-1: not asked yet)
+  // library-owned third level of the two-step passes (single rank): with it an ODD number of passes still ends in the
+  // level the step-by-step schedule leaves the result in (a -> b -> scratch -> a), so a run of n steps is (n-2)/2
+  // passes + the two plain steps instead of an even number of passes + up to three fused one-step sweeps
+  sgc_level_s* t2_scratch = nullptr;
   // peer-memory halo session (sgc_comm.cu): the two ping-pong levels of a step loop, their arenas on
   // the z neighbours mapped through cudaIpc, and progress counters
   struct P2P {
