@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write("[%s]\n%s\n" % (src, out))
+            sys.stderr.write("[%s] nvcc exit code %d\n%s\n" % (src, p.returncode, out))
         ok = ok and p.returncode == 0
     if not ok:
         raise RuntimeError("nvcc failed")
