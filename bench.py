@@ -544,6 +544,39 @@ def sub_config_c3(sgc, a, peak, peak_src):
     return out
 
 
+def sub_config_c4(sgc, dist, a, world, rank, peak, peak_src):
+    """BASELINE configs[3] inside the default 8-GPU run: the 1024^3 heat equation in 64^3 boxes over the 8 GPUs (128
+    planes = two box layers per GPU: EVERY box reads a z neighbour over NVLink), the same 100-sweep step.  Collective:
+    every rank calls it."""
+    import torch
+    n, box = 1024, 64
+    dbl = sgc.DisjointBoxLayout(sgc.Box((0, 0, 0), (n - 1, n - 1, n - 1)), box, world, rank)
+    A, B = sgc.LevelData(dbl, 1, 1), sgc.LevelData(dbl, 1, 1)
+    host = np.empty(A.elems)
+    fill_level_host(host, dbl.local_boxes(), 1)
+    A.upload(host)
+    B.upload(host)
+    cp = sgc.Copier().defineExchangeLD(A, 7, 0)
+    sgc.sync()
+    dist.barrier()
+    ms, launches, prof, cur = measure_heat(sgc, A, B, cp, a.f, a.sweeps, 3, 2)
+    out = cur.download()
+    m = box + 2
+    sums = torch.tensor([float(out.reshape(A.size(), m, m, m)[:, 1:-1, 1:-1, 1:-1].sum(dtype=np.float64)),
+                         float(host.reshape(A.size(), m, m, m)[:, 1:-1, 1:-1, 1:-1].sum(dtype=np.float64))], dtype=torch.float64)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    t = torch.tensor([ms], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    cells_local = float(n) * n * (n // world)
+    return {"workload": "C4: 1024^3 heat equation in 64^3 boxes over %d GPUs (z-slabs of %d planes), periodic, %d x {exchange; sweep} "
+                        "per step, z halo read over NVLink peer memory inside the sweeps" % (world, n // world, a.sweeps),
+            "value": float(n) ** 3 * a.sweeps / (ms * 1e-3) / 1e9, "unit": "Gcell-updates/s", "ms_per_step": ms, "steps": 3, "warmup": 2,
+            "scaling": "strong", "n_gpus": world, "gpu_launches_per_step": int(launches // 3), "remote_items": cp.numRemoteItem(),
+            "sum_conserved": bool(abs(float(sums[0]) - float(sums[1])) <= 1e-9 * abs(float(sums[1]))),
+            "roofline": kernel_roofline(sgc, cells_local, 3 * a.sweeps, prof, peak, peak_src, 64)}
+
+
 def run_c1(sgc, a, peak, peak_src, steps, warmup, with_cpu=True):
     """BASELINE configs[0]: the reference's laplacian driver (laplacian.cpp:11-120) with n = 128: A on (1..128)^3,
     B on (2..127)^3, 16 iterations of the three directional passes B -= 0.5 * T_d(A).  One step = the 16
@@ -953,6 +986,14 @@ def main():
                 configs[name] = fn()
             except Exception as ex:
                 configs[name] = {"error": repr(ex)}
+
+    # ... and at 8 GPUs the 8-GPU config (collective)
+    if world == 8 and a.config == "C5" and not a.no_configs:
+        try:
+            c4 = sub_config_c4(sgc, dist, a, world, rank, peak, peak_src)
+        except Exception as ex:
+            c4 = {"error": repr(ex)}
+        configs = {"C4": c4}
 
     if rank == 0:
         name, sms, mem = sgc.device_info()

@@ -274,7 +274,8 @@ struct DevTmp {              // device scratch freed on every path out of a func
 };
 
 struct P2PMsg {
-  cudaIpcMemHandle_t lev[2];
+  cudaIpcMemHandle_t lev[3];
+  int nlev;
   cudaIpcMemHandle_t flag;
   unsigned long long counter;
 };
@@ -284,7 +285,7 @@ void comm_p2p_release(sgc_plan_s* p) {
   if (S.tried && rt().ready) { cudaStreamSynchronize(rt().compute); cudaStreamSynchronize(rt().comm); }
   // closing OUR mappings of the neighbours' memory is always legal
   for (int k = 0; k < 2; ++k) {
-    for (int l = 0; l < 2; ++l)
+    for (int l = 0; l < 3; ++l)
       if (S.peer_base[k][l]) { cudaIpcCloseMemHandle(S.peer_base[k][l]); S.peer_base[k][l] = nullptr; }
     if (S.peer_flag_base[k]) { cudaIpcCloseMemHandle(S.peer_flag_base[k]); S.peer_flag_base[k] = nullptr; }
   }
@@ -301,7 +302,7 @@ void comm_p2p_release(sgc_plan_s* p) {
 void comm_level_destroyed(sgc_level_s* l) {
   const std::vector<sgc_plan_s*> reg = p2p_plans();      // copy: release edits the registry
   for (sgc_plan_s* p : reg)
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k)
       if (p->p2p.lev[k] == l && p->p2p.gen[k] == l->generation) { comm_p2p_release(p); break; }
 }
 
@@ -394,11 +395,13 @@ int comm_all_min(int v, int* out) {
 
 // Returns 0 when the call went through (p->p2p.ready tells whether the session is usable on EVERY
 // rank — decided by an all-reduce, so all ranks take the same path); < 0 on hard errors.
-int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {
+int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b, sgc_level_s* third) {
   sgc_plan_s::P2P& S = p->p2p;
-  // the session is tied to the two LEVELS (generation ids), not to their addresses
-  if (S.tried && ((S.lev[0] == a && S.gen[0] == a->generation && S.lev[1] == b && S.gen[1] == b->generation) ||
-                  (S.lev[0] == b && S.gen[0] == b->generation && S.lev[1] == a && S.gen[1] == a->generation)))
+  // the session is tied to the LEVELS (generation ids), not to their addresses
+  const bool same_third = S.lev[2] == third && (!third || S.gen[2] == third->generation);
+  if (S.tried && same_third &&
+      ((S.lev[0] == a && S.gen[0] == a->generation && S.lev[1] == b && S.gen[1] == b->generation) ||
+       (S.lev[0] == b && S.gen[0] == b->generation && S.lev[1] == a && S.gen[1] == a->generation)))
     return 0;
   Comm& c = cm();
   if (!c.ready || c.nproc < 2) return 0;
@@ -406,6 +409,7 @@ int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {
   S.tried = true;
   S.lev[0] = a; S.gen[0] = a->generation;
   S.lev[1] = b; S.gen[1] = b->generation;
+  S.lev[2] = third; S.gen[2] = third ? third->generation : 0;
   p2p_plans().push_back(p);
   Runtime& r = rt();
   // 1. which boxes have a z neighbour on another rank, and is every remote FACE a z face?
@@ -440,7 +444,9 @@ int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {
       ok = cudaIpcGetMemHandle(&mine.lev[0], a->d_base) == cudaSuccess &&
            cudaIpcGetMemHandle(&mine.lev[1], b->d_base) == cudaSuccess &&
            cudaIpcGetMemHandle(&mine.flag, S.d_flag) == cudaSuccess;
-      if (ok) a->exported = b->exported = true;
+      mine.nlev = 2;
+      if (ok && third) { ok = cudaIpcGetMemHandle(&mine.lev[2], third->d_base) == cudaSuccess; mine.nlev = 3; }
+      if (ok) { a->exported = b->exported = true; if (third) third->exported = true; }
     }
     cudaGetLastError();
   }
@@ -466,7 +472,8 @@ int comm_p2p_setup(sgc_plan_s* p, sgc_level_s* a, sgc_level_s* b) {
     SGC_CUDA(cudaStreamSynchronize(r.comm));
     SGC_CUDA(cudaMemcpy(theirs, d_msg + 1, sizeof(P2PMsg) * 2, cudaMemcpyDeviceToHost));
     for (int k = 0; k < S.npeer && ok; ++k) {
-      for (int l = 0; l < 2 && ok; ++l)
+      if (theirs[k].nlev != mine.nlev) ok = 0;           // every rank takes the same decisions; a mismatch is a bug
+      for (int l = 0; l < mine.nlev && ok; ++l)
         ok = cudaIpcOpenMemHandle(&S.peer_base[k][l], theirs[k].lev[l], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
       if (ok) ok = cudaIpcOpenMemHandle(&S.peer_flag_base[k], theirs[k].flag, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
     }

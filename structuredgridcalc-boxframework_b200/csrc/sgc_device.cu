@@ -32,7 +32,7 @@ int launch_heat_stream(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
                         cudaStream_t s, const PushArgs* fuse);
 // peer-memory halo session (sgc_comm.cu)
-int comm_p2p_setup(sgc_plan_s* plan, sgc_level_s* a, sgc_level_s* b);
+int comm_p2p_setup(sgc_plan_s* plan, sgc_level_s* a, sgc_level_s* b, sgc_level_s* third);
 void comm_p2p_release(sgc_plan_s* plan);
 int comm_p2p_signal(sgc_plan_s* plan, unsigned long long value, cudaStream_t s);
 int comm_p2p_check(sgc_plan_s* plan);
@@ -1340,7 +1340,7 @@ static int run_t2_passes(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f
     T2Args ra;
     memset(&ra, 0, sizeof ra);
     if (p2p) {
-      const int li = (cur == S.lev[0]) ? 0 : 1;
+      const int li = (cur == S.lev[0]) ? 0 : (cur == S.lev[1] ? 1 : 2);       // 2: the plan's third level
       ra.rz = S.d_rz;
       for (int q = 0; q < S.npeer; ++q) {
         ra.peer_in[q] = (const double*)((char*)S.peer_base[q][li] + cur->lead * cur->esz);
@@ -1530,8 +1530,21 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
     // producer straight out of that GPU's memory (cudaIpc-mapped arenas over NVLink), gated by a
     // progress counter the neighbour bumps after each of its sweeps — no pack / NCCL / unpack and
     // ONE launch per step.  SGC_P2P=0 keeps the NCCL schedule below.
+    // the library-owned third level of the two-step passes (see below): on a multi-rank run it has to exist before the
+    // peer-memory session, which maps it on the neighbours
+    auto third_level = [&]() -> sgc_level_t {
+      if (!plan->t2_scratch && !getenv("SGC_NO_T2_SCRATCH")) {
+        std::vector<int> boxes6((size_t)a->nbox * 6);
+        for (int i = 0; i < a->nbox; ++i)
+          for (int d = 0; d < 3; ++d) { boxes6[6 * i + d] = a->boxes[i].lo[d]; boxes6[6 * i + 3 + d] = a->boxes[i].hi[d]; }
+        if (sgc_level_create(boxes6.data(), a->nbox, 1, 1, 8, a->gidx0, &plan->t2_scratch)) plan->t2_scratch = nullptr;
+      }
+      return plan->t2_scratch;
+    };
     const char* pe = getenv("SGC_P2P");
-    const bool p2p = plan->nremote > 0 && !(pe && pe[0] == '0') && comm_p2p_setup(plan, a, b) == 0 && plan->p2p.ready;
+    const bool want_p2p = plan->nremote > 0 && !(pe && pe[0] == '0');
+    sgc_level_t third = (want_p2p && heat_t2_covers(b, a)) ? third_level() : nullptr;
+    const bool p2p = want_p2p && comm_p2p_setup(plan, a, b, third) == 0 && plan->p2p.ready;
     // every rank has reached this run before any kernel that waits on a neighbour's counter starts
     if (p2p) { st = comm_stream_barrier(rt().compute); if (st) return st; }
 
@@ -1542,19 +1555,11 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
     int npass = (nstep - 2) / 2;
     const bool t2_remote_ok = plan->nremote == 0 || p2p;          // remote z faces need the peer-memory session
     bool t2 = heat_t2_covers(b, a) && (plan->t2_local || ((plan->t2_slab || plan->t2_bnd) && t2_remote_ok));
-    // an odd number of passes needs the library-owned third level (single rank: the neighbours of a peer-memory
-    // session map two arenas only); otherwise one pass fewer
+    // an odd number of passes needs the library-owned third level (with a peer-memory session: the one the
+    // neighbours have mapped); otherwise one pass fewer
     sgc_level_t scratch = nullptr;
     if (npass & 1) {
-      if (t2 && npass >= 3 && plan->nremote == 0 && !getenv("SGC_NO_T2_SCRATCH")) {
-        if (!plan->t2_scratch) {
-          std::vector<int> boxes6((size_t)a->nbox * 6);
-          for (int i = 0; i < a->nbox; ++i)
-            for (int d = 0; d < 3; ++d) { boxes6[6 * i + d] = a->boxes[i].lo[d]; boxes6[6 * i + 3 + d] = a->boxes[i].hi[d]; }
-          if (sgc_level_create(boxes6.data(), a->nbox, 1, 1, 8, a->gidx0, &plan->t2_scratch)) plan->t2_scratch = nullptr;
-        }
-        scratch = plan->t2_scratch;
-      }
+      if (t2 && npass >= 3) scratch = plan->nremote == 0 ? third_level() : (p2p ? plan->p2p.lev[2] : nullptr);
       if (!scratch) npass &= ~1;
     }
     if (plan->nremote > 0) {
@@ -1588,8 +1593,10 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
     };
     // otherwise the exchange below also orders the phases on a multi-GPU run: its receives complete only after
     // the neighbours have left their last pass, so their reads of our levels are over
-    // (single rank with no fused step left: the plain steps below start with this very exchange)
-    if (plan->nremote > 0 || s0 < nstep - 2) st = pull ? exchange_pull(cur) : sgc_exchange(cur, plan);
+    // (with no fused step left the plain steps below start with this very exchange; on a multi-GPU run their
+    // receives order the phases the same way: a boundary box is swept only after the neighbours' messages, which
+    // they send after their last pass, have arrived, and interior boxes are never read by a neighbour)
+    if (s0 < nstep - 2) st = pull ? exchange_pull(cur) : sgc_exchange(cur, plan);
     if (p2p && !st) {
       sgc_plan_s::P2P& S = plan->p2p;
       for (; s0 < nstep - 2 && !st; ++s0) {

@@ -303,16 +303,16 @@ struct sgc_plan_s {
   // the z neighbours mapped through cudaIpc, and progress counters
   struct P2P {
     bool tried = false, ready = false;
-    sgc_level_s* lev[2] = {nullptr, nullptr};
+    sgc_level_s* lev[3] = {nullptr, nullptr, nullptr};   // the two ping-pong levels + the plan's third level (or null)
     int npeer = 0;
     int peer_rank[2] = {-1, -1};
-    void* peer_base[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [peer slot][level] opened allocations
+    void* peer_base[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // [peer slot][level] opened allocations
     void* peer_flag_base[2] = {nullptr, nullptr};
     unsigned long long* d_flag = nullptr;    // this rank's counter (cudaMalloc, exported)
     unsigned int* d_err = nullptr;
     int* d_rz = nullptr;                     // [nbox][2]
     unsigned long long counter = 0;          // value last signalled
-    unsigned long long gen[2] = {0, 0};      // generations of lev[0], lev[1] (a recycled address is not the same level)
+    unsigned long long gen[3] = {0, 0, 0};   // generations of the levels (a recycled address is not the same level)
   } p2p;
   // Re-boxed step loop (sgc_device.cu: rebox_setup): a level of many small boxes (16^3, 32^3, 8^3) is
   // advanced on a library-owned pair of levels whose device fabs are 64^2-footprint unions of the user's
