@@ -90,8 +90,6 @@ def main():
              "SHARE of the step is what must agree with bench.py, not the absolute."]
     traffic = {}
     tp = os.path.join(OUT, "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
     for rep, title, key in (("r02_t2.ncu-rep", "k_heat_t2<64>: two steps per pass, C2 level (512^3 in 64^3 boxes), one launch", "t2_dram_bytes_per_launch"),
                             ("r02_stream.ncu-rep", "k_heat_stream<64,64>: one-step sweep writing the outer edge strips, C2 level", "sweep_dram_bytes_per_launch"),
                             ("r02_copy.ncu-rep", "k_copy_items: stand-alone exchange of the C2 level, x faces from the edge strips, 16-byte path", "exchange_dram_bytes_per_launch")):
