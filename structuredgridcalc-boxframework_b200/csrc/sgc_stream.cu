@@ -43,7 +43,7 @@ constexpr int kGatherWarps = 4;   // helper warps of the narrow-box fused mode (
 // Narrow-box instances have few consumer warps per CTA (one or four columns per thread): when the ring
 // is small enough two CTAs share an SM, which doubles the warps that hide shared-memory / FP64 latency.
 __host__ __device__ constexpr size_t stream_smem_bytes(int vnx, int vny, int ng, int ps, int ns, int op, int esz = 8) {
-  return (size_t)ns * ps * ((size_t)vnx * (vny + 2 * ng) + 2 * ng * (vny + 2 * ng) + (op == 1 ? (size_t)vnx * vny : 0)) * esz +
+  return (size_t)ns * ps * ((size_t)vnx * (vny + 2 * ng) + 2 * (vny + 2 * ng) + (op == 1 ? (size_t)vnx * vny : 0)) * esz +
          2 * (size_t)ns * 8;
 }
 __host__ __device__ constexpr int stream_ctas_per_sm(int vnx, int vny, int ng, int ps, int ns, int op, int esz = 8) {
@@ -106,14 +106,15 @@ k_heat_stream(const T* __restrict__ in_main, const T* __restrict__ in_xg, T* __r
   constexpr int NT = NCW * 32;                   // consumer threads
   constexpr int N1 = VNY + 2 * NG;
   constexpr int PLANE = VNX * N1;                // elements per main plane (dense rows, y ghosts included)
-  constexpr int STRIP = NG * N1;                 // elements per x-ghost strip of one plane and side
+  constexpr int STRIP = N1;                      // elements per x-ghost strip of one plane and side: the ghost column NEXT to
+                                                 // the valid ones (xg layer NG-1 of the low side, layer 0 of the high side)
   constexpr int AUXP = (OP == 1) ? VNX * VNY : 0;   // elements of the third level carried per plane (valid rows)
   constexpr int STAGE = PS * (PLANE + 2 * STRIP + AUXP);   // ring slot: planes | low strips | high strips | aux rows
   constexpr int AUX_OFF = PS * (PLANE + 2 * STRIP);
   constexpr uint32_t MAIN_BYTES = PS * PLANE * ESZ, STRIP_BYTES = PS * STRIP * ESZ, AUX_BYTES = PS * AUXP * ESZ;
   constexpr int COLS = VNX * VNY;
   constexpr int CPT = (COLS + NT - 1) / NT;      // columns per consumer thread
-  static_assert(NG == 1, "one ghost layer");
+  static_assert(NG == 1 || (NG == 2 && !PUSH && !GATHER && OP == 0), "wider ghost layers: the plain heat sweep only");
   static_assert(MAIN_BYTES % 16 == 0 && STRIP_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
   static_assert(NT % VNX == 0, "a thread keeps the same x for all its columns");
   static_assert(NS >= 3, "two stages are being read while at least one is in flight");
@@ -144,7 +145,7 @@ k_heat_stream(const T* __restrict__ in_main, const T* __restrict__ in_xg, T* __r
     if (lane == 0) {
       int slot = 0, round = 0;                   // ring slot of stage t is (t - l_begin) % NS
       long long tr = l_begin + (l_begin >= seam ? jump : 0);   // real stage index
-      const long long xfab = (long long)2 * STRIP * n2;        // xg block elements per fab
+      const long long xfab = (long long)2 * NG * STRIP * n2;   // xg block elements per fab: [side][layer][k][j]
       int pb = -1, dym = -1, dyp = -1, dzm = -1, dzp = -1;     // cached pull sources of box pb
       int rzm = -1, rzp = -1;                                  // remote z neighbours of box pb (peer memory)
       bool waited[2] = {false, false};
@@ -179,7 +180,7 @@ k_heat_stream(const T* __restrict__ in_main, const T* __restrict__ in_xg, T* __r
           const long long box = pl / n2;
           const int kz0 = (int)(pl - box * n2);
           T* dst = ring + (size_t)slot * STAGE;
-          const T* xg = in_xg + box * xfab + (long long)kz0 * STRIP;
+          const T* xg = in_xg + box * xfab + ((long long)(NG - 1) * n2 + kz0) * STRIP;      // low side, innermost layer
           if (GATHER) {
             // planes only: a ghost plane whole (from its z source), an interior plane's valid rows;
             // the gather warp fills the y-ghost rows and the x strips
@@ -253,7 +254,7 @@ k_heat_stream(const T* __restrict__ in_main, const T* __restrict__ in_xg, T* __r
             }
           }
           bulk_g2s(dst + PS * PLANE, xg, STRIP_BYTES, full + slot);
-          bulk_g2s(dst + PS * PLANE + PS * STRIP, xg + (long long)n2 * STRIP, STRIP_BYTES, full + slot);
+          bulk_g2s(dst + PS * PLANE + PS * STRIP, xg + (long long)n2 * STRIP, STRIP_BYTES, full + slot);   // high side, layer 0
         }
         if (++slot == NS) { slot = 0; ++round; }
       }
@@ -266,7 +267,7 @@ k_heat_stream(const T* __restrict__ in_main, const T* __restrict__ in_xg, T* __r
     // kGatherWarps warps take the stages round-robin; each issues all loads of its stage in one batch
     // (they are L2 round trips) before it stores them, so a stage costs one latency, spread over 4 warps.
     const int gw = warp - NCW - 1;
-    const long long fabm = (long long)PLANE * n2, xfab = (long long)2 * STRIP * n2;
+    const long long fabm = (long long)PLANE * n2, xfab = (long long)2 * NG * STRIP * n2;
     int pb = -1, dxm = -1, dxp = -1, dym = -1, dyp = -1;
     constexpr int NXH = 2 * PS * VNY;              // x-halo values of a stage: (side, plane, valid row)
     constexpr int NYH = 2 * PS * VNX;              // y-ghost values of a stage: (side, plane, x)
@@ -336,7 +337,7 @@ k_heat_stream(const T* __restrict__ in_main, const T* __restrict__ in_xg, T* __r
   const int sr0 = j0 + NG;                              // its fab-relative row
   // fused ghost fill: which faces of the box this thread's cells lie on
   const int fx = at_lo ? -1 : (at_hi ? 1 : 0);
-  const long long fab_xg = (long long)2 * STRIP * n2;
+  const long long fab_xg = (long long)2 * NG * STRIP * n2;
   T* xdst = nullptr;      // x-face destination strip of the current fab (threads on an x face only)
   // edge strips of the output level ([box][valid plane][4][VNY] = copies of columns 0, 1, VNX-2, VNX-1)
   constexpr bool XE = (VNX >= 32 && OP == 0 && MODE == 0 && sizeof(T) == 8);
@@ -447,7 +448,7 @@ static int launch_cfg(const T* in_main, const T* in_xg, T* out_main, int nstages
                       int fma, int seam, int jump, cudaStream_t s, PushArgs push = PushArgs(),
                       const T* aux_main = nullptr) {
   constexpr int E = (int)sizeof(T);
-  static_assert((PS * VNX * (VNY + 2 * NG) * E) % 16 == 0 && (PS * NG * (VNY + 2 * NG) * E) % 16 == 0, "bulk copies move multiples of 16 bytes");
+  static_assert((PS * VNX * (VNY + 2 * NG) * E) % 16 == 0 && (PS * (VNY + 2 * NG) * E) % 16 == 0, "bulk copies move multiples of 16 bytes");
   constexpr size_t smem = stream_smem_bytes(VNX, VNY, NG, PS, NS, OP, E);
   static_assert(smem <= 232448, "ring exceeds the 227 KB of shared memory a CTA can have");
   static bool configured = false;
@@ -469,8 +470,9 @@ static int launch_cfg(const T* in_main, const T* in_xg, T* out_main, int nstages
 // Returns 1 when the geometry is not covered (caller falls back to the table-driven kernel).
 int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, int a0, int a1, int b0, int b1,
                         cudaStream_t s, const PushArgs* fuse) {
-  if (!u->uniform || !unew->uniform || u->ncomp != unew->ncomp || u->ng != unew->ng || u->ng != 1) return 1;
+  if (!u->uniform || !unew->uniform || u->ncomp != unew->ncomp || u->ng != unew->ng || u->ng < 1 || u->ng > 2) return 1;
   if (u->esz != unew->esz || (u->esz != 8 && u->esz != 4)) return 1;
+  if (u->ng == 2 && (fuse || u->esz != 8)) return 1;           // two ghost layers: the plain double sweep
   // Several components: component c of fab b is the virtual fab b*ncomp + c of the plane sequence (the main
   // blocks [comp][k][j][i] and xg blocks [comp][side][k][j] of a fab follow each other).  The fused modes and
   // float levels take the plain sweep only.
@@ -505,6 +507,20 @@ int launch_heat_stream2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, in
   const double* in_main = (const double*)u->d_arena + (long long)a0 * nc * g.cs;
   const double* in_xg = (const double*)u->d_arena + u->xg_base + (long long)a0 * nc * g.xcs;
   double* out = (double*)unew->d_arena + (long long)a0 * nc * g.cs;
+  if (u->ng == 2) {
+    // levels with two ghost layers (Copier plans exist for any width, Copier.H:521-528): the 7-point sweep reads the inner
+    // layer only; same pipeline, planes of (vny + 4) rows, the x-ghost strip = the innermost column of each side
+    unew->xe_valid = 0;
+#define SGC_STREAM_CASE_G2(VX, VY, PS_, NS_, NCW_)                                                                \
+  if (vnx == VX && vny == VY && n2 % PS_ == 0)                                                                    \
+    return launch_cfg<VX, VY, 2, PS_, NS_, NCW_>(in_main, in_xg, out, (int)(planes / PS_), n2, f, fma, (int)(planesA / PS_), \
+                                                 (int)(gap / PS_), s)
+    SGC_STREAM_CASE_G2(64, 64, 1, 6, 16);
+    SGC_STREAM_CASE_G2(32, 32, 2, 10, 8);
+    SGC_STREAM_CASE_G2(16, 16, 4, 6, 8);
+#undef SGC_STREAM_CASE_G2
+    return 1;
+  }
   PushArgs pa;
   memset(&pa, 0, sizeof pa);
   if (fuse) pa = *fuse;

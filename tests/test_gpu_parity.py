@@ -728,6 +728,30 @@ def test_single_precision_and_multicomponent_sweeps(g, oracle):
             assert np.array_equal(gc, vc), (mb, c)
 
 
+def test_two_ghost_layers_streaming_and_step_loop(g, oracle):
+    """Levels with nghost = 2 (Copier plans exist for any ghost width, Copier.H:521-528): the 7-point sweep reads the
+    inner layer only — streaming instances for 64^2 / 32^2 / 16^2 boxes, the table-driven kernel otherwise — and the
+    step loop exchanges both layers every step.  Against the oracle, every cell of both levels."""
+    rng = np.random.default_rng(47)
+    for dlo, dhi, mb, per in (((0, 0, 0), (127, 63, 15), (64, 64, 8), 7), ((0, 0, 0), (63, 31, 31), (32, 32, 16), 3),
+                              ((-16, 0, 0), (15, 31, 15), (16, 16, 16), 5), ((0, 0, 0), (11, 9, 8), (6, 5, 3), 0)):
+        dbl = g.DisjointBoxLayout(g.Box(dlo, dhi), mb)
+        a, b = g.LevelData(dbl, 1, 2), g.LevelData(dbl, 1, 2)
+        u, v = rng.standard_normal(a.elems), rng.standard_normal(a.elems)
+        a.upload(u); b.upload(v)
+        g.heat_sweep(b, a, 0.2)
+        want = v.copy()
+        oracle.level_heat_sweep(dbl.boxes, 2, u, want, 0.2, 1)
+        assert np.array_equal(b.download(), want), (mb, "sweep")
+        assert np.array_equal(a.download(), u)
+        a.upload(u); b.upload(u)
+        cp = g.Copier().defineExchangeLD(a, per, 0)
+        res = g.heat_run(a, b, cp, 0.125, 5, 0)
+        want = u.copy()
+        oracle.level_heat(dlo, dhi, mb, 2, per, 0, 0.125, 5, want, 0)
+        assert np.array_equal(res.download(), want), (mb, "run")
+
+
 def test_reference_device_kats_gpuSandbox(g):
     """The reference's device-side known-answer tests restated through this library (gpuSandbox.cpp:66-151;
     its own kernels live in the application's sandbox_Cuda.cu on CudaFab / SlabFab): fab on grow((-1..2)^3, 1)
