@@ -85,6 +85,8 @@ if __name__ == "__main__":
     if what in ("exchange", "all"):
         res["exchange_C2"] = exchange_probe(512, 64)
         res["exchange_32"] = exchange_probe(512, 32)
+    if what == "c3":
+        res["rebox_C3"] = rebox_probe(512, 16)
     if what in ("rebox", "all"):
         res["rebox_C3"] = rebox_probe(512, 16)
         res["rebox_32"] = rebox_probe(512, 32)

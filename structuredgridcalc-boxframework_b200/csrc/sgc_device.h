@@ -75,7 +75,6 @@ struct CopyTable {
   int nwitem = 0, nwchunk = 0;
   long long ncell = 0, nwcell = 0;
   bool strided_reads = false;          // a good share of the cells are single elements of long rows (x faces)
-  bool mostly_big = false;             // most units belong to items of at least a chunk: the single-item kernel variant pays
   void release();
   int upload(const std::vector<CopyItem>& items, int esz = 0);   // esz 8 enables the wide class
 };

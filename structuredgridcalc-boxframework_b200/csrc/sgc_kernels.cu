@@ -32,84 +32,15 @@ __device__ __forceinline__ uint64_t ld_small_fetch<uint64_t>(const uint64_t* p) 
   return v;
 }
 
-// one unit (an element, or 16 bytes of a wide item) per thread and iteration
-template <typename T, bool SMALL_FETCH_OK, int VARIANT>
+// one unit (an element, or 16 bytes of a wide item) per thread and iteration.  Kept deliberately small (32 registers,
+// eight CTAs per SM): variants that decode a single-item chunk once and batch its eight loads, or batch the searches
+// of multi-item chunks, execute a third of the instructions but run at 72 registers and were never faster on the
+// exchange and up to 1.7x slower on tables of small items (profiles/r02_copy_variants.log) — occupancy, not instruction
+// count, is what hides this kernel's dependent loads.
+template <typename T, bool SMALL_FETCH_OK>
 __device__ __forceinline__ void copy_units(const CopyItem* __restrict__ items, const long long* __restrict__ cell_start,
                                            int it_lo, int it_hi, long long base, long long end, T* __restrict__ dst_arena,
                                            const T* __restrict__ src_arena, int small_fetch) {
-  constexpr int NIT = kCopyChunk / kCopyThreads;
-  if (VARIANT == 2 && (it_lo == it_hi || __ldg(cell_start + it_lo + 1) >= end)) {
-    const CopyItem* __restrict__ I = items + it_lo;
-    const unsigned nx = I->nx, ny = I->ny, nz = I->nz;
-    const long long dsx = I->dsx, dsy = I->dsy, dsz = I->dsz, ssx = I->ssx, ssy = I->ssy, ssz = I->ssz;
-    const long long dcs = I->dcs, scs = I->scs, dst0 = I->dst, src0 = I->src;
-    const unsigned flags = I->flags, c0 = I->c0;
-    unsigned r = (unsigned)(base - __ldg(cell_start + it_lo)) + threadIdx.x;
-    unsigned x = r % nx; r /= nx;
-    unsigned y = r % ny; r /= ny;
-    unsigned z = r % nz;
-    unsigned c = r / nz;
-    unsigned q = kCopyThreads;
-    const unsigned sx = q % nx; q /= nx;
-    const unsigned sy = q % ny; q /= ny;
-    const unsigned sz = q % nz;
-    const unsigned sc = q / nz;
-    const int n = (int)(end - base);
-#pragma unroll 2
-    for (int t = threadIdx.x; t < n; t += kCopyThreads) {
-      const unsigned dc = c0 + c;
-      if (!(dc < 32u && !((flags >> dc) & 1u)))
-        dst_arena[dst0 + c * dcs + x * dsx + y * dsy + z * dsz] = src_arena[src0 + c * scs + x * ssx + y * ssy + z * ssz];
-      x += sx; unsigned cy = x >= nx; x -= cy ? nx : 0u;
-      y += sy + cy; cy = y >= ny; y -= cy ? ny : 0u;
-      z += sz + cy; cy = z >= nz; z -= cy ? nz : 0u;
-      c += sc + cy;
-    }
-    return;
-  }
-  if (VARIANT == 1 && (it_lo == it_hi || __ldg(cell_start + it_lo + 1) >= end)) {
-    // The whole chunk lies inside ONE item (faces, planes, layout conversions: most of the bytes).  The
-    // (x, y, z, comp) coordinate of a thread's first unit is decoded once; every further unit lies
-    // kCopyThreads units on, i.e. a fixed coordinate step with carries — no division in the loop — and
-    // all loads of the chunk are issued before its stores.
-    const CopyItem* __restrict__ I = items + it_lo;
-    const unsigned nx = I->nx, ny = I->ny, nz = I->nz;
-    const long long dsx = I->dsx, dsy = I->dsy, dsz = I->dsz, ssx = I->ssx, ssy = I->ssy, ssz = I->ssz;
-    const long long dcs = I->dcs, scs = I->scs, dst0 = I->dst, src0 = I->src;
-    const unsigned flags = I->flags, c0 = I->c0;
-    unsigned r = (unsigned)(base - __ldg(cell_start + it_lo)) + threadIdx.x;
-    unsigned x = r % nx; r /= nx;
-    unsigned y = r % ny; r /= ny;
-    unsigned z = r % nz;
-    unsigned c = r / nz;
-    unsigned q = kCopyThreads;
-    const unsigned sx = q % nx; q /= nx;
-    const unsigned sy = q % ny; q /= ny;
-    const unsigned sz = q % nz;
-    const unsigned sc = q / nz;
-    const int n = (int)(end - base);
-    T v[NIT];
-    long long d[NIT];
-#pragma unroll
-    for (int k = 0; k < NIT; ++k) {
-      const unsigned dc = c0 + c;
-      const bool live = (int)threadIdx.x + k * kCopyThreads < n && !(dc < 32u && !((flags >> dc) & 1u));
-      d[k] = live ? dst0 + c * dcs + x * dsx + y * dsy + z * dsz : -1;
-      const long long s = src0 + c * scs + x * ssx + y * ssy + z * ssz;
-      if (live) {
-        if (SMALL_FETCH_OK) v[k] = (small_fetch != 0) ? ld_small_fetch(src_arena + s) : src_arena[s];
-        else v[k] = src_arena[s];
-      }
-      x += sx; unsigned cy = x >= nx; x -= cy ? nx : 0u;
-      y += sy + cy; cy = y >= ny; y -= cy ? ny : 0u;
-      z += sz + cy; cy = z >= nz; z -= cy ? nz : 0u;
-      c += sc + cy;
-    }
-#pragma unroll
-    for (int k = 0; k < NIT; ++k)
-      if (d[k] >= 0) dst_arena[d[k]] = v[k];
-    return;
-  }
 #pragma unroll 2
   for (int t = threadIdx.x; t < kCopyChunk; t += kCopyThreads) {
     const long long cell = base + t;
@@ -137,7 +68,7 @@ __device__ __forceinline__ void copy_units(const CopyItem* __restrict__ items, c
 }
 
 // CTAs [0, nwchunk) run the wide items (16-byte units, 8-byte element tables only), the others the rest.
-template <typename T, int VARIANT>
+template <typename T>
 __global__ void __launch_bounds__(kCopyThreads)
 k_copy_items(const CopyItem* __restrict__ items, const long long* __restrict__ cell_start,
              const int* __restrict__ chunk_first, T* __restrict__ dst_arena,
@@ -146,14 +77,14 @@ k_copy_items(const CopyItem* __restrict__ items, const long long* __restrict__ c
     const unsigned ch = blockIdx.x;
     const long long base = (long long)ch * kCopyChunk;
     const long long end = base + kCopyChunk < nwcell ? base + kCopyChunk : nwcell;
-    copy_units<ulonglong2, false, VARIANT>(items, cell_start, chunk_first[ch], chunk_first[ch + 1], base, end,
+    copy_units<ulonglong2, false>(items, cell_start, chunk_first[ch], chunk_first[ch + 1], base, end,
                                   reinterpret_cast<ulonglong2*>(dst_arena), reinterpret_cast<const ulonglong2*>(src_arena), 0);
     return;
   }
   const unsigned c = blockIdx.x - nwchunk;
   const long long base = nwcell + (long long)c * kCopyChunk;
   const long long end = base + kCopyChunk < ncell ? base + kCopyChunk : ncell;
-  copy_units<T, true, VARIANT>(items, cell_start, chunk_first[nwchunk + c + 1], chunk_first[nwchunk + c + 2], base, end, dst_arena,
+  copy_units<T, true>(items, cell_start, chunk_first[nwchunk + c + 1], chunk_first[nwchunk + c + 2], base, end, dst_arena,
                       src_arena, getenv_small_fetch);
 }
 
@@ -163,22 +94,13 @@ int launch_copy(const CopyTable& t, void* dst_arena, const void* src_arena, int 
   const int small_fetch = sf_env ? atoi(sf_env) : (t.strided_reads ? 1 : 0);
   if (t.nwchunk > 0 && (esz != 8 || (((uintptr_t)dst_arena | (uintptr_t)src_arena) & 15)))
     return fail(SGC_ERR_ARG, "copy table has 16-byte items but the buffers are not 16-byte aligned 8-byte arrays");
-  static const char* var_env = getenv("SGC_COPY_VARIANT");
-  // 0: per-unit decode only (32 registers, 8 CTAs per SM: best when chunks hold many small items — 16^3 / 32^3 box faces,
-  // edges, corners); 1: + single-item chunks with batched loads (72 registers: best when most units sit in items of at
-  // least a chunk — 64^3 box faces, layout conversions); 2: single-item chunks, loads not batched (A/B only)
-  const int variant = var_env ? atoi(var_env) : (t.mostly_big ? 1 : 0);
-#define SGC_COPY_LAUNCH(T, V, NW, WC)                                                                               \
-  k_copy_items<T, V><<<t.nchunk, kCopyThreads, 0, s>>>(t.d_items, t.d_cell_start, t.d_chunk_first, (T*)dst_arena,   \
-                                                       (const T*)src_arena, t.ncell, small_fetch, NW, WC)
+#define SGC_COPY_LAUNCH(T, NW, WC)                                                                                \
+  k_copy_items<T><<<t.nchunk, kCopyThreads, 0, s>>>(t.d_items, t.d_cell_start, t.d_chunk_first, (T*)dst_arena,     \
+                                                    (const T*)src_arena, t.ncell, small_fetch, NW, WC)
   switch (esz) {
-    case 8:
-      if (variant == 0) SGC_COPY_LAUNCH(uint64_t, 0, t.nwchunk, t.nwcell);
-      else if (variant == 2) SGC_COPY_LAUNCH(uint64_t, 2, t.nwchunk, t.nwcell);
-      else SGC_COPY_LAUNCH(uint64_t, 1, t.nwchunk, t.nwcell);
-      break;
-    case 4: SGC_COPY_LAUNCH(uint32_t, 1, 0, 0); break;
-    case 1: SGC_COPY_LAUNCH(uint8_t, 1, 0, 0); break;
+    case 8: SGC_COPY_LAUNCH(uint64_t, t.nwchunk, t.nwcell); break;
+    case 4: SGC_COPY_LAUNCH(uint32_t, 0, 0); break;
+    case 1: SGC_COPY_LAUNCH(uint8_t, 0, 0); break;
     default:
       return fail(SGC_ERR_UNSUPPORTED, "element size must be 1, 4 or 8 bytes");
   }
