@@ -32,6 +32,7 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
+    extra = os.environ.get("SGC_NVCC_EXTRA", "").split()        # A/B builds: e.g. SGC_NVCC_EXTRA=-DSGC_T2_PAIR
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     bdir = os.path.join(HERE, "build")
@@ -40,7 +41,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(bdir, src + ".o")
         objs.append(obj)
-        cmd = [nvcc, "-c", os.path.join(CSRC, src), "-o", obj] + NVCC_FLAGS
+        cmd = [nvcc, "-c", os.path.join(CSRC, src), "-o", obj] + NVCC_FLAGS + extra
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
