@@ -340,9 +340,12 @@ int sgc_wave_run(sgc_level_t levels[3], sgc_plan_t exchange_plan, sgc_plan_t bc_
  * (the shape of driverAdvanceIterGroup, WavePatch_Cuda.cu:352-378).  *result_in_b = 1 when the
  * last-written level is b (always nstep & 1).  With nproc > 1 each step overlaps the halo with
  * interior boxes.  The library is free to restructure the loop — fused ghost fill inside the sweep,
- * two time steps per pass over memory (uniform levels of 64x64xN boxes; periodic or physical boundaries),
- * z halos read straight out of the neighbouring GPU's memory — but on return BOTH levels hold, ghost
- * cells included, exactly the bits nstep x { exchange ; sweep } would have left (tests pin this).  */
+ * two time steps per pass over memory (uniform levels of 64x64xN boxes; periodic or physical boundaries;
+ * an odd number of passes goes through a library-owned third level), levels of many small boxes advanced
+ * on library-owned levels whose device fabs are 64x64 unions of the caller's boxes (DisjointBoxLayout with
+ * maxBoxSize 8/16/32: sgc_plan_rebox_factors), z halos read straight out of the neighbouring GPU's memory
+ * — but on return BOTH levels hold, ghost cells included, exactly the bits nstep x { exchange ; sweep }
+ * would have left (tests pin this).  The plan keeps up to three extra level arenas alive for this.        */
 int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags,
                  int nstep, int* result_in_b);
 /* Introspection: how sgc_heat_run re-boxes this plan's level for its step loop (levels of many small
