@@ -711,6 +711,36 @@ static int ensure_valid_table(sgc_level_s* l) {
   return st ? st : l->conv_valid_in.upload(w, l->esz);
 }
 
+// Valid cells of a UNIFORM level straight between a host buffer [box][comp][k][j][i] and the arena, by the copy
+// engine alone: in the split-x layout the valid rows of one fab plane are ONE contiguous block (vny rows of mx
+// elements) at the plane pitch mx*n1, planes repeat at that pitch, (box, comp) blocks at cs — exactly a pitched 3-D
+// copy (x = the plane's valid block in bytes, y = the valid planes, z = box*ncomp + comp).  No staging buffer, no
+// conversion kernel, nothing that competes with the sweeps for SMs or HBM beyond the bytes themselves.  (The e2e pipeline
+// of bench.py did not get faster with it — 27.1 ms per C2 batch either way, against 23.6 ms for the two copies alone and
+// 24.4 ms for the sweeps alone: with the sweeps running the copy engines get ~39 instead of 45 GB/s per direction, and
+// that, not a conversion kernel, is what the pipeline waits for.)  Returns 1 when the level is not uniform (the item
+// tables serve it).
+static int valid_cells_dma(sgc_level_s* l, void* host, bool to_device, cudaStream_t s) {
+  if (!l->uniform || l->nbox == 0 || getenv("SGC_NO_DMA3D")) return 1;
+  const FabGeom& g = l->geom[0];
+  const size_t row = (size_t)g.mx * g.vn[1] * l->esz;                 // one plane's valid block
+  const size_t pitch = (size_t)g.mx * g.n[1] * l->esz;                // plane pitch in the arena
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof p);
+  cudaPitchedPtr hp = make_cudaPitchedPtr(host, row, row, (size_t)g.vn[2]);
+  cudaPitchedPtr dp = make_cudaPitchedPtr(l->d_arena, pitch, pitch, (size_t)g.n[2]);
+  const cudaPos hpos = make_cudaPos(0, 0, 0);
+  const cudaPos dpos = make_cudaPos((size_t)l->ng * g.mx * l->esz, (size_t)l->ng, 0);     // skip the ghost rows / planes
+  p.srcPtr = to_device ? hp : dp;
+  p.dstPtr = to_device ? dp : hp;
+  p.srcPos = to_device ? hpos : dpos;
+  p.dstPos = to_device ? dpos : hpos;
+  p.extent = make_cudaExtent(row, (size_t)g.vn[2], (size_t)l->nbox * l->ncomp);
+  p.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  SGC_CUDA(cudaMemcpy3DAsync(&p, s));
+  return 0;
+}
+
 // The reverse of the plot gather: the valid cells of every fab from a dense host buffer [box][comp][k][j][i];
 // ghost cells keep their contents (the next exchange / BC fill writes them).  9-27 % fewer bytes over PCIe than
 // the whole-fab copyToDevice of BaseFab.cpp:427-483 (66^3 -> 64^3: 8.8 %; 18^3 -> 16^3: 30 %).
@@ -718,11 +748,13 @@ int sgc_level_upload_valid(sgc_level_t l, const void* host) {
   SGC_REQUIRE_RT();
   if (!l || !host) return fail(SGC_ERR_ARG, "sgc_level_upload_valid: bad argument");
   const size_t bytes = (size_t)sgc_level_valid_elems(l) * l->esz;
-  int st = ensure_valid_table(l);
+  level_written(l);
+  int st = valid_cells_dma(l, const_cast<void*>(host), true, rt().compute);
+  if (st <= 0) return st;
+  st = ensure_valid_table(l);
   if (!st) st = ensure_stage(bytes);
   if (st) return st;
   SGC_CUDA(cudaMemcpyAsync(rt().d_stage, host, bytes, cudaMemcpyHostToDevice, rt().compute));
-  level_written(l);
   return launch_copy(l->conv_valid_in, l->d_arena, rt().d_stage, l->esz, rt().compute);
 }
 
@@ -730,18 +762,23 @@ int sgc_level_upload_valid_async(sgc_level_t l, const void* host, sgc_stream_t x
   SGC_REQUIRE_RT();
   if (!l || !host || !x) return fail(SGC_ERR_ARG, "sgc_level_upload_valid_async: bad argument");
   const size_t bytes = (size_t)sgc_level_valid_elems(l) * l->esz;
-  int st = ensure_valid_table(l);
+  level_written(l);
+  int st = valid_cells_dma(l, const_cast<void*>(host), true, x->s);
+  if (st <= 0) return st;
+  st = ensure_valid_table(l);
   if (!st) st = stream_stage(x, bytes);
   if (st) return st;
   SGC_CUDA(cudaMemcpyAsync(x->d_stage, host, bytes, cudaMemcpyHostToDevice, x->s));
-  level_written(l);
   return launch_copy(l->conv_valid_in, l->d_arena, x->d_stage, l->esz, x->s);
 }
 
 int sgc_level_download_valid(sgc_level_t l, void* host) {
   SGC_REQUIRE_RT();
   if (!l || !host) return fail(SGC_ERR_ARG, "sgc_level_download_valid: bad argument");
-  int st = ensure_valid_table(l);
+  int st = valid_cells_dma(l, host, false, rt().compute);
+  if (st < 0) return st;
+  if (st == 0) { SGC_CUDA(cudaStreamSynchronize(rt().compute)); return 0; }
+  st = ensure_valid_table(l);
   if (!st) st = ensure_stage((size_t)sgc_level_valid_elems(l) * l->esz);
   if (!st) st = launch_copy(l->conv_valid, rt().d_stage, l->d_arena, l->esz, rt().compute);
   if (st) return st;
@@ -754,7 +791,13 @@ int sgc_level_download_valid_async(sgc_level_t l, void* host, sgc_stream_t x, sg
   SGC_REQUIRE_RT();
   if (!l || !host || !x) return fail(SGC_ERR_ARG, "sgc_level_download_valid_async: bad argument");
   const size_t bytes = (size_t)sgc_level_valid_elems(l) * l->esz;
-  int st = ensure_valid_table(l);
+  int st = valid_cells_dma(l, host, false, x->s);
+  if (st < 0) return st;
+  if (st == 0) {           // the copy engine reads the level itself: "gathered" = the copy has finished
+    if (gathered) SGC_CUDA(cudaEventRecord(gathered->ev, x->s));
+    return 0;
+  }
+  st = ensure_valid_table(l);
   if (!st) st = stream_stage(x, bytes);
   if (!st) st = launch_copy(l->conv_valid, x->d_stage, l->d_arena, l->esz, x->s);
   if (st) return st;
