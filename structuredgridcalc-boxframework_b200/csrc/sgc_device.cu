@@ -1688,8 +1688,12 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
 
   // ---- plain schedule.  "split": halo in flight while the boxes without remote items sweep, then
   // the boundary layers (two box ranges, one launch); otherwise exchange, then one sweep.
+  // (after a fused phase only the last two or three steps are left: there one whole-level sweep behind a complete
+  // exchange beats the split — 25.55 against 25.85 ms per 100 steps at N = 2 — so the split is for runs that are
+  // plain from the first step)
+  const bool split_here = split && !fused;
   for (int s = s0; s < nstep; ++s) {
-    if (split) {
+    if (split_here) {
       st = sgc_exchange_begin(cur, plan);
       if (!st) st = sgc_heat_sweep_range(nxt, cur, f, flags, b0, b1);
       if (!st) st = sgc_exchange_end(cur, plan);
