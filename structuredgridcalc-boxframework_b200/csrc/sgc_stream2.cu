@@ -9,7 +9,8 @@
 // neighbouring boxes — is recomputed with the same operations in the same order from the same
 // inputs.
 //
-// Per box the CTA marches along z through VZ+4 "virtual planes" z = -2 .. VZ+1.  For every virtual
+// Per box the CTA marches DOWN along z through VZ+4 "virtual planes" l = 0 .. VZ+3, i.e. z = VZ+1 .. -2 (why
+// downwards: see heat_zhalf below).  For every virtual
 // plane a TILE of level t is assembled in a ring slot — entirely from VALID cells (ghost cells are
 // not read where a neighbour exists, so no exchange is needed between the two steps or between passes):
 //     rows y = -2..V+1 of the V valid columns      (own valid rows + 2 rows of each y neighbour)
@@ -21,11 +22,11 @@
 //   exchanged ghost cells instead — see the comment at the producer roles.
 // All NCW warps are consumers (thread = one x and CPT consecutive rows, all state in registers);
 // six of them also bring in one piece of each tile, the last 4V/32 warps also compute the flanks:
-//   stage 1: t+1 on plane z-1 for the V x V cells and for the four 1-cell-wide flanks (x = -1, V and
-//            y = -1, V) — the values the x / y neighbours would have exchanged.  Results go to
-//            registers (z neighbours of stage 2) and to one of two t+1 plane buffers in shared
-//            memory (x / y neighbours of stage 2).
-//   stage 2: t+2 on plane z-2 from the t+1 planes z-3, z-2, z-1; stored as dense rows.
+//   stage 1: when the tile of plane z arrives, t+1 on plane z+1 for the V x V cells and for the four
+//            1-cell-wide flanks (x = -1, V and y = -1, V) — the values the x / y neighbours would have
+//            exchanged.  Results go to registers (z neighbours of stage 2) and to one of two t+1 plane
+//            buffers in shared memory (x / y neighbours of stage 2).
+//   stage 2: t+2 on plane z+2 from the t+1 planes z+3, z+2, z+1; stored as dense rows.
 //   One __syncthreads() per plane orders the t+1 buffer hand-over between the warps.
 // EDGE STRIPS (xe): a per-level side array [box][kz][4][V] holding copies of the box's own columns
 // x = 0, 1, V-2, V-1, written by stage 2 straight from the result registers (and built once per
@@ -37,10 +38,13 @@
 // for the one-step sweep; the algorithmic figure stays 16 B per cell-update.
 //
 // Instances: V = 64 (16 warps, 8 rows per thread, one CTA per SM), V = 32 (8 warps, 4 rows per thread, three
-// CTAs per SM) and, on request only, V = 16 (4 warps, 2 rows per thread: slower than the one-step sweep).  The V = 64 kernel uses the whole register file (128 x 512) without spilling and is bound by instruction
-// issue / FP64 latency, not HBM; its speed is sensitive to anything that costs a register (DESIGN.md
-// §4.1d has the history; profiles/micro/ab.sh times variants on one GPU).
+// CTAs per SM) and, on request only, V = 16 (4 warps, 2 rows per thread: slower than the one-step sweep).
+// The V = 64 kernel uses the whole register file (128 x 512) without spilling and is bound by dependency latency
+// (FP64 chains, shared-memory loads, the per-plane barrier) with four warps per scheduler, not by HBM; its speed
+// is sensitive to anything that costs a register or lengthens the serial path from the barrier to the first row
+// (DESIGN.md §4.1d has the history; profiles/micro/ab_t2_round2b.sh times variants on one GPU).
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -49,14 +53,23 @@
 
 namespace sgc {
 
+// The reference's update, association of its loop: ((u[+e] - 2u) + u[-e]) per direction, x -> y -> z, then
+// u + f*S.  2u is exact in binary floating point, so fma(-2, u, p) rounds p - 2u ONCE: the same bits as the
+// reference's multiply-then-subtract (short of an overflow of 2u), one FP64 instruction less per update.
+//
+// The z term is formed in two parts, which is why the march goes DOWN: zh = u[+e] - 2u needs the plane ABOVE,
+// the value a column has held in a register since it arrived two tiles ago; the plane BELOW (u[-e]) — the
+// arriving tile for stage 1, the fresh stage-1 result for stage 2 — is only added at the end.  The held value
+// is therefore dead before the new one is needed and the new one is born in its register.  Marching upwards
+// both are operands of the same expression, every new value lands in a different register from the one it
+// replaces, and the compiler rotates 32 doubles back with register moves on every second plane.
+__device__ __forceinline__ double heat_zhalf(double c, double zabove) { return __fma_rn(-2.0, c, zabove); }
 template <bool FMA>
-__device__ __forceinline__ double heat_update(double c, double xm, double xp, double ym, double yp, double zm, double zp,
+__device__ __forceinline__ double heat_finish(double c, double xm, double xp, double ym, double yp, double zh, double zbelow,
                                               double f) {
-  // association of the reference loop: ((u[+e] - 2u) + u[-e]) per direction, x -> y -> z, then u + f*S
-  const double twoc = __dmul_rn(2.0, c);
-  const double tx = sd2(xp, twoc, xm);
-  const double ty = sd2(yp, twoc, ym);
-  const double tz = sd2(zp, twoc, zm);
+  const double tx = __dadd_rn(__fma_rn(-2.0, c, xp), xm);
+  const double ty = __dadd_rn(__fma_rn(-2.0, c, yp), ym);
+  const double tz = __dadd_rn(zh, zbelow);
   const double S = __dadd_rn(__dadd_rn(tx, ty), tz);
   return FMA ? __fma_rn(f, S, c) : __dadd_rn(c, __dmul_rn(f, S));
 }
@@ -140,11 +153,21 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   // S = source box of the current tiles (bit 30 remote, 29 peer slot, 28 z face missing), N = this role's
   // neighbour of S (BND: -1 = missing), ct = BND corner role: where the lane's corner cell comes from
   int Sa = -1, Na = 0, cta = 0, Sb = -1, Nb = 0, ctb = 0;
+#ifdef SGC_T2_RUNSRC
+  // periodic 64^2 instance: a role's source address of the previous tile; inside a source box consecutive tiles lie
+  // one fab plane (one strip plane) apart, so only the tiles where the source box changes form it from scratch
+  constexpr bool kRunSrc = !BND && V >= 64;
+#else
+  constexpr bool kRunSrc = false;
+#endif
+  const double* Ra = nullptr;
+  const double* Rb = nullptr;
   unsigned waited = 0;                // bit per peer slot
-  auto issue = [&](int slot, int tbox, int tl, const int role, int& S, int& N, int& ct) {   // tile = virtual plane tl of box tbox
-    const int z = tl - 2;
+  auto issue = [&](int slot, int tbox, int tl, const int role, int& S, int& N, int& ct, const double*& R) {   // tile = virtual plane tl of box tbox
+    const int z = vz + 1 - tl;                             // the march goes down
     const int cls = z < 0 ? 0 : (z >= vz ? 2 : 1);
-    if (S < 0 || tl == 0 || tl == 2 || tl == vz + 2) {    // first tile, or the source box changes here
+    const bool fresh = S < 0 || tl == 0 || tl == 2 || tl == vz + 2;
+    if (fresh) {    // first tile, or the source box changes here
       if (cls == 1) S = tbox;
       else {
         S = __ldg(a.nbr + (size_t)tbox * 27 + (cls == 0 ? 4 : 22));
@@ -195,10 +218,17 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
     const double* g1 = !BND ? nullptr : (!rem ? a.ghost[1] : a.peer_ghost[ps1 ? 1 : 0][1]);
     const double* base = zmiss ? ((tl == 1 || tl == vz + 2) ? g0 : g1)
                                : (!rem ? a.in_level : (ps1 ? a.peer_in[1] : a.peer_in[0]));
+    if (kRunSrc) {
+      if (fresh) {
+        if (role == 3 || role == 4) R = base + a.xe_in + ((long long)N * vz + kz) * (4 * V) + (role == 3 ? 2 * V : 0);
+        else R = base + N * fabm + prow + (role == 1 ? (V - 2) * V : 0) +
+                 (role == 5 ? ((lane & 2) ? 0 : V - 1) * V + ((lane & 1) ? 0 : V - 1) : 0);
+      } else R -= (role == 3 || role == 4) ? 4 * V : FABP;
+    }
     if (role == 5) {
       if (lane < 4) {
         const bool xh = lane & 1, yh = lane & 2;
-        const double* src = base + N * fabm + prow + (long long)(yh ? 0 : V - 1) * V + (xh ? 0 : V - 1);
+        const double* src = kRunSrc ? R : base + N * fabm + prow + (long long)(yh ? 0 : V - 1) * V + (xh ? 0 : V - 1);
         if (BND && ct == 1) src = g0 + N * fabm + ((long long)fp * N1 + (yh ? N1 - 1 : 0)) * V + (xh ? 0 : V - 1);
         if (BND && ct == 2)
           src = g0 + a.xg_base + (long long)N * (2 * N1 * (vz + 2)) + ((long long)((xh ? 1 : 0) * (vz + 2) + fp)) * N1 + 1 +
@@ -239,13 +269,13 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
       if (role == 0) {
         if (BND) mbar_expect_tx(full + slot, V * V * 8u);
         else mbar_expect_tx(full + slot, TILE_BYTES);             // this warp's arrival + the tile's byte count
-        bulk_g2s(dst + 2 * V, base + N * fabm + prow, V * V * 8u, full + slot);                           // rows 0..V-1
+        bulk_g2s(dst + 2 * V, kRunSrc ? R : base + N * fabm + prow, V * V * 8u, full + slot);             // rows 0..V-1
       } else if (role == 1 || role == 2) {
         const bool hi = role == 2;
         if (BND) mbar_expect_tx_only(full + slot, 2 * V * 8u);
         if (!BND || N >= 0) {
-          if (!hi) bulk_g2s(dst, base + N * fabm + prow + (long long)(V - 2) * V, 2 * V * 8u, full + slot);   // rows -2,-1
-          else bulk_g2s(dst + (V + 2) * V, base + N * fabm + prow, 2 * V * 8u, full + slot);                  // rows V,V+1
+          if (!hi) bulk_g2s(dst, kRunSrc ? R : base + N * fabm + prow + (long long)(V - 2) * V, 2 * V * 8u, full + slot);   // rows -2,-1
+          else bulk_g2s(dst + (V + 2) * V, kRunSrc ? R : base + N * fabm + prow, 2 * V * 8u, full + slot);    // rows V,V+1
         } else {
           // no y neighbour: the ghost row of S in the level-t ghosts, and the level-t+1 ghosts in the outer row
           const long long ro = (long long)(S & 0x0fffffff) * fabm + ((long long)fp * N1 + (hi ? N1 - 1 : 0)) * V;
@@ -253,7 +283,7 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
           bulk_g2s(dst + (hi ? (V + 3) * V : 0), g1 + ro, V * 8u, full + slot);
         }
       } else {
-        const double* e = base + a.xe_in + ((long long)N * vz + kz) * (4 * V);
+        const double* e = kRunSrc ? R - (role == 3 ? 2 * V : 0) : base + a.xe_in + ((long long)N * vz + kz) * (4 * V);
         if (role == 3) {
           bulk_g2s(dst + E(0), e + 2 * V, V * 8u, full + slot);     // x = -2  <- x neighbour's column V-2
           bulk_g2s(dst + E(1), e + 3 * V, V * 8u, full + slot);     // x = -1  <- column V-1
@@ -267,8 +297,8 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   };
   // a warp's role(s) for one tile
   auto issue_roles = [&](int slot, int tbox, int tl) {
-    if (warp < NROLE) issue(slot, tbox, tl, warp, Sa, Na, cta);
-    if (NCW < NROLE && warp + NCW < NROLE) issue(slot, tbox, tl, warp + NCW, Sb, Nb, ctb);
+    if (warp < NROLE) issue(slot, tbox, tl, warp, Sa, Na, cta, Ra);
+    if (NCW < NROLE && warp + NCW < NROLE) issue(slot, tbox, tl, warp + NCW, Sb, Nb, ctb, Rb);
   };
   {
     const int b0 = l_begin / VP, l0 = l_begin - b0 * VP;
@@ -277,9 +307,27 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   }
 
   // ---------------- flank role (the last FW warps): one cell of the x / y flanks per thread ----------------
-  // warp-uniform m = 0..3: x flanks (side m>>1, y = (m&1)*32 + lane); m = 4..7: y flanks (side, x likewise)
   const bool flank = warp >= NCW - FW;
   double hA = 0.0, hB = 0.0;          // the flank cell at the two latest planes of level t (roles alternate)
+  // tile offsets of the flank cell and its four in-plane neighbours.  Flank cell number
+  // (warp - first flank warp) * 32 + lane: side 0..3 = x = -1, x = V, y = -1, y = V; position p along it
+  auto flank_offsets = [&](int& hc, int& hxm, int& hxp, int& hym, int& hyp, int& side, int& p) {
+    const int fidx = (warp - (NCW - FW)) * 32 + lane;
+    side = V >= 32 ? ((warp - (NCW - FW)) * 32) / V : fidx / V;      // warp-uniform for V >= 32
+    p = V >= 32 ? ((warp - (NCW - FW)) * 32) % V + lane : fidx % V;
+    if (side == 0)      { hc = E(1) + p; hxm = E(0) + p; hxp = (p + 2) * V; hym = hc - 1; hyp = hc + 1; }             // x = -1
+    else if (side == 1) { hc = E(2) + p; hxm = (p + 2) * V + V - 1; hxp = E(3) + p; hym = hc - 1; hyp = hc + 1; }     // x = V
+    else if (side == 2) { hc = V + p; hym = p; hyp = 2 * V + p;                                                       // y = -1
+                      hxm = p > 0 ? hc - 1 : E(1) - 1; hxp = p < V - 1 ? hc + 1 : E(2) - 1; }
+    else            { hc = (V + 2) * V + p; hym = (V + 1) * V + p; hyp = (V + 3) * V + p;                         // y = V
+                      hxm = p > 0 ? hc - 1 : E(1) + V; hxp = p < V - 1 ? hc + 1 : E(2) + V; }
+  };
+  // Per-thread constants of the plane loop.  What lies between the per-plane barrier and a warp's first row is
+  // serial latency every warp pays 68 times per box, so the 64^2 instance keeps these in registers across the
+  // loop (kKeep); the 32^2 / 16^2 instances (80 / 64 registers per thread) would spill and re-derive them.
+  constexpr bool kKeep = V >= 64;
+  int hc0 = 0, hxm0 = 0, hxp0 = 0, hym0 = 0, hyp0 = 0, side0 = 0, p0 = 0;
+  if (kKeep && flank) flank_offsets(hc0, hxm0, hxp0, hym0, hyp0, side0, p0);
 
   // ---------------- regular role (every thread): x = xi, rows y0 .. y0+CPT-1 ----------------
   const int xi = tid % V, y0 = (tid / V) * CPT;
@@ -291,6 +339,11 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   int oxm0 = xi == 0 ? E(1) + y0 : oC0 - 1, sxm = xi == 0 ? 8 : V * 8;
   int oxp0 = xi == V - 1 ? E(2) + y0 : oC0 + 1, sxp = xi == V - 1 ? 8 : V * 8;
   asm volatile("" : "+r"(sxm), "+r"(sxp));
+  // edge-strip index of this thread's column (-1: none), opaque and therefore kept in a register: left to itself
+  // the compiler re-derives it from the thread index on every plane — through a JUMP TABLE (a constant-bank load
+  // and an indirect branch in all 16 warps; hoisting it took 5 % off the launch)
+  int xs = xi == 0 ? 0 : (xi == 1 ? 1 : (xi == V - 2 ? 2 : (xi == V - 1 ? 3 : -1)));
+  asm volatile("" : "+r"(xs));
   // Column state, all in registers: level t at the two latest planes (tA / tB) and level t+1 at the two
   // latest planes (uA / uB).  The roles "newest / previous" alternate from plane to plane — the loop
   // below is unrolled by two so that no value is ever moved between registers.
@@ -299,15 +352,34 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   for (int m = 0; m < CPT; ++m) tA[m] = tB[m] = uA[m] = uB[m] = 0.0;
   const double f = a.f;
   int box = l_begin / VP, l = l_begin - box * VP;
+  // kKeep: running bases of the current box in the output level (its main block / its edge strips, at this
+  // thread's column and first row), advanced when the box changes instead of multiplied out of the box index
+  double* obox = a.out_level + (kKeep ? box * fabm + (oC0 + (N1 - 1) * V) : 0);
+  double* ebox = a.out_level + a.xe_out + (kKeep ? (long long)box * vz * (4 * V) + (oC0 / V - 2) : 0);
   const int n_iter = s_end - l_begin, lead = s_begin - l_begin;
 
-  // One plane: tile i arrives as the z+1 plane of stage 1.  X = level t at the previous plane (centre of
-  // stage 1), Y = the plane before (overwritten with the arriving plane); U = level t+1 at the previous
-  // plane (centre of stage 2), W = the plane before (overwritten with the stage-1 result).
+  // One plane: tile i arrives as the plane BELOW stage 1's.  X = level t at the previous plane (centre of
+  // stage 1), Y = the plane before, i.e. above (replaced by the arriving plane); U = level t+1 at the previous
+  // plane (centre of stage 2), W = the plane before (replaced by the stage-1 result).
+#ifdef SGC_T2_DIAG
+  // diagnostic build (profiles/micro/ab_t2_round2b.sh): cycles each warp of one CTA waits for the tile and at the
+  // per-plane barrier — the warps that wait least at the barrier are the ones the others wait for
+  long long diag_tile = 0, diag_bar = 0;
+  const long long diag_t0 = clock64();
+#endif
   auto plane = [&](int i, double (&X)[CPT], double (&Y)[CPT], double (&U)[CPT], double (&W)[CPT], double& hX, double& hY) {
     const int slot = i & (NS - 1);
+#ifdef SGC_T2_DIAG
+    const long long d0 = clock64();
+    mbar_wait(full + slot, (i / NS) & 1u);
+    const long long d1 = clock64();
+    __syncthreads();
+    const long long d2 = clock64();
+    diag_tile += d1 - d0; diag_bar += d2 - d1;
+#else
     mbar_wait(full + slot, (i / NS) & 1u);
     __syncthreads();                 // t+1 buffer hand-over; every warp has left tile i-2 and t+1 plane i-3
+#endif
     const bool more = i + 2 < n_iter;
     if (more) issue_roles((i + 2) & (NS - 1), l + 2 >= VP ? box + 1 : box, l + 2 >= VP ? l + 2 - VP : l + 2);
     const double* __restrict__ C = ring + (size_t)slot * SLOT;
@@ -319,22 +391,12 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
     double* __restrict__ Tw = t1 + (par ^ 1) * T1SZ - V;          // virtual plane v-1 (written now)
     const double* __restrict__ Tr = t1 + par * T1SZ - V;          // virtual plane v-2 (written last iteration)
     if (flank) {
-      // tile offsets of the flank cell and its four in-plane neighbours (a handful of integer
-      // instructions per plane; keeping them in registers would cost more than recomputing)
-      // flank cell number (warp - first flank warp) * 32 + lane: side 0..3 = x = -1, x = V, y = -1, y = V; position p along it
-      const int fidx = (warp - (NCW - FW)) * 32 + lane;
-      const int side = V >= 32 ? ((warp - (NCW - FW)) * 32) / V : fidx / V;      // warp-uniform for V >= 32
-      const int p = V >= 32 ? ((warp - (NCW - FW)) * 32) % V + lane : fidx % V;
-      int hc, hxm, hxp, hym, hyp;
-      if (side == 0)      { hc = E(1) + p; hxm = E(0) + p; hxp = (p + 2) * V; hym = hc - 1; hyp = hc + 1; }             // x = -1
-      else if (side == 1) { hc = E(2) + p; hxm = (p + 2) * V + V - 1; hxp = E(3) + p; hym = hc - 1; hyp = hc + 1; }     // x = V
-      else if (side == 2) { hc = V + p; hym = p; hyp = 2 * V + p;                                                       // y = -1
-                        hxm = p > 0 ? hc - 1 : E(1) - 1; hxp = p < V - 1 ? hc + 1 : E(2) - 1; }
-      else            { hc = (V + 2) * V + p; hym = (V + 1) * V + p; hyp = (V + 3) * V + p;                         // y = V
-                        hxm = p > 0 ? hc - 1 : E(1) + V; hxp = p < V - 1 ? hc + 1 : E(2) + V; }
-      const double zp = C[hc];
+      int hc = hc0, hxm = hxm0, hxp = hxp0, hym = hym0, hyp = hyp0, side = side0, p = p0;
+      if (!kKeep) flank_offsets(hc, hxm, hxp, hym, hyp, side, p);
+      const double zh = heat_zhalf(hX, hY);                       // the held plane is consumed here ...
+      const double zp = C[hc];                                    // ... and the arriving one may take its register
       if (do1) {
-        double r = heat_update<FMA>(hX, P[hxm], P[hxp], P[hym], P[hyp], hY, zp, f);
+        double r = heat_finish<FMA>(hX, P[hxm], P[hxp], P[hym], P[hyp], zh, zp, f);
         if (BND) {
           // no neighbour on this flank's side: the "flank" is this box's ghost cell; its level-t+1 value was
           // brought in the slot of the outer halo layer
@@ -353,55 +415,73 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
       // output plane inside the fab's valid region.  While the stages are being primed (do2 false) the
       // stage-2 values are meaningless: they go to a scratch plane and a spare strip plane behind the edge
       // strips, which keeps the stores free of branches.
-      const int kz = l - 4;
+      const int kz = vz + 3 - l;                                  // output plane: two virtual planes behind the arriving tile
       // (xi, y0) of fab plane kz: fab-relative offset = tile offset + (N1 - 1) * V
-      double* __restrict__ po = do2 ? a.out_level + box * fabm + (long long)kz * FABP + (oC0 + (N1 - 1) * V)
-                                    : a.out_level + a.dump + (oC0 - 2 * V);
-      // BND: a missing z face: level t+1 on the ghost plane below / above the box is not computed but is the
+      double* __restrict__ po =
+          do2 ? (kKeep ? obox + (long long)kz * FABP : obox + box * fabm + (long long)kz * FABP + (oC0 + (N1 - 1) * V))
+              : a.out_level + a.dump + (oC0 - 2 * V);
+      // BND: a missing z face: level t+1 on the ghost plane above / below the box is not computed but is the
       // ghost plane of the level-t+1 ghosts, which arrived as the tile of the outer halo plane: it sits in
-      // Y (plane z = -2, read two planes ago) resp. in the arriving tile (plane z = vz+1)
-      bool ovr_lo = false, ovr_hi = false;
+      // Y (plane z = vz+1, read two planes ago: l == 2) resp. in the arriving tile (plane z = -2: l == vz+3)
+      bool ovr_held = false, ovr_arriving = false;
       if (BND && (l == 2 || l == vz + 3)) {
-        const bool hi = l != 2;
-        const bool miss = __ldg(a.nbr + (size_t)box * 27 + (hi ? 22 : 4)) < 0 && !(a.rz && __ldg(a.rz + 2 * box + (hi ? 1 : 0)) >= 0);
-        ovr_lo = miss && !hi; ovr_hi = miss && hi;
+        const bool top = l == 2;                                  // the march starts above the box
+        const bool miss = __ldg(a.nbr + (size_t)box * 27 + (top ? 22 : 4)) < 0 && !(a.rz && __ldg(a.rz + 2 * box + (top ? 1 : 0)) >= 0);
+        ovr_held = miss && top; ovr_arriving = miss && !top;
       }
-      const int xq = oC0 & (V - 1);                               // = xi; edge-strip index of this column, if any
-      const int xs = xq == 0 ? 0 : (xq == 1 ? 1 : (xq == V - 2 ? 2 : (xq == V - 1 ? 3 : -1)));
-      const long long eplane = do2 ? (long long)box * vz + kz : a.xe_spare_plane;
-      double* __restrict__ pe = a.out_level + a.xe_out + (eplane * 4 + (xs < 0 ? 0 : xs)) * V + (oC0 / V - 2);
+      // edge strips of the output plane: strip xs of this thread's column, if it is one of the four
+      double* __restrict__ pe =
+          (do2 ? (kKeep ? ebox + (long long)kz * (4 * V) : ebox + ((long long)box * vz + kz) * (4 * V) + (oC0 / V - 2))
+               : a.out_level + a.xe_out + a.xe_spare_plane * (4 * V) + (oC0 / V - 2)) + (xs < 0 ? 0 : xs) * V;
       const double yfirst = P[oC0 - V], ylast = P[oC0 + CPT * V];
       const double yfirst1 = Tr[oC0 - V], ylast1 = Tr[oC0 + CPT * V];
       const uint32_t pxm = smem_u32(P + oxm0), pxp = smem_u32(P + oxp0);      // x neighbours of row y0, level t
       const uint32_t qxm = smem_u32(Tr + oxm0), qxp = smem_u32(Tr + oxp0);    // and level t+1
-      // the loads of the next column are issued before the arithmetic of this one (software prefetch)
-      double zpN = C[oC0], xmN = lds64(pxm), xpN = lds64(pxp);
+      // Row m's held values are consumed FIRST (zh = Y - 2X, wh = W - 2U) and only then replaced — Y[m] by the
+      // arriving plane's value, W[m] by the stage-1 result — so each new value is born in the register of the
+      // value it replaces.  Row m+1's zh, arriving value and x neighbours are formed / requested before the
+      // arithmetic of row m (software prefetch).
+      double zhN = heat_zhalf(X[0], Y[0]);
+      const double y0old = BND ? Y[0] : 0.0;
+      Y[0] = C[oC0];
+      double xmN = lds64(pxm), xpN = lds64(pxp), yoldN = y0old;
       double oprev = 0.0;
 #pragma unroll
       for (int m = 0; m < CPT; ++m) {
-        const double zp = zpN, xm = xmN, xp = xpN;
-        if (m < CPT - 1) { zpN = C[oC0 + (m + 1) * V]; xmN = lds64(pxm + (m + 1) * sxm); xpN = lds64(pxp + (m + 1) * sxp); }
-        double r1 = heat_update<FMA>(X[m], xm, xp, m > 0 ? X[m - 1] : yfirst, m < CPT - 1 ? X[m + 1] : ylast,
-                                     Y[m], zp, f);
-        if (BND) r1 = ovr_lo ? Y[m] : (ovr_hi ? zp : r1);
-        Y[m] = zp;
-        Tw[oC0 + m * V] = r1;
+        const double zh = zhN, xm = xmN, xp = xpN, yold = yoldN;
+        if (m < CPT - 1) {
+          zhN = heat_zhalf(X[m + 1], Y[m + 1]);
+          if (BND) yoldN = Y[m + 1];
+          Y[m + 1] = C[oC0 + (m + 1) * V];
+          xmN = lds64(pxm + (m + 1) * sxm);
+          xpN = lds64(pxp + (m + 1) * sxp);
+        }
+        const double wh = heat_zhalf(U[m], W[m]);
+        W[m] = heat_finish<FMA>(X[m], xm, xp, m > 0 ? X[m - 1] : yfirst, m < CPT - 1 ? X[m + 1] : ylast, zh, Y[m], f);
+        if (BND) W[m] = ovr_held ? yold : (ovr_arriving ? Y[m] : W[m]);
+        Tw[oC0 + m * V] = W[m];
         // stage 2
         const double xm1 = lds64(qxm + m * sxm), xp1 = lds64(qxp + m * sxp);
-        const double o = heat_update<FMA>(U[m], xm1, xp1, m > 0 ? U[m - 1] : yfirst1, m < CPT - 1 ? U[m + 1] : ylast1,
-                                          W[m], r1, f);
-        W[m] = r1;
+        const double o = heat_finish<FMA>(U[m], xm1, xp1, m > 0 ? U[m - 1] : yfirst1, m < CPT - 1 ? U[m + 1] : ylast1,
+                                          wh, W[m], f);
         po[m * V] = o;
         // edge strips: two rows per 16-byte store (only the four edge columns of 64 store at all)
         if (m & 1) { if (xs >= 0) *reinterpret_cast<double2*>(pe + m - 1) = make_double2(oprev, o); } else oprev = o;
       }
     }
-    if (++l == VP) { l = 0; ++box; }
+    if (++l == VP) {
+      l = 0; ++box;
+      if (kKeep) { obox += fabm; ebox += (long long)vz * (4 * V); }
+    }
   };
   for (int i = 0; i < n_iter; i += 2) {
     plane(i, tA, tB, uA, uB, hA, hB);
     if (i + 1 < n_iter) plane(i + 1, tB, tA, uB, uA, hB, hA);
   }
+#ifdef SGC_T2_DIAG
+  if (blockIdx.x == 5 && lane == 0 && V == 64 && !BND)
+    printf("T2DIAG warp %d planes %d total %lld tile_wait %lld barrier_wait %lld\n", warp, n_iter, clock64() - diag_t0, diag_tile, diag_bar);
+#endif
 }
 
 // edge strips of a level from its main blocks: xe[box][kz][s][y], s = columns 0, 1, V-2, V-1
