@@ -145,6 +145,13 @@ int sgc_layout_define(const int dlo[3], const int dhi[3], const int maxbox[3], i
 #define SGC_LOOP_TWO_STEP_BND 8     /* ... some faces have no motion item (physical boundary / trimmed)      */
 int sgc_step_loop_class(const int dlo[3], const int dhi[3], const int maxbox[3], int nghost,
                         unsigned periodic, unsigned trim, int nproc, int rank);
+/* The PILLARS the two-step sweep marches down for the same layout, exchange and rank (host only): pillars[0]
+ * pillars of pillars[1] boxes stacked in z, each box the LOCAL z neighbour of the one below it under this
+ * exchange (DisjointBoxLayout.cpp:104-139 orders boxes x-fastest, so box p + k * pillars[0] sits on top of
+ * box p + (k-1) * pillars[0]) and with the same in-plane neighbours present; pillars[1] = 1 (every box its own
+ * pillar) when the rank's boxes have no such structure.  Returns the step-loop mask of sgc_step_loop_class.  */
+int sgc_step_loop_pillars(const int dlo[3], const int dhi[3], const int maxbox[3], int nghost,
+                          unsigned periodic, unsigned trim, int nproc, int rank, int pillars[2]);
 
 int sgc_copier_define(const int dlo[3], const int dhi[3], const int maxbox[3], int nghost,
                       unsigned periodic, unsigned trim, int nproc, int rank,
@@ -353,6 +360,9 @@ int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsign
  * device fab along d, all 1 when the level runs as it is.  Decided on the first sgc_heat_run of >= 8 steps;
  * returns 1 once decided, 0 before.                                                                   */
 int sgc_plan_rebox_factors(sgc_plan_t plan, int factor[3]);
+/* Introspection: the pillar structure (see sgc_step_loop_pillars) the two-step passes of this plan's level use:
+ * pillars[0] pillars of pillars[1] boxes; {nbox, 1} when the level is swept box by box.  Returns 0.            */
+int sgc_plan_pillars(sgc_plan_t plan, int pillars[2]);
 
 /* ------------------------------------------------------------------ lattice Boltzmann ---- */
 

@@ -30,7 +30,7 @@ SYMBOLS = [
     "sgc_plan_create_exchange", "sgc_plan_create_items", "sgc_plan_destroy", "sgc_plan_num_items",
     "sgc_plan_num_remote_items", "sgc_plan_num_cells", "sgc_exchange", "sgc_exchange_begin", "sgc_exchange_end",
     "sgc_plan_create_bc_zero_gradient", "sgc_heat_sweep", "sgc_heat_sweep_range", "sgc_heat_sweep_ranges", "sgc_laplacian_apply",
-    "sgc_wave_step", "sgc_wave_run", "sgc_heat_run", "sgc_step_loop_class", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
+    "sgc_wave_step", "sgc_wave_run", "sgc_heat_run", "sgc_step_loop_class", "sgc_step_loop_pillars", "sgc_plan_pillars", "sgc_comm_unique_id", "sgc_comm_init", "sgc_comm_finalize", "sgc_comm_nproc",
     "sgc_comm_rank", "sgc_halo_describe", "sgc_stream_create", "sgc_stream_destroy", "sgc_stream_sync", "sgc_event_record_stream", "sgc_stream_wait_event",
     "sgc_level_upload_async", "sgc_level_download_async", "sgc_copyset_create", "sgc_copyset_run", "sgc_copyset_destroy",
     "sgc_copyset_num_cells", "sgc_level_valid_elems", "sgc_level_download_valid", "sgc_level_download_valid_async", "sgc_lb_collide", "sgc_lb_macroscopic", "sgc_lb_copy_ops", "sgc_lb_run", "sgc_lb_selftest_divconst",
@@ -98,6 +98,8 @@ def lib():
     L.sgc_layout_define.argtypes = [_i3, _i3, _i3, C.c_int, C.c_void_p, C.c_void_p, C.c_int, _i3]
     L.sgc_copier_define.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.sgc_step_loop_class.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int]
+    L.sgc_step_loop_pillars.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int * 2]
+    L.sgc_plan_pillars.argtypes = [C.c_void_p, C.c_int * 2]
     L.sgc_halo_describe.argtypes = [_i3, _i3, _i3, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_int), C.c_void_p, C.c_int]
     L.sgc_level_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -557,6 +559,12 @@ class Copier:
         decided = check(lib().sgc_plan_rebox_factors(self.h, f))
         return bool(decided), tuple(f)
 
+    def pillars(self):
+        """(npil, nbz): the two-step sweep marches down npil pillars of nbz boxes stacked in z"""
+        p = (C.c_int * 2)()
+        check(lib().sgc_plan_pillars(self.h, p))
+        return tuple(p)
+
     def _release(self):
         if self.h and _lib is not None:
             _lib.sgc_plan_destroy(self.h)
@@ -607,6 +615,16 @@ def step_loop_class(dlo, dhi, maxbox, nghost=1, periodic=7, trim=0, nproc=1, ran
     if r < 0:
         check(r)
     return r
+
+
+def step_loop_pillars(dlo, dhi, maxbox, nghost=1, periodic=7, trim=0, nproc=1, rank=0):
+    """(npil, nbz) of the two-step sweep's pillars for rank `rank`'s boxes of this layout and exchange (host only)."""
+    mb = (maxbox,) * 3 if np.isscalar(maxbox) else maxbox
+    p = (C.c_int * 2)()
+    r = lib().sgc_step_loop_pillars(_i3(*dlo), _i3(*dhi), _i3(*mb), nghost, periodic, trim, nproc, rank, p)
+    if r < 0:
+        check(r)
+    return tuple(p)
 
 
 def heat_run(a, b, copier, f, nstep, flags=SGC_FMA):

@@ -1094,6 +1094,7 @@ int sgc_plan_create_exchange_ex(sgc_level_t l, const int dlo[3], const int dhi[3
     p->t2_local = p->fusable && (loops & SGC_LOOP_TWO_STEP_LOCAL);
     p->t2_slab = p->fusable && (loops & SGC_LOOP_TWO_STEP_SLAB);
     p->t2_bnd = p->fusable && (loops & SGC_LOOP_TWO_STEP_BND);
+    pillar_structure(l->boxes, nbr, p->t2_npil, p->t2_nbz);
   }
   if (st) { sgc_plan_destroy(p); return st; }
   *plan = p;
@@ -1378,6 +1379,8 @@ static int run_t2_passes(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f
   for (int k = 0; k < npass && !st; ++k) {
     T2Args ra;
     memset(&ra, 0, sizeof ra);
+    ra.npil = plan->t2_npil;
+    ra.nbz = plan->t2_nbz;
     if (p2p) {
       const int li = (cur == S.lev[0]) ? 0 : (cur == S.lev[1] ? 1 : 2);       // 2: the plan's third level
       ra.rz = S.d_rz;
@@ -1504,6 +1507,14 @@ int sgc_plan_rebox_factors(sgc_plan_t p, int factor[3]) {
   if (!p || !factor) return fail(SGC_ERR_ARG, "sgc_plan_rebox_factors: null argument");
   for (int d = 0; d < 3; ++d) factor[d] = p->rebox.ok ? p->rebox.factor[d] : 1;
   return p->rebox.tried ? 1 : 0;
+}
+
+int sgc_plan_pillars(sgc_plan_t p, int pillars[2]) {
+  if (!p || !pillars) return fail(SGC_ERR_ARG, "sgc_plan_pillars: null argument");
+  const bool have = p->t2_npil > 0 && p->t2_nbz > 0;
+  pillars[0] = have ? p->t2_npil : p->nbox;
+  pillars[1] = have ? p->t2_nbz : 1;
+  return 0;
 }
 
 int sgc_heat_run(sgc_level_t a, sgc_level_t b, sgc_plan_t plan, double f, unsigned flags, int nstep, int* result_in_b) {

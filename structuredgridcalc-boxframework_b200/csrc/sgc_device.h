@@ -183,8 +183,9 @@ struct T2Args {
   const double* ghost[2];
   const double* peer_ghost[2][2];            // the same arenas on the z neighbours' GPUs, [peer slot][0/1]
   const int* nbr;             // [nbox][27], as PushArgs::nbr
-  int nplanes;                // nbox * (vz + 4) virtual planes
+  int nplanes;                // npil * (nbz * vz + 4) virtual planes
   int vz;                     // valid planes per box
+  int npil, nbz;              // pillars: boxes p + k * npil, k = 0 .. nbz-1, are stacked in z (nbz = 1: box by box)
   double f;
   // z neighbours in the neighbouring GPU's memory (z-slab partitions), as PushArgs
   const int* rz;
@@ -294,6 +295,7 @@ struct sgc_plan_s {
   bool t2_local = false, t2_slab = false;
   bool t2_bnd = false;                  // as t2_slab, but some faces have no motion item at all (physical boundary)
   int t2_agreed = -1;                   // multi-rank: every rank can run the two-step passes (-1: not asked yet)
+  int t2_npil = 0, t2_nbz = 1;          // pillar structure of the level's boxes under this plan (sgc::pillar_structure)
   // library-owned third level of the two-step passes (single rank): with it an ODD number of passes still ends in the
   // level the step-by-step schedule leaves the result in (a -> b -> scratch -> a), so a run of n steps is (n-2)/2
   // passes + the two plain steps instead of an even number of passes + up to three fused one-step sweeps

@@ -68,6 +68,12 @@ int build_exchange_items(const Grid& g, int ng, unsigned periodic, unsigned trim
 // by another rank), and returns a mask of SGC_LOOP_* bits (sgc_b200.h).
 int classify_step_loops(const std::vector<sgc_motion_item>& items, int nbox, int gidx0, std::vector<int>& nbr);
 
+// Pillars of the two-step sweep (host only).  The local boxes form npil pillars of nbz boxes — box p + k * npil sits
+// exactly on top of box p + (k-1) * npil, both are each other's LOCAL z neighbour in `nbr` (so the plan exchanges
+// that face), and every box of a pillar has the same in-plane neighbours present / missing — or else nbz = 1 and
+// npil = nbox (every box its own pillar).  `boxes` are the valid boxes in local order.
+void pillar_structure(const std::vector<IBox>& boxes, const std::vector<int>& nbr, int& npil, int& nbz);
+
 void set_error(const std::string& msg);
 int fail(int status, const std::string& msg);
 

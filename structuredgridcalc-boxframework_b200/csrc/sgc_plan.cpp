@@ -171,6 +171,30 @@ int classify_step_loops(const std::vector<sgc_motion_item>& items, int nbox, int
   return mask;
 }
 
+void pillar_structure(const std::vector<IBox>& boxes, const std::vector<int>& nbr, int& npil, int& nbz) {
+  const int nbox = (int)boxes.size();
+  npil = nbox;
+  nbz = 1;
+  if (nbox < 2 || nbr.size() != (size_t)nbox * 27) return;
+  // candidate: the boxes of the lowest layer come first (the layout's x-fastest order)
+  int n = 0;
+  while (n < nbox && boxes[n].lo[2] == boxes[0].lo[2]) ++n;
+  if (n == nbox || nbox % n != 0) return;
+  const int vz = boxes[0].ext(2);
+  for (int b = n; b < nbox; ++b) {
+    const IBox &up = boxes[b], &dn = boxes[b - n];
+    if (up.lo[0] != dn.lo[0] || up.lo[1] != dn.lo[1] || up.hi[0] != dn.hi[0] || up.hi[1] != dn.hi[1]) return;
+    if (up.lo[2] != dn.lo[2] + vz || up.ext(2) != vz || dn.ext(2) != vz) return;
+    if (nbr[(size_t)b * 27 + 4] != b - n || nbr[(size_t)(b - n) * 27 + 22] != b) return;      // the shared face is exchanged, locally
+    for (int code = 9; code < 18; ++code) {                                                     // the in-plane directions
+      if (code == 13) continue;
+      if ((nbr[(size_t)b * 27 + code] < 0) != (nbr[(size_t)(b - n) * 27 + code] < 0)) return;
+    }
+  }
+  npil = n;
+  nbz = nbox / n;
+}
+
 }  // namespace sgc
 
 extern "C" {
@@ -216,6 +240,22 @@ int sgc_step_loop_class(const int dlo[3], const int dhi[3], const int maxbox[3],
   if (st) return st;
   std::vector<int> nbr;
   return sgc::classify_step_loops(v, g.bpp, rank * g.bpp, nbr);
+}
+
+int sgc_step_loop_pillars(const int dlo[3], const int dhi[3], const int maxbox[3], int nghost, unsigned periodic,
+                          unsigned trim, int nproc, int rank, int pillars[2]) {
+  if (!dlo || !dhi || !maxbox || !pillars) return sgc::fail(SGC_ERR_ARG, "sgc_step_loop_pillars: null argument");
+  sgc::Grid g(dlo, dhi, maxbox, nproc);
+  if (g.status) return sgc::fail(SGC_ERR_ARG, "sgc_step_loop_pillars: boxes must tile the domain and divide among ranks");
+  std::vector<sgc_motion_item> v;
+  const int st = sgc::build_exchange_items(g, nghost, periodic, trim, rank, v);
+  if (st) return st;
+  std::vector<int> nbr;
+  const int mask = sgc::classify_step_loops(v, g.bpp, rank * g.bpp, nbr);
+  std::vector<sgc::IBox> boxes(g.bpp);
+  for (int b = 0; b < g.bpp; ++b) boxes[b] = g.box(rank * g.bpp + b);
+  sgc::pillar_structure(boxes, nbr, pillars[0], pillars[1]);
+  return mask;
 }
 
 }  // extern "C"

@@ -116,7 +116,16 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   uint64_t* full = reinterpret_cast<uint64_t*>(t1 + 2 * T1SZ);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int vz = a.vz, VP = vz + 4;
+  // PILLARS.  Boxes stacked in z whose faces towards each other are ordinary local neighbours form a pillar
+  // (box p + k * npil, k = 0 .. nbz-1 from the bottom; the host checks the structure, launch_heat_t2).  The march
+  // runs down a whole pillar: HC = nbz * vz planes + the two halo planes above and below, so the tiles of a box's
+  // halo planes — which ARE its z neighbour's outermost planes — are read and swept once per pillar, not once
+  // per box (512^3 in 64^3 boxes: 516 tiles per pillar instead of 8 x 68).  nbz = 1 is the box-by-box march.
+  // Only the periodic 64^2 instance has the registers for it (kPil; the boundary instance spills 52 bytes with
+  // it and runs 9 % slower than box by box); the others are launched with nbz = 1.
+  constexpr bool kPil = V >= 64 && !BND;
+  const int vz = a.vz, npil = a.npil, nbz = kPil ? a.nbz : 1, HC = nbz * vz, VP = HC + 4;
+  const int topoff = (nbz - 1) * npil;                   // top box of pillar p = p + topoff
   const long long fabm = (long long)FABP * (vz + 2);
   // ranges start on even virtual planes (vz is even: heat_t2_covers), which makes the parity of a plane's
   // t+1 buffer the parity of the loop counter
@@ -153,23 +162,21 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
   // S = source box of the current tiles (bit 30 remote, 29 peer slot, 28 z face missing), N = this role's
   // neighbour of S (BND: -1 = missing), ct = BND corner role: where the lane's corner cell comes from
   int Sa = -1, Na = 0, cta = 0, Sb = -1, Nb = 0, ctb = 0;
-#ifdef SGC_T2_RUNSRC
-  // periodic 64^2 instance: a role's source address of the previous tile; inside a source box consecutive tiles lie
-  // one fab plane (one strip plane) apart, so only the tiles where the source box changes form it from scratch
-  constexpr bool kRunSrc = !BND && V >= 64;
-#else
-  constexpr bool kRunSrc = false;
-#endif
-  const double* Ra = nullptr;
-  const double* Rb = nullptr;
+  int Ka = 0, Kb = 0;                 // plane (valid index) of the role's source box the previous tile came from
   unsigned waited = 0;                // bit per peer slot
-  auto issue = [&](int slot, int tbox, int tl, const int role, int& S, int& N, int& ct, const double*& R) {   // tile = virtual plane tl of box tbox
-    const int z = vz + 1 - tl;                             // the march goes down
-    const int cls = z < 0 ? 0 : (z >= vz ? 2 : 1);
-    const bool fresh = S < 0 || tl == 0 || tl == 2 || tl == vz + 2;
-    if (fresh) {    // first tile, or the source box changes here
-      if (cls == 1) S = tbox;
-      else {
+  auto issue = [&](int slot, int tpil, int tl, const int role, int& S, int& N, int& ct, int& K) {   // tile = virtual plane tl of pillar tpil
+    const int h = HC + 1 - tl;                             // plane of the pillar, from its bottom; the march goes down
+    const int cls = h < 0 ? 0 : (h >= HC ? 2 : 1);         // below the pillar / inside / above
+    // first tile, or the source box changes here (kPil: the previous tile was its plane 0)
+    const bool fresh = S < 0 || tl == 0 || (kPil ? K <= 0 : (tl == 2 || tl == vz + 2));
+    if (!kPil) K = cls == 0 ? h + vz : (cls == 2 ? h - vz : h);
+    if (fresh) {
+      if (cls == 1) {
+        if (kPil) { const int kb = h / vz; K = h - kb * vz; S = tpil + kb * npil; }
+        else S = tpil;
+      } else {
+        const int tbox = cls == 0 ? tpil : tpil + topoff;  // the pillar's bottom / top box
+        if (kPil) K = cls == 0 ? h + vz : h - HC;
         S = __ldg(a.nbr + (size_t)tbox * 27 + (cls == 0 ? 4 : 22));
         if (S < 0) {
           const int rr = a.rz ? __ldg(a.rz + 2 * tbox + (cls == 0 ? 0 : 1)) : -1;
@@ -203,9 +210,9 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
         else if (Y >= 0) { N = Y; ct = 2; }                  // x face missing: the y neighbour's ghost column
         else { N = 0; ct = 3; }                              // neither flank is computed: not needed
       }
-    }
+    } else if (kPil) --K;
     const bool zmiss = BND && (S & 0x10000000);
-    const int kz = cls == 0 ? z + vz : (cls == 2 ? z - vz : z);           // plane of the source box (valid index)
+    const int kz = K;                                               // plane of the source box (valid index)
     // fab plane the tile is read from; a missing z face: the lower / upper GHOST plane of the box and of its
     // in-plane neighbours (whose cells on that plane are the z neighbours of the flank cells), taken from
     // the level-t ghosts for the inner halo plane and from the level-t+1 ghosts for the outer one
@@ -216,19 +223,12 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
     // BND: the levels whose ghost cells are level t (g0) and level t+1 (g1), on the GPU that owns S
     const double* g0 = !BND ? nullptr : (!rem ? a.ghost[0] : a.peer_ghost[ps1 ? 1 : 0][0]);
     const double* g1 = !BND ? nullptr : (!rem ? a.ghost[1] : a.peer_ghost[ps1 ? 1 : 0][1]);
-    const double* base = zmiss ? ((tl == 1 || tl == vz + 2) ? g0 : g1)
+    const double* base = zmiss ? ((tl == 1 || tl == HC + 2) ? g0 : g1)
                                : (!rem ? a.in_level : (ps1 ? a.peer_in[1] : a.peer_in[0]));
-    if (kRunSrc) {
-      if (fresh) {
-        if (role == 3 || role == 4) R = base + a.xe_in + ((long long)N * vz + kz) * (4 * V) + (role == 3 ? 2 * V : 0);
-        else R = base + N * fabm + prow + (role == 1 ? (V - 2) * V : 0) +
-                 (role == 5 ? ((lane & 2) ? 0 : V - 1) * V + ((lane & 1) ? 0 : V - 1) : 0);
-      } else R -= (role == 3 || role == 4) ? 4 * V : FABP;
-    }
     if (role == 5) {
       if (lane < 4) {
         const bool xh = lane & 1, yh = lane & 2;
-        const double* src = kRunSrc ? R : base + N * fabm + prow + (long long)(yh ? 0 : V - 1) * V + (xh ? 0 : V - 1);
+        const double* src = base + N * fabm + prow + (long long)(yh ? 0 : V - 1) * V + (xh ? 0 : V - 1);
         if (BND && ct == 1) src = g0 + N * fabm + ((long long)fp * N1 + (yh ? N1 - 1 : 0)) * V + (xh ? 0 : V - 1);
         if (BND && ct == 2)
           src = g0 + a.xg_base + (long long)N * (2 * N1 * (vz + 2)) + ((long long)((xh ? 1 : 0) * (vz + 2) + fp)) * N1 + 1 +
@@ -269,13 +269,13 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
       if (role == 0) {
         if (BND) mbar_expect_tx(full + slot, V * V * 8u);
         else mbar_expect_tx(full + slot, TILE_BYTES);             // this warp's arrival + the tile's byte count
-        bulk_g2s(dst + 2 * V, kRunSrc ? R : base + N * fabm + prow, V * V * 8u, full + slot);             // rows 0..V-1
+        bulk_g2s(dst + 2 * V, base + N * fabm + prow, V * V * 8u, full + slot);                           // rows 0..V-1
       } else if (role == 1 || role == 2) {
         const bool hi = role == 2;
         if (BND) mbar_expect_tx_only(full + slot, 2 * V * 8u);
         if (!BND || N >= 0) {
-          if (!hi) bulk_g2s(dst, kRunSrc ? R : base + N * fabm + prow + (long long)(V - 2) * V, 2 * V * 8u, full + slot);   // rows -2,-1
-          else bulk_g2s(dst + (V + 2) * V, kRunSrc ? R : base + N * fabm + prow, 2 * V * 8u, full + slot);    // rows V,V+1
+          if (!hi) bulk_g2s(dst, base + N * fabm + prow + (long long)(V - 2) * V, 2 * V * 8u, full + slot);   // rows -2,-1
+          else bulk_g2s(dst + (V + 2) * V, base + N * fabm + prow, 2 * V * 8u, full + slot);                  // rows V,V+1
         } else {
           // no y neighbour: the ghost row of S in the level-t ghosts, and the level-t+1 ghosts in the outer row
           const long long ro = (long long)(S & 0x0fffffff) * fabm + ((long long)fp * N1 + (hi ? N1 - 1 : 0)) * V;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
           bulk_g2s(dst + (hi ? (V + 3) * V : 0), g1 + ro, V * 8u, full + slot);
         }
       } else {
-        const double* e = kRunSrc ? R - (role == 3 ? 2 * V : 0) : base + a.xe_in + ((long long)N * vz + kz) * (4 * V);
+        const double* e = base + a.xe_in + ((long long)N * vz + kz) * (4 * V);
         if (role == 3) {
           bulk_g2s(dst + E(0), e + 2 * V, V * 8u, full + slot);     // x = -2  <- x neighbour's column V-2
           bulk_g2s(dst + E(1), e + 3 * V, V * 8u, full + slot);     // x = -1  <- column V-1
@@ -296,9 +296,9 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
     }
   };
   // a warp's role(s) for one tile
-  auto issue_roles = [&](int slot, int tbox, int tl) {
-    if (warp < NROLE) issue(slot, tbox, tl, warp, Sa, Na, cta, Ra);
-    if (NCW < NROLE && warp + NCW < NROLE) issue(slot, tbox, tl, warp + NCW, Sb, Nb, ctb, Rb);
+  auto issue_roles = [&](int slot, int tpil, int tl) {
+    if (warp < NROLE) issue(slot, tpil, tl, warp, Sa, Na, cta, Ka);
+    if (NCW < NROLE && warp + NCW < NROLE) issue(slot, tpil, tl, warp + NCW, Sb, Nb, ctb, Kb);
   };
   {
     const int b0 = l_begin / VP, l0 = l_begin - b0 * VP;
@@ -351,11 +351,19 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
 #pragma unroll
   for (int m = 0; m < CPT; ++m) tA[m] = tB[m] = uA[m] = uB[m] = 0.0;
   const double f = a.f;
-  int box = l_begin / VP, l = l_begin - box * VP;
-  // kKeep: running bases of the current box in the output level (its main block / its edge strips, at this
-  // thread's column and first row), advanced when the box changes instead of multiplied out of the box index
-  double* obox = a.out_level + (kKeep ? box * fabm + (oC0 + (N1 - 1) * V) : 0);
-  double* ebox = a.out_level + a.xe_out + (kKeep ? (long long)box * vz * (4 * V) + (oC0 / V - 2) : 0);
+  int pil = l_begin / VP, l = l_begin - pil * VP;
+  // the plane stage 2 writes, two virtual planes behind the arriving tile: plane okz of box obx (for l < 4, where
+  // nothing is written yet, okz >= vz counts down towards the top box's last plane), stepped at the end of a plane
+  int obx_run = 0, okz_run = 0;       // kPil only; a box-by-box march derives them from (pil, l)
+  if (kPil) {
+    const int ho = HC + 3 - l, kb = ho / vz < nbz - 1 ? ho / vz : nbz - 1;
+    obx_run = pil + kb * npil;
+    okz_run = ho - kb * vz;
+  }
+  // kKeep: running bases of that box in the output level (its main block / its edge strips, at this thread's
+  // column and first row), advanced when the box changes instead of multiplied out of the box index
+  double* obox = a.out_level + (kKeep ? (kPil ? obx_run : pil) * fabm + (oC0 + (N1 - 1) * V) : 0);
+  double* ebox = a.out_level + a.xe_out + (kKeep ? (long long)(kPil ? obx_run : pil) * vz * (4 * V) + (oC0 / V - 2) : 0);
   const int n_iter = s_end - l_begin, lead = s_begin - l_begin;
 
   // One plane: tile i arrives as the plane BELOW stage 1's.  X = level t at the previous plane (centre of
@@ -381,7 +389,7 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
     __syncthreads();                 // t+1 buffer hand-over; every warp has left tile i-2 and t+1 plane i-3
 #endif
     const bool more = i + 2 < n_iter;
-    if (more) issue_roles((i + 2) & (NS - 1), l + 2 >= VP ? box + 1 : box, l + 2 >= VP ? l + 2 - VP : l + 2);
+    if (more) issue_roles((i + 2) & (NS - 1), l + 2 >= VP ? pil + 1 : pil, l + 2 >= VP ? l + 2 - VP : l + 2);
     const double* __restrict__ C = ring + (size_t)slot * SLOT;
     const double* __restrict__ P = ring + (size_t)((i + NS - 1) & (NS - 1)) * SLOT;
     const bool do1 = (l >= 2) && (i >= 2);
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
           // brought in the slot of the outer halo layer
           const int code = side == 0 ? 12 : (side == 1 ? 14 : (side == 2 ? 10 : 16));
           const int alt = side == 0 ? E(0) + p : (side == 1 ? E(3) + p : (side == 2 ? p : (V + 3) * V + p));
-          if (__ldg(a.nbr + (size_t)box * 27 + code) < 0) r = P[alt];
+          if (__ldg(a.nbr + (size_t)pil * 27 + code) < 0) r = P[alt];        // the same for every box of a pillar (host-checked)
         }
         Tw[hc] = r;
       }
@@ -415,23 +423,24 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
       // output plane inside the fab's valid region.  While the stages are being primed (do2 false) the
       // stage-2 values are meaningless: they go to a scratch plane and a spare strip plane behind the edge
       // strips, which keeps the stores free of branches.
-      const int kz = vz + 3 - l;                                  // output plane: two virtual planes behind the arriving tile
-      // (xi, y0) of fab plane kz: fab-relative offset = tile offset + (N1 - 1) * V
+      const int obx = kPil ? obx_run : pil, okz = kPil ? okz_run : vz + 3 - l;
+      // (xi, y0) of fab plane okz: fab-relative offset = tile offset + (N1 - 1) * V
       double* __restrict__ po =
-          do2 ? (kKeep ? obox + (long long)kz * FABP : obox + box * fabm + (long long)kz * FABP + (oC0 + (N1 - 1) * V))
+          do2 ? (kKeep ? obox + (long long)okz * FABP : obox + obx * fabm + (long long)okz * FABP + (oC0 + (N1 - 1) * V))
               : a.out_level + a.dump + (oC0 - 2 * V);
-      // BND: a missing z face: level t+1 on the ghost plane above / below the box is not computed but is the
+      // BND: a missing z face: level t+1 on the ghost plane above / below the pillar is not computed but is the
       // ghost plane of the level-t+1 ghosts, which arrived as the tile of the outer halo plane: it sits in
-      // Y (plane z = vz+1, read two planes ago: l == 2) resp. in the arriving tile (plane z = -2: l == vz+3)
+      // Y (plane HC+1, read two planes ago: l == 2) resp. in the arriving tile (plane -2: l == HC+3)
       bool ovr_held = false, ovr_arriving = false;
-      if (BND && (l == 2 || l == vz + 3)) {
-        const bool top = l == 2;                                  // the march starts above the box
-        const bool miss = __ldg(a.nbr + (size_t)box * 27 + (top ? 22 : 4)) < 0 && !(a.rz && __ldg(a.rz + 2 * box + (top ? 1 : 0)) >= 0);
+      if (BND && (l == 2 || l == HC + 3)) {
+        const bool top = l == 2;                                  // the march starts above the pillar
+        const int ebx = top ? pil + topoff : pil;                 // the pillar's top / bottom box
+        const bool miss = __ldg(a.nbr + (size_t)ebx * 27 + (top ? 22 : 4)) < 0 && !(a.rz && __ldg(a.rz + 2 * ebx + (top ? 1 : 0)) >= 0);
         ovr_held = miss && top; ovr_arriving = miss && !top;
       }
       // edge strips of the output plane: strip xs of this thread's column, if it is one of the four
       double* __restrict__ pe =
-          (do2 ? (kKeep ? ebox + (long long)kz * (4 * V) : ebox + ((long long)box * vz + kz) * (4 * V) + (oC0 / V - 2))
+          (do2 ? (kKeep ? ebox + (long long)okz * (4 * V) : ebox + ((long long)obx * vz + okz) * (4 * V) + (oC0 / V - 2))
                : a.out_level + a.xe_out + a.xe_spare_plane * (4 * V) + (oC0 / V - 2)) + (xs < 0 ? 0 : xs) * V;
       const double yfirst = P[oC0 - V], ylast = P[oC0 + CPT * V];
       const double yfirst1 = Tr[oC0 - V], ylast1 = Tr[oC0 + CPT * V];
@@ -469,9 +478,13 @@ __global__ void __launch_bounds__(NCW * 32, t2_ctas_per_sm(V)) k_heat_t2(T2Args 
         if (m & 1) { if (xs >= 0) *reinterpret_cast<double2*>(pe + m - 1) = make_double2(oprev, o); } else oprev = o;
       }
     }
-    if (++l == VP) {
-      l = 0; ++box;
-      if (kKeep) { obox += fabm; ebox += (long long)vz * (4 * V); }
+    if (++l == VP) {                       // next pillar: from the bottom box of this one to the top box of the next
+      l = 0; ++pil;
+      if (kPil) { okz_run = vz + 3; obx_run += topoff + 1; }
+      if (kKeep) { obox += (topoff + 1) * fabm; ebox += (long long)(topoff + 1) * vz * (4 * V); }
+    } else if (kPil && --okz_run < 0) {    // the box below in the same pillar
+      okz_run = vz - 1; obx_run -= npil;
+      if (kKeep) { obox -= npil * fabm; ebox -= (long long)npil * vz * (4 * V); }
     }
   };
   for (int i = 0; i < n_iter; i += 2) {
@@ -563,7 +576,12 @@ int launch_heat_t2(sgc_level_s* unew, sgc_level_s* u, double f, int fma, const i
   a.xe_out = unew->xe_base;
   a.nbr = d_nbr;
   a.vz = g.vn[2];
-  const long long np = (long long)u->nbox * (g.vn[2] + 4);
+  // pillars (plan->t2_npil / t2_nbz through `remote`); none given, or SGC_T2_NO_PILLARS: every box its own pillar
+  if (a.npil <= 0 || a.nbz <= 0 || a.npil * a.nbz != u->nbox || g.vn[0] != 64 || a.ghost[0] || getenv("SGC_T2_NO_PILLARS")) {
+    a.npil = u->nbox;
+    a.nbz = 1;
+  }
+  const long long np = (long long)a.npil * ((long long)a.nbz * g.vn[2] + 4);
   if (np > 0x7fffffffLL) return 1;
   a.nplanes = (int)np;
   a.xe_spare_plane = (long long)u->nbox * g.vn[2];
