@@ -1005,7 +1005,7 @@ def main():
                 "parity": parity, "parity_nranks": par_n, "unfused": unfused, "configs": configs,
                 "clocks": clocks, "gpu_launches": int(launches), "device": name, "sm_count": sms,
                 "plan_build_ms": plan_ms, "motion_items": cp.numMotionItem(), "remote_items": cp.numRemoteItem(),
-                "rebox_factors": list(cp.reboxFactors()[1]), "sum_conserved": bool(conserved)}
+                "rebox_factors": list(cp.reboxFactors()[1]), "pillars": list(cp.pillars()), "sum_conserved": bool(conserved)}
         emit(line)
         if par_n is not None and not par_n["ok"]:
             raise SystemExit("PARITY FAILURE at N = %d: %r" % (world, par_n))

@@ -86,7 +86,7 @@ def launch_share(path, lines, title):
 
 def main():
     lines = ["Round 2 — ncu summaries (B200, sm_100a, --clock-control none).  Produced by profiles/micro/r02_summarise.py from",
-             "the captures of profiles/micro/r02_ncu.sh; per-launch times under ncu are cold-cache and serialised: the kernel's",
+             "the captures of profiles/micro/r02_ncu.sh (copy / one-step kernels) and r02_ncu_t2.sh (two-step sweep after the pillar march, launch lists); per-launch times under ncu are cold-cache and serialised: the kernel's",
              "SHARE of the step is what must agree with bench.py, not the absolute."]
     traffic = {}
     tp = os.path.join(OUT, "traffic.json")
@@ -105,7 +105,7 @@ def main():
                 o.write(open(p).read())
     with open(os.path.join(OUT, "r02_ncu_summary.txt"), "w") as o:
         o.write("\n".join(lines) + "\n")
-    traffic["source"] = "ncu --set full, one launch each, profiles/micro/r02_ncu.sh (round 2); t2/sweep on the 512^3/64^3 level"
+    traffic["source"] = "ncu --set full, one launch each, profiles/micro/r02_ncu.sh + r02_ncu_t2.sh (round 2); t2/sweep on the 512^3/64^3 level"
     json.dump(traffic, open(tp, "w"), indent=1)
     print("\n".join(lines))
 

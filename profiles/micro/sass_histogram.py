@@ -12,8 +12,7 @@ WANT = (("k_heat_t2<64, NS 4, 16 warps, fma, periodic>", "k_heat_t2ILi64ELi4ELi1
         ("k_heat_stream<64,64, PS 1, NS 6, 16 warps, double> (plain one-step sweep)", "k_heat_streamILi64ELi64ELi1ELi1ELi6ELi16ELi0ELb0ELi0ELb0Ed"),
         ("k_heat_stream<64,64, PS 2, NS 6, 16 warps, float>", "k_heat_streamILi64ELi64ELi1ELi2ELi6ELi16ELi0ELb0ELi0ELb0Ef"),
         ("k_heat_stream<64,64, ..., fused ghost fill (pull y/z, push x)>", "k_heat_streamILi64ELi64ELi1ELi1ELi6ELi16ELi0ELb1ELi0ELb0Ed"),
-        ("k_copy_items<u64, variant 1> (single-item chunks, batched 16-byte loads)", "k_copy_itemsImLi1"),
-        ("k_copy_items<u64, variant 0> (per-unit decode)", "k_copy_itemsImLi0"),
+        ("k_copy_items<u64> (batched region copy: exchange, pack / unpack, BaseFab::copy, BC)", "k_copy_itemsImEE"),
         ("k_sweep7<double, LapOp> (laplacian driver, C1)", "k_sweep7IdNS_5LapOpIdEELi1"))
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
