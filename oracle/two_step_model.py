@@ -7,6 +7,10 @@ steps of the oracle (LevelData.H:455-566 + the sweep loop): the claim behind the
 a box needs can be recomputed from valid cells and static ghosts, bit for bit — holds on the CPU too.
 
 Arithmetic: the reference loop's association without contraction (oracle contract = 0).
+
+What the model leaves out on purpose, because it changes no value: the ORDER in which the kernel visits planes
+(it marches down pillars of z-stacked boxes and reads the planes two boxes share once) and its form
+fma(-2, u, u[+e]) of (u[+e] - 2u), which is exact (tests/test_two_step_model.py::test_fma_form_of_the_update_is_exact).
 """
 import numpy as np
 

@@ -63,3 +63,34 @@ def test_two_step_pass_uses_each_levels_own_static_ghosts(oracle):
     wa = M.split(a, boxes)
     for k in range(len(boxes)):
         assert np.array_equal(got[k], wa[k][1:7, 1:9, 1:9]), k
+
+
+def test_fma_form_of_the_update_is_exact():
+    """csrc/sgc_stream2.cu forms the reference's (u[+e] - 2u) as ONE fma(-2, u, u[+e]) (heat_zhalf / heat_finish): 2u is
+    exact in binary floating point, so both round the same real number once.  Checked on random doubles over the
+    whole exponent range, on subnormals and on cancelling operands; the only inputs on which the two forms differ
+    are those where 2u overflows (|u| >= 2^1023), which no heat field reaches."""
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.fma.restype = ctypes.c_double
+    libm.fma.argtypes = [ctypes.c_double] * 3
+    rng = np.random.default_rng(11)
+    n = 20000
+    mant = rng.uniform(1.0, 2.0, (2, n)) * rng.choice([-1.0, 1.0], (2, n))
+    e_u = rng.integers(-1070, 1020, n)
+    # the neighbour within a few binades of u (where cancellation and rounding matter) or anywhere
+    e_p = np.where(rng.random(n) < 0.7, e_u + rng.integers(-3, 4, n), rng.integers(-1070, 1020, n))
+    u = np.ldexp(mant[0], e_u)
+    p = np.ldexp(mant[1], np.clip(e_p, -1074, 1023))
+    cases = list(zip(u, p))
+    cases += [(5e-324, 1e-323), (-5e-324, 5e-324), (2.2250738585072014e-308, 4.4501477170144023e-308), (1.0, 2.0), (1.0, 2.0000000000000004),
+              (0.1, 0.2), (1e308 / 4, 1e308), (-0.0, 0.0), (0.0, -0.0), (3.0, 6.000000000000001)]
+    for uu, pp in cases:
+        ref = np.float64(pp) - np.float64(2.0) * np.float64(uu)          # the reference: multiply, then subtract
+        got = libm.fma(-2.0, float(uu), float(pp))
+        assert ref == got and np.signbit(ref) == np.signbit(got), (uu, pp, ref, got)
+    # and the documented exception
+    big = 1.5 * 2.0 ** 1023
+    with np.errstate(over="ignore", invalid="ignore"):
+        assert not np.isfinite(np.float64(big) - np.float64(2.0) * np.float64(big)) and np.isfinite(libm.fma(-2.0, big, big))
