@@ -9,15 +9,17 @@
 // neighbouring boxes — is recomputed with the same operations in the same order from the same
 // inputs.
 //
-// Per box the CTA marches DOWN along z through VZ+4 "virtual planes" l = 0 .. VZ+3, i.e. z = VZ+1 .. -2 (why
-// downwards: see heat_zhalf below).  For every virtual
+// The CTA marches DOWN a PILLAR of z-stacked boxes (HC = nbz * VZ planes; nbz = 1: a single box) through HC+4
+// "virtual planes" l = 0 .. HC+3, i.e. z = HC+1 .. -2 counted from the pillar's bottom (why downwards: see
+// heat_zhalf below; why pillars: the halo planes of a box ARE its z neighbour's outermost planes, and a pillar
+// reads and sweeps them once).  For every virtual
 // plane a TILE of level t is assembled in a ring slot — entirely from VALID cells (ghost cells are
 // not read where a neighbour exists, so no exchange is needed between the two steps or between passes):
 //     rows y = -2..V+1 of the V valid columns      (own valid rows + 2 rows of each y neighbour)
 //     x strips x = -2,-1,V,V+1 for y = 0..V-1      (the x neighbours' EDGE STRIPS, see below)
 //     the 4 corner cells (-1|V, -1|V)              (the xy-diagonal neighbours; 8-byte cp.async)
-//   planes z < 0 / z >= VZ are the same tile of the z neighbour (a local fab or, on a z-slab
-//   partition, a fab in the neighbouring GPU's memory over NVLink, gated by its progress counter).
+//   planes z < 0 / z >= HC are the same tile of the z neighbour of the pillar's bottom / top box (a local fab
+//   or, on a z-slab partition, a fab in the neighbouring GPU's memory over NVLink, gated by its progress counter).
 //   Faces WITHOUT a neighbour (physical boundaries; template flag BND) read the box's own, never
 //   exchanged ghost cells instead — see the comment at the producer roles.
 // All NCW warps are consumers (thread = one x and CPT consecutive rows, all state in registers);
@@ -34,14 +36,15 @@
 // fetch one 32-byte sector per 8-byte value; the strips make the x halo dense.
 //
 // HBM traffic per plane pass (V = 64): 36.9 KB tile + 32 KB rows + 2 KB strips for TWO cell-updates
-// of 4096 cells = 8.7 B per cell-update (x (VZ+4)/VZ for the z overlap; ncu: 9.1 B) against 16.8 B
+// of 4096 cells = 8.7 B per cell-update (x (HC+4)/HC for the halo planes of a pillar; ncu: 8.8 B) against 16.8 B
 // for the one-step sweep; the algorithmic figure stays 16 B per cell-update.
 //
 // Instances: V = 64 (16 warps, 8 rows per thread, one CTA per SM), V = 32 (8 warps, 4 rows per thread, three
 // CTAs per SM) and, on request only, V = 16 (4 warps, 2 rows per thread: slower than the one-step sweep).
-// The V = 64 kernel uses the whole register file (128 x 512) without spilling and is bound by dependency latency
-// (FP64 chains, shared-memory loads, the per-plane barrier) with four warps per scheduler, not by HBM; its speed
-// is sensitive to anything that costs a register or lengthens the serial path from the barrier to the first row
+// The V = 64 kernel uses the whole register file (128 x 512) without spilling; with four warps per scheduler its
+// dependency latency (FP64 chains, shared-memory loads, the per-plane barrier) and its HBM traffic (2.35 GB per
+// launch at 0.87-0.89 of the measured copy bandwidth) are in balance.  Its speed is sensitive to anything that
+// costs a register or lengthens the serial path from the barrier to the first row
 // (DESIGN.md §4.1d has the history; profiles/micro/ab_t2_round2b.sh times variants on one GPU).
 #include <cstdint>
 #include <cstdio>
