@@ -485,6 +485,46 @@ def test_two_step_sweep_matches_oracle_and_step_by_step(g, oracle, monkeypatch):
                               oracle.gather(dlo, dhi, dbl.boxes, 1, 1, 0, want)), (dhi, mb, per, "vs oracle")
 
 
+def test_two_step_sweep_marches_down_pillars(g, oracle, monkeypatch):
+    """The two-step kernel marches down PILLARS of z-stacked boxes (sgc_plan.cpp: pillar_structure; halo planes two
+    boxes share are read and swept once).  The plan reports the structure; with the pillars switched off
+    (SGC_T2_NO_PILLARS: box by box, the round-1 traversal) BOTH levels come out with the same bits, ghost cells
+    included; and the valid cells equal the oracle's step-by-step run.  Pillars of 3 boxes whose top box wraps onto
+    their own bottom box, 2 x 2 pillars of 2, flat boxes in pillars of 4, odd and even pass counts."""
+    cases = [((0, 0, 0), (63, 63, 191), (64, 64, 64), 7, 0.2, 9, (1, 3)),
+             ((0, 0, 0), (127, 127, 127), (64, 64, 64), 7, 0.125, 12, (4, 2)),
+             ((0, 0, 0), (63, 127, 31), (64, 64, 8), 7, 0.3, 11, (2, 4)),
+             ((0, 0, 0), (127, 63, 127), (64, 64, 64), 3, 0.2, 8, (2, 2))]     # physical z ends: the boundary instance marches box by box
+    rng = np.random.default_rng(31)
+    for dlo, dhi, mb, per, f, nstep, want_pillars in cases:
+        dbl, a = make_level(g, dlo, dhi, mb, 1, 1)
+        b = g.LevelData(dbl, 1, 1)
+        u0 = rng.standard_normal(a.elems)
+        cp = g.Copier().defineExchangeLD(a, per, 0)
+        assert cp.pillars() == want_pillars, (dhi, mb, cp.pillars())
+        outs = []
+        for off in (False, True):
+            if off:
+                monkeypatch.setenv("SGC_T2_NO_PILLARS", "1")
+            else:
+                monkeypatch.delenv("SGC_T2_NO_PILLARS", raising=False)
+            a.upload(u0); b.upload(u0)
+            g.profile_enable(True)
+            g.profile_read(2)
+            res = g.heat_run(a, b, cp, f, nstep)
+            n2, _ = g.profile_read(2)
+            g.profile_enable(False)
+            assert n2 == t2_passes(nstep) and (res is b) == bool(nstep & 1)
+            outs.append((a.download(), b.download()))
+        monkeypatch.delenv("SGC_T2_NO_PILLARS", raising=False)
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), (dhi, mb, "pillars vs box by box")
+        want = u0.copy()
+        oracle.level_heat(dlo, dhi, mb, 1, per, 0, f, nstep, want, 1)
+        got = outs[0][1] if nstep & 1 else outs[0][0]
+        assert np.array_equal(oracle.gather(dlo, dhi, dbl.boxes, 1, 1, 0, got),
+                              oracle.gather(dlo, dhi, dbl.boxes, 1, 1, 0, want)), (dhi, mb, per, "vs oracle")
+
+
 def test_two_step_sweep_physical_boundary_and_fallback(g, oracle):
     """Non-periodic z: boxes at the domain boundary have no z neighbour; the two-step kernel's boundary
     instance reads the (never exchanged) ghost planes instead — every cell of the result, ghost cells
