@@ -215,6 +215,7 @@ def test_committed_bench_line_follows_the_contract():
     c3, c1 = j["configs"]["C3"], j["configs"]["C1"]
     assert c3["parity"]["ok"] is True and c3["value"] >= 350.0 and c3["motion_items"] == 851968
     assert c3["rebox_factors"] == [4, 4, 4]
+    assert j["pillars"] == [64, 8]            # the two-step sweep marched down 8 x 8 pillars of 8 boxes
     assert c1["parity"]["ok"] is True and c1["parity"]["linear_field_B_is_zero"] is True and c1["gpu_launches_per_step"] == 16
     u = j["unfused"]
     assert u["exchange_x_faces_from_edge_strips"] is True and u["exchange_ms_per_sweep"] < 0.1
